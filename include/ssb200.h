@@ -1,0 +1,120 @@
+/*
+ * ssb200.h -- C ABI of libssb200.so: the B200 (sm_100a) implementation of the two
+ * data-parallel hot paths of stochasticSim.
+ *
+ * The reference has no library/FFI boundary: its two hot paths are standalone C
+ * programs whose interface is argv + files.  The drop-in boundary is
+ * therefore the pair of executables built from stochasticsim_b200/host/ (same argv,
+ * same outputs, same exit codes); those mains stay in C and reach the GPU only
+ * through the entry points below.  Each entry point names the reference code it
+ * replaces.
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, one ssb_ctx per
+ * device, no global state, return 0 on success or a negative SSB_E_* code
+ * (ssb_strerror() gives the text).  There is NO CPU fallback anywhere behind this
+ * header: without a usable CUDA device ssb_ctx_create() fails.
+ */
+#ifndef SSB200_H
+#define SSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+
+enum {
+    SSB_OK            =  0,
+    SSB_E_CUDA        = -1,   /* CUDA runtime error (text kept in the ctx)              */
+    SSB_E_NODEVICE    = -2,   /* no CUDA device / wrong architecture                    */
+    SSB_E_ARG         = -3,   /* bad argument                                           */
+    SSB_E_NOMEM       = -4,
+    SSB_E_FORMAT      = -5,   /* input violates a documented precondition */
+    SSB_E_UNSORTED    = -6,   /* SAM input not coordinate sorted                        */
+    SSB_E_DEPTH       = -7,   /* pileup deeper than MAX_PILEUP_SIZE (stochasticSpike.c:38) */
+    SSB_E_REF         = -8,   /* contig missing from / longer than the reference FASTA  */
+    SSB_E_STATE       = -9,   /* call order violated                                    */
+    SSB_E_NCCL        = -10
+};
+
+typedef struct ssb_ctx ssb_ctx;
+
+int         ssb_abi_version(void);
+const char *ssb_strerror(int code);
+/* Last CUDA/NCCL error text recorded in this context ("" if none). */
+const char *ssb_last_error(const ssb_ctx *ctx);
+
+/* Binds to CUDA device `device`; fails with SSB_E_NODEVICE unless it is compute capability 10.x. */
+int  ssb_ctx_create(int device, ssb_ctx **out);
+void ssb_ctx_destroy(ssb_ctx *ctx);
+/* Name, SM count, memory of the bound device (any pointer may be NULL). */
+int  ssb_ctx_device_info(const ssb_ctx *ctx, char *name, size_t name_cap, int *sm_count, size_t *total_mem);
+
+/* Plumbing shared by the C mains, tests and bench (pinned host / device buffers, copies on the
+ * context's stream, device timing).  Nothing here computes anything. */
+int  ssb_host_alloc(ssb_ctx *ctx, size_t bytes, void **out);      /* pinned */
+void ssb_host_free(ssb_ctx *ctx, void *p);
+int  ssb_dev_alloc(ssb_ctx *ctx, size_t bytes, void **out);
+void ssb_dev_free(ssb_ctx *ctx, void *p);
+int  ssb_memcpy_h2d(ssb_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* async on ctx stream */
+int  ssb_memcpy_d2h(ssb_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);   /* async on ctx stream */
+int  ssb_memset_dev(ssb_ctx *ctx, void *dst_dev, int value, size_t bytes);
+int  ssb_sync(ssb_ctx *ctx);
+/* CUDA-event stopwatch on the context's stream: start, stop -> elapsed device milliseconds. */
+int  ssb_timer_start(ssb_ctx *ctx);
+int  ssb_timer_stop(ssb_ctx *ctx, float *ms);
+/* Number of kernels this library launched through this context since creation. */
+uint64_t ssb_kernel_launches(const ssb_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path 2: trinucleotide-context scan.
+ * Replaces: tncCountsProfile.c:391-447 (the getline/3-byte-window loop) and incCtx
+ * (tncCountsProfile.c:105-363).  counts64[] is indexed 16*a+4*b+c with A<C<G<T
+ * (tncCountsProfile.c:14-77), exactly the reference's `long ctxCnt[64]`.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Scanner state carried from one piece of a FASTA to the next, so a file can be cut anywhere
+ * (host chunks, or one shard per GPU).  A zeroed struct means "start of file". */
+typedef struct ssb_tnc_carry {
+    uint8_t started;        /* 0 = start of file (the other fields are ignored)                    */
+    uint8_t prev[3];        /* the 3 bytes preceding this piece                                     */
+    uint8_t carry;          /* last byte of the nearest kept, newline-terminated line; 0 = none    */
+    uint8_t frag_nonempty;  /* the piece starts inside a line that already has >= 1 byte            */
+    uint8_t frag_first;     /* first byte of that line                                              */
+    uint8_t frag_has_base;  /* that line already holds an upper-case A/C/G/T                        */
+} ssb_tnc_carry;
+
+/* Device-resident piece: d_fasta[0..n) (n < 2^32) in HBM.  Adds this piece's windows to the 64
+ * device counters d_counts64 (int64, caller zeroes them once).  carry_in may be NULL (= start of
+ * file); carry_out may be NULL.  Asynchronous on the context's stream except for carry_out,
+ * which synchronises.  This is the call bench.py times for `value`. */
+int ssb_tnc_count_device(ssb_ctx *ctx, const uint8_t *d_fasta, size_t n,
+                         const ssb_tnc_carry *carry_in, ssb_tnc_carry *carry_out,
+                         int64_t *d_counts64);
+
+/* Host-resident FASTA of any size: streams it through double-buffered pinned chunks on two
+ * copy/compute streams and returns the 64 totals in counts64 (host, overwritten).  `fasta` may be
+ * pageable or pinned.  This is what the tncCountsProfile main calls, and bench.py's `e2e`. */
+int ssb_tnc_count_host(ssb_ctx *ctx, const uint8_t *fasta, size_t n,
+                       const ssb_tnc_carry *carry_in, ssb_tnc_carry *carry_out,
+                       int64_t counts64[64]);
+
+/* The state a scanner is in after consuming fasta[0..n) from `carry_in`, computed on the host
+ * WITHOUT counting anything: used to cut a FASTA into independent shards (one per GPU). */
+int ssb_tnc_carry_after(const uint8_t *fasta, size_t n, const ssb_tnc_carry *carry_in, ssb_tnc_carry *carry_out);
+
+/* Sum the 64 device counters across ranks (the path's only collective).  `nccl_comm` is an
+ * ncclComm_t created by the caller; the reduction runs on the context's stream. */
+int ssb_tnc_allreduce(ssb_ctx *ctx, void *nccl_comm, int64_t *d_counts64);
+
+/* The reference's 32-line stdout (tncCountsProfile.c:452-483): "CTX\t%ld\n", ctx + reverse
+ * complement, fixed order.  Returns bytes written (excluding NUL) or SSB_E_ARG if cap is short. */
+int ssb_tnc_format(const int64_t counts64[64], char *dst, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB200_H */
