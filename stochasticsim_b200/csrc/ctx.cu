@@ -38,7 +38,7 @@ extern "C" int ssb_ctx_create(int device, ssb_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->total_mem = prop.totalGlobalMem;
-    snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
+    snprintf(ctx->name, sizeof ctx->name, "%.127s", prop.name);
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||

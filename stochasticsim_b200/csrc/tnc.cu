@@ -33,6 +33,9 @@ constexpr int      TNC_BLOCK = 256;
 constexpr int      TNC_BPT   = 32;            // bytes per thread per iteration
 constexpr uint32_t EXC_HEADER = 0x80000000u;  // exception kind flag (positions stay < 2^31)
 constexpr size_t   TNC_MAX_PIECE = (size_t)1 << 30;
+// A piece this small can never overflow the exception list: at most one record per 2 bytes
+// ("\n>" headers) = 65536 < tnc_exc_cap(131072) = 8192 + 65536.
+constexpr size_t   TNC_SAFE_PIECE = (size_t)1 << 17;
 
 struct TncDevState {                          // mirrors ssb_tnc_carry
     uint8_t started, prev[3], carry, frag_nonempty, frag_first, frag_has_base;
@@ -442,7 +445,7 @@ extern "C" int ssb_tnc_count_device(ssb_ctx *ctx, const uint8_t *d_fasta, size_t
         int r = tnc_scratch(ctx, piece, 0, &s);
         if (r) return r;
         // attempt 1 (after an overflow): pieces so small that the list holds their worst case
-        size_t use = attempt == 0 ? piece : ((size_t)(s.exc_cap - 16) * 2) & ~(size_t)31;
+        size_t use = attempt == 0 ? piece : TNC_SAFE_PIECE;
         if ((r = tnc_begin(ctx, ctx->stream, s, carry_in))) return r;
         int cur = 0;
         if ((r = tnc_run_device(ctx, d_fasta, n, use, s, &cur))) return r;
@@ -509,7 +512,7 @@ extern "C" int ssb_tnc_count_host(ssb_ctx *ctx, const uint8_t *fasta, size_t n, 
         SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (!ovf) { if (carry_out) *carry_out = out; return SSB_OK; }
         // adversarial input (a header every few bytes): redo with chunks whose worst case fits the list
-        chunk = ((size_t)(s.exc_cap - 16) * 2) & ~(size_t)31;
+        chunk = TNC_SAFE_PIECE;
     }
     snprintf(ctx->err, sizeof ctx->err, "tnc: exception list overflow in safe mode");
     return SSB_E_FORMAT;
