@@ -68,6 +68,13 @@ int  ssb_timer_start(ssb_ctx *ctx);
 int  ssb_timer_stop(ssb_ctx *ctx, float *ms);
 /* Number of kernels this library launched through this context since creation. */
 uint64_t ssb_kernel_launches(const ssb_ctx *ctx);
+/* Optional per-kernel device timing: when enabled every launch of the kernels below is bracketed by
+ * CUDA events on its own stream; ssb_profile_read() synchronises and returns the summed duration
+ * and the number of launches of one kernel slot (and optionally resets them). */
+enum { SSB_PROF_TNC_SCAN = 0, SSB_PROF_TNC_FIXUP = 1, SSB_PROF_SPIKE_PARSE = 2, SSB_PROF_SPIKE_EMIT = 3,
+       SSB_PROF_SPIKE_CHAIN = 4, SSB_PROF_SPIKE_OTHER = 5, SSB_PROF_SPIKE_TALLY = 6 };
+int  ssb_profile_enable(ssb_ctx *ctx, int on);
+int  ssb_profile_read(ssb_ctx *ctx, int slot, double *total_ms, uint64_t *launches, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * Hot path 2: trinucleotide-context scan.

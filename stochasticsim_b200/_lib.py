@@ -52,6 +52,8 @@ def lib():
         "ssb_timer_start": (C.c_int, [vp]),
         "ssb_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "ssb_kernel_launches": (C.c_uint64, [vp]),
+        "ssb_profile_enable": (C.c_int, [vp, C.c_int]),
+        "ssb_profile_read": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
         "ssb_tnc_count_device": (C.c_int, [vp, u8p, sz, C.POINTER(TncCarry), C.POINTER(TncCarry), vp]),
         "ssb_tnc_count_host": (C.c_int, [vp, u8p, sz, C.POINTER(TncCarry), C.POINTER(TncCarry), i64p]),
         "ssb_tnc_carry_after": (C.c_int, [u8p, sz, C.POINTER(TncCarry), C.POINTER(TncCarry)]),
@@ -143,3 +145,12 @@ class Context:
 
     def launches(self):
         return int(self._L.ssb_kernel_launches(self.handle))
+
+    def profile_enable(self, on=True):
+        check(self._L.ssb_profile_enable(self.handle, 1 if on else 0), self.handle)
+
+    def profile_read(self, slot, reset=True):
+        """(total device ms, launches) of one kernel slot (SSB_PROF_* in include/ssb200.h)."""
+        ms, n = C.c_double(), C.c_uint64()
+        check(self._L.ssb_profile_read(self.handle, slot, C.byref(ms), C.byref(n), 1 if reset else 0), self.handle)
+        return ms.value, int(n.value)

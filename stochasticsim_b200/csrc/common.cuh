@@ -22,7 +22,16 @@ struct ssb_ctx {
     size_t       scratch_bytes;
     void        *pinned;
     size_t       pinned_bytes;
+    // optional per-kernel device timing (ssb_profile_*): CUDA events around individual launches
+    int          prof_on;
+    struct ssb_prof *prof;
 };
+
+// kernel slots for ssb_profile_read()
+enum { SSB_K_TNC_SCAN = 0, SSB_K_TNC_FIXUP = 1, SSB_K_SPIKE_PARSE = 2, SSB_K_SPIKE_EMIT = 3, SSB_K_SPIKE_CHAIN = 4,
+       SSB_K_SPIKE_OTHER = 5, SSB_K_SPIKE_TALLY = 6, SSB_K_SLOTS = 8 };
+void ssb_prof_begin(ssb_ctx *ctx, int slot, cudaStream_t s);
+void ssb_prof_end(ssb_ctx *ctx, int slot, cudaStream_t s);
 
 #define SSB_CUDA(ctx, call)                                                                  \
     do {                                                                                     \
@@ -39,6 +48,16 @@ struct ssb_ctx {
     do {                                                                                     \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
         (ctx)->launches++;                                                                   \
+        SSB_CUDA(ctx, cudaGetLastError());                                                   \
+    } while (0)
+
+// Same, with the launch bracketed by profiling events when ssb_profile_enable() is on.
+#define SSB_LAUNCH_P(ctx, slot, kernel, grid, block, smem, stream, ...)                      \
+    do {                                                                                     \
+        if ((ctx)->prof_on) ssb_prof_begin((ctx), (slot), (stream));                         \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+        (ctx)->launches++;                                                                   \
+        if ((ctx)->prof_on) ssb_prof_end((ctx), (slot), (stream));                           \
         SSB_CUDA(ctx, cudaGetLastError());                                                   \
     } while (0)
 

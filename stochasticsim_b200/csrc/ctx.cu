@@ -2,6 +2,14 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+struct ssb_prof {
+    static const int CAP = 1024;
+    cudaEvent_t a[SSB_K_SLOTS][CAP], b[SSB_K_SLOTS][CAP];
+    int         made[SSB_K_SLOTS], used[SSB_K_SLOTS];
+    double      ms[SSB_K_SLOTS];
+    uint64_t    n[SSB_K_SLOTS];
+};
+
 extern "C" int ssb_abi_version(void) { return SSB_ABI_VERSION; }
 
 extern "C" const char *ssb_strerror(int code)
@@ -60,6 +68,11 @@ extern "C" void ssb_ctx_destroy(ssb_ctx *ctx)
     cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->prof) {
+        for (int s = 0; s < SSB_K_SLOTS; s++)
+            for (int i = 0; i < ctx->prof->made[s]; i++) { cudaEventDestroy(ctx->prof->a[s][i]); cudaEventDestroy(ctx->prof->b[s][i]); }
+        free(ctx->prof);
+    }
     for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev[i]);
     cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
     cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
@@ -156,4 +169,54 @@ extern "C" int ssb_timer_stop(ssb_ctx *ctx, float *ms)
     SSB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
     return SSB_OK;
 }
+// ---- per-kernel timing: event pairs around single launches, summed on read -------------------
+
+static void prof_flush(ssb_ctx *ctx, int slot)
+{
+    ssb_prof *p = ctx->prof;
+    for (int i = 0; i < p->used[slot]; i++) {
+        float ms = 0;
+        if (cudaEventSynchronize(p->b[slot][i]) == cudaSuccess && cudaEventElapsedTime(&ms, p->a[slot][i], p->b[slot][i]) == cudaSuccess) {
+            p->ms[slot] += ms; p->n[slot]++;
+        }
+    }
+    p->used[slot] = 0;
+}
+
+void ssb_prof_begin(ssb_ctx *ctx, int slot, cudaStream_t s)
+{
+    ssb_prof *p = ctx->prof;
+    if (!p || slot < 0 || slot >= SSB_K_SLOTS) return;
+    if (p->used[slot] == ssb_prof::CAP) prof_flush(ctx, slot);
+    int i = p->used[slot];
+    if (i >= p->made[slot]) { cudaEventCreate(&p->a[slot][i]); cudaEventCreate(&p->b[slot][i]); p->made[slot] = i + 1; }
+    cudaEventRecord(p->a[slot][i], s);
+}
+
+void ssb_prof_end(ssb_ctx *ctx, int slot, cudaStream_t s)
+{
+    ssb_prof *p = ctx->prof;
+    if (!p || slot < 0 || slot >= SSB_K_SLOTS) return;
+    cudaEventRecord(p->b[slot][p->used[slot]++], s);
+}
+
+extern "C" int ssb_profile_enable(ssb_ctx *ctx, int on)
+{
+    if (!ctx) return SSB_E_ARG;
+    if (on && !ctx->prof) { ctx->prof = (ssb_prof *)calloc(1, sizeof(ssb_prof)); if (!ctx->prof) return SSB_E_NOMEM; }
+    ctx->prof_on = on ? 1 : 0;
+    return SSB_OK;
+}
+
+extern "C" int ssb_profile_read(ssb_ctx *ctx, int slot, double *total_ms, uint64_t *launches, int reset)
+{
+    if (!ctx || !ctx->prof || slot < 0 || slot >= SSB_K_SLOTS) return SSB_E_ARG;
+    SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+    prof_flush(ctx, slot);
+    if (total_ms) *total_ms = ctx->prof->ms[slot];
+    if (launches) *launches = ctx->prof->n[slot];
+    if (reset) { ctx->prof->ms[slot] = 0; ctx->prof->n[slot] = 0; }
+    return SSB_OK;
+}
+
 extern "C" uint64_t ssb_kernel_launches(const ssb_ctx *ctx) { return ctx ? ctx->launches : 0; }

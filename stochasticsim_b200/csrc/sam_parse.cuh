@@ -1,0 +1,306 @@
+// sam_parse.cuh -- one streaming pass over SAM text: find lines, parse the fields the spike path
+// needs, apply the reference's read filter.  (Stands in for htslib's sam_read1 + read_bam,
+// stochasticSpike.c:243-268, for SAM text input.)
+//
+// Shape: persistent blocks pull 32 KiB tiles of the body in order (atomic ticket).  A block
+//   1. stages its tile (+ an overhang for the line that runs past the end) in shared memory with
+//      16-byte loads;
+//   2. finds newlines byte-parallel: SWAR zero-byte test per 32-bit word, 16-bit mask per 16-byte
+//      chunk, block-wide exclusive scan of the per-thread popcounts -> ordered line starts;
+//   3. learns the global index of its first line from a decoupled look-back over per-tile line
+//      counts (single pass, no separate counting kernel);
+//   4. parses one line per thread out of shared memory and writes a 64-byte SamRec.
+// HBM traffic: the text is read once; 64 B per line are written.
+#pragma once
+#include "common.cuh"
+#include "spike_types.cuh"
+
+namespace samparse {
+
+constexpr int TILE      = 32768;
+constexpr int OVERHANG  = 8192;
+constexpr int THREADS   = 256;
+constexpr int MAX_LINES = 2048;                 // a valid SAM line has >= 22 bytes -> <= 1490 per tile
+constexpr int CHUNKS    = TILE / 16;            // 16-byte chunks per tile
+constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64;
+
+// tile_state word: bits 63..62 = status (0 none, 1 aggregate, 2 inclusive prefix), low 62 bits = line count
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
+
+struct ContigNames {          // device: concatenated names + offsets, for RNAME -> tid
+    const char *text;
+    const uint32_t *off;      // n + 1 offsets
+    int n;
+};
+
+__device__ __forceinline__ uint32_t nl_mask16(uint4 v)
+{
+    // 16-bit mask of '\n' bytes in 16 bytes
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t d = w[j] ^ 0x0A0A0A0Au;
+        uint32_t t = (d & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+        uint32_t z = ~(t | d | 0x7f7f7f7fu);                   // 0x80 per '\n'
+        m |= ((((z >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * j);
+    }
+    return m;
+}
+
+struct Cursor {               // byte access: shared memory while inside the staged window, else global
+    const uint8_t *smem; const uint8_t *g; size_t base; size_t lim; size_t n;
+    __device__ __forceinline__ uint8_t at(size_t p) const { return p < lim ? smem[p - base] : (p < n ? g[p] : (uint8_t)'\n'); }
+};
+
+__device__ __forceinline__ bool seq_char_ok(uint8_t c)
+{
+    // the bytes htslib's 4-bit round trip maps to themselves: "=ACMGRSVTWYHKDBN"
+    if (c == '=') return true;
+    if (c < 'A' || c > 'Z') return false;
+    return ((0x16e34cfu >> (c - 'A')) & 1u) != 0;          // A B C D G H K M N R S T V W Y
+}
+
+// Parses the line starting at `s` (ending at newline position `e`, e == n for an unterminated last
+// line).  Returns 0 or an SSB_E_* code.
+__device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNames &names, int &tid_cache, SamRec &r)
+{
+    size_t p = s;
+    r.line_off = s;
+    r.line_len = (uint32_t)(e - s + (e < cur.n ? 1 : 0));
+    r.bits = e < cur.n ? 0 : REC_NO_NL;
+    for (int k = 0; k < 6; k++) r.pad[k] = 0;
+    // QNAME
+    uint64_t h = 1469598103934665603ull;
+    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; h = (h ^ c) * 1099511628211ull; p++; }
+    if (p >= e || p == s) return SSB_E_FORMAT;
+    r.qhash = h; r.qname_len = (uint16_t)(p - s);
+    if (p - s > 65535) return SSB_E_FORMAT;
+    p++;
+    // FLAG (decimal)
+    uint32_t v = 0; size_t p0 = p;
+    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '0' || c > '9') return SSB_E_FORMAT; v = v * 10 + (c - '0'); p++; }
+    if (p >= e || p == p0 || v > 65535) return SSB_E_FORMAT;
+    r.flag = (uint16_t)v; p++;
+    // RNAME
+    p0 = p;
+    while (p < e && cur.at(p) != '\t') p++;
+    if (p >= e || p == p0) return SSB_E_FORMAT;
+    {
+        size_t len = p - p0;
+        int tid = -1;
+        if (!(len == 1 && cur.at(p0) == '*')) {
+            auto same = [&](int c) {
+                uint32_t a = names.off[c], b = names.off[c + 1];
+                if (b - a != len) return false;
+                for (size_t i = 0; i < len; i++) if ((uint8_t)names.text[a + i] != cur.at(p0 + i)) return false;
+                return true;
+            };
+            if (tid_cache >= 0 && same(tid_cache)) tid = tid_cache;      // consecutive lines share a contig
+            else for (int c = 0; c < names.n; c++) if (same(c)) { tid = c; break; }   // first @SQ with that name (sam_hdr_name2tid)
+            if (tid >= 0) tid_cache = tid;
+        }
+        r.tid = tid;
+    }
+    p++;
+    // POS
+    p0 = p; uint64_t pv = 0;
+    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '0' || c > '9') return SSB_E_FORMAT; pv = pv * 10 + (c - '0'); if (pv > 0x7fffffffull) return SSB_E_FORMAT; p++; }
+    if (p >= e || p == p0) return SSB_E_FORMAT;
+    r.pos = (int32_t)pv - 1; p++;
+    // MAPQ
+    p0 = p; v = 0;
+    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '0' || c > '9') return SSB_E_FORMAT; v = v * 10 + (c - '0'); if (v > 255) return SSB_E_FORMAT; p++; }
+    if (p >= e || p == p0) return SSB_E_FORMAT;
+    r.mapq = (uint8_t)v; p++;
+    // CIGAR
+    p0 = p;
+    uint64_t rlen = 0, qlen = 0; bool has_cigar = true;
+    if (cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { has_cigar = false; p++; }
+    else {
+        uint64_t num = 0; bool have = false;
+        while (p < e) {
+            uint8_t c = cur.at(p);
+            if (c == '\t') break;
+            if (c >= '0' && c <= '9') { num = num * 10 + (c - '0'); have = true; if (num > 0x0fffffffull) return SSB_E_FORMAT; }
+            else {
+                if (!have) return SSB_E_FORMAT;
+                switch (c) {
+                case 'M': case '=': case 'X': rlen += num; qlen += num; break;
+                case 'D': case 'N': rlen += num; break;
+                case 'I': case 'S': qlen += num; break;
+                case 'H': case 'P': break;
+                default: return SSB_E_FORMAT;
+                }
+                num = 0; have = false;
+            }
+            p++;
+        }
+        if (have) return SSB_E_FORMAT;
+    }
+    if (p >= e || p == p0 || p - p0 > 65535 || p0 - s > 65535) return SSB_E_FORMAT;
+    r.cigar_off = (uint16_t)(p0 - s); r.cigar_len = has_cigar ? (uint16_t)(p - p0) : 0;
+    if ((uint64_t)r.pos + rlen > 0x7fffffffull) return SSB_E_FORMAT;
+    r.end = r.pos + (int32_t)rlen;
+    p++;
+    // RNEXT, PNEXT, TLEN: not needed, only delimited
+    for (int k = 0; k < 3; k++) { p0 = p; while (p < e && cur.at(p) != '\t') p++; if (p >= e || p == p0) return SSB_E_FORMAT; p++; }
+    // SEQ
+    r.seq_off = (uint32_t)(p - s);
+    p0 = p;
+    if (cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { r.l_seq = 0; p++; }
+    else {
+        while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (!seq_char_ok(c)) return SSB_E_FORMAT; p++; }
+        r.l_seq = (uint32_t)(p - p0);
+        if (has_cigar && qlen != r.l_seq) return SSB_E_FORMAT;      // htslib: "CIGAR and query sequence are of different length"
+    }
+    if (p >= e || p == p0) return SSB_E_FORMAT;
+    p++;
+    // QUAL
+    r.qual_off = (uint32_t)(p - s);
+    if (p >= e) return SSB_E_FORMAT;
+    size_t qend;
+    if (cur.at(p) == '*' && (p + 1 == e || cur.at(p + 1) == '\t')) { r.bits |= REC_QUALSTAR; qend = p + 1; }
+    else {
+        qend = p + r.l_seq;
+        if (r.l_seq == 0 || qend > e) return SSB_E_FORMAT;
+        if (qend < e && cur.at(qend) != '\t') return SSB_E_FORMAT;  // htslib: "SEQ and QUAL are of different length"
+    }
+    if (e > s && cur.at(e - 1) == '\r') return SSB_E_FORMAT;          // CRLF input is outside the byte-exact pass-through envelope
+    // read_bam (stochasticSpike.c:253-263) + bam_plp_push's tid/unmapped test
+    bool pass = !(r.flag & (4 | 256 | 512 | 1024)) && r.mapq >= 30 && !((r.flag & 1) && !(r.flag & 2));
+    if (pass && r.tid >= 0) {
+        r.bits |= REC_PUSHED;
+        if (r.end > r.pos) r.bits |= REC_KEEP;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(THREADS)
+parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamRec *__restrict__ recs, size_t rec_cap,
+             unsigned long long *__restrict__ tile_state, unsigned int *__restrict__ ticket,
+             unsigned long long *__restrict__ n_lines_out, SpikeErr *__restrict__ err)
+{
+    extern __shared__ __align__(16) uint8_t sm[];
+    uint8_t  *text   = sm;                                            // TILE + OVERHANG
+    uint16_t *masks  = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG);          // CHUNKS
+    uint32_t *starts = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2);   // MAX_LINES (tile-relative)
+    __shared__ unsigned int s_tile;
+    __shared__ unsigned int s_warp_tot[THREADS / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_first;
+
+    const size_t n_tiles = (n + TILE - 1) / TILE;
+    const int tid_ = threadIdx.x, lane = tid_ & 31, wid = tid_ >> 5;
+    int tid_cache = -1;
+
+    for (;;) {
+        __syncthreads();
+        if (tid_ == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const size_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const size_t T0 = tile * TILE;
+        const size_t stage_end = (T0 + TILE + OVERHANG < n) ? T0 + TILE + OVERHANG : n;
+        // 1. stage
+        for (size_t o = (size_t)tid_ * 16; T0 + o < stage_end; o += THREADS * 16) {
+            if (T0 + o + 16 <= n) *reinterpret_cast<uint4 *>(text + o) = *reinterpret_cast<const uint4 *>(body + T0 + o);
+            else for (int k = 0; k < 16; k++) text[o + k] = (T0 + o + k < n) ? body[T0 + o + k] : (uint8_t)'\n';
+        }
+        if (tid_ == 0) s_first = (T0 == 0) ? 1u : (body[T0 - 1] == '\n');
+        __syncthreads();
+        // 2. newline masks per 16-byte chunk (chunk c covers tile bytes [16c, 16c+16))
+        const size_t tile_bytes = (T0 + TILE <= n) ? TILE : n - T0;
+        for (int c = tid_; c < CHUNKS; c += THREADS) {
+            uint32_t m = 0;
+            if ((size_t)c * 16 < tile_bytes) {
+                m = nl_mask16(*reinterpret_cast<const uint4 *>(text + c * 16));
+                size_t rem = tile_bytes - (size_t)c * 16;
+                if (rem < 16) m &= (1u << rem) - 1u;
+            }
+            masks[c] = (uint16_t)m;
+        }
+        __syncthreads();
+        // a line starts after every newline except one sitting on the last byte of the tile (or of the body)
+        // thread t owns chunks [8t, 8t+8)
+        uint32_t mym[8]; uint32_t cnt = 0;
+        {
+            const uint4 mm = *reinterpret_cast<const uint4 *>(masks + 8 * tid_);
+            const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) { mym[2 * k] = w4[k] & 0xFFFFu; mym[2 * k + 1] = w4[k] >> 16; }
+            if (tid_ == THREADS - 1) mym[7] &= 0x7FFFu;              // newline on the last byte of a full tile: next tile's line
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                // drop a newline that is the very last byte of the body: nothing starts after it
+                size_t cb = T0 + (size_t)(8 * tid_ + k) * 16;
+                if (n > cb && n - cb <= 16) mym[k] &= ~(1u << (n - cb - 1));
+                cnt += __popc(mym[k]);
+            }
+        }
+        // block exclusive scan of cnt
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) s_warp_tot[wid] = incl;
+        __syncthreads();
+        uint32_t warp_base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) { uint32_t t = s_warp_tot[w]; if (w < wid) warp_base += t; total += t; }
+        const uint32_t first = s_first;
+        uint32_t my_base = first + warp_base + incl - cnt;
+        const uint32_t n_here = first + total;
+        // 3. decoupled look-back for the global index of this tile's first line
+        if (tid_ == 0) {
+            unsigned long long excl = 0;
+            if (tile == 0) {
+                atomicExch(&tile_state[0], ST_INC | (unsigned long long)n_here);
+            } else {
+                atomicExch(&tile_state[tile], ST_AGG | (unsigned long long)n_here);
+                size_t j = tile - 1;
+                for (;;) {
+                    unsigned long long v;
+                    do { v = atomicAdd(&tile_state[j], 0ull); } while ((v & ST_MASK) == 0);
+                    excl += v & ~ST_MASK;
+                    if ((v & ST_MASK) == ST_INC) break;
+                    j--;
+                }
+                atomicExch(&tile_state[tile], ST_INC | (excl + n_here));
+            }
+            s_base = excl;
+            if (tile == n_tiles - 1) *n_lines_out = excl + n_here;
+        }
+        if (n_here > MAX_LINES) {                                      // > 2048 lines in 32 KiB cannot be SAM
+            if (tid_ == 0 && atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = T0;
+            __syncthreads();
+            continue;
+        }
+        if (tid_ == 0 && first) starts[0] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t m = mym[k];
+            while (m) {
+                int b = __ffs(m) - 1; m &= m - 1;
+                starts[my_base++] = (uint32_t)((8 * tid_ + k) * 16 + b + 1);
+            }
+        }
+        __syncthreads();
+        const unsigned long long gbase = s_base;
+        // 4. one line per thread
+        Cursor cur{text, body, T0, stage_end, n};
+        for (uint32_t i = tid_; i < n_here; i += THREADS) {
+            size_t s = T0 + starts[i];
+            size_t e;
+            if (i + 1 < n_here) e = T0 + starts[i + 1] - 1;
+            else { e = s; while (e < n && cur.at(e) != '\n') e++; }   // last line of the tile: find its newline in the overhang
+            SamRec r;
+            int rc = parse_line(cur, s, e, names, tid_cache, r);
+            if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = s; r.bits = 0; r.tid = -1; r.pos = 0; r.end = 0; }
+            unsigned long long gi = gbase + i;
+            if (gi < rec_cap) recs[gi] = r;
+            else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
+        }
+    }
+}
+
+} // namespace samparse

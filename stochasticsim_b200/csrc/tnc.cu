@@ -399,9 +399,9 @@ int tnc_piece(ssb_ctx *ctx, cudaStream_t stream, const uint8_t *d, size_t n, con
     int max_grid = ctx->sm_count * 2 * 4;        // 2 resident blocks per SM, 4 block slots of work each
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
-    SSB_LAUNCH(ctx, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, s.acc, s.exc_count, s.exc, s.exc_cap);
+    SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, s.acc, s.exc_count, s.exc, s.exc_cap);
     int fgrid = ctx->sm_count * 4;
-    SSB_LAUNCH(ctx, tnc_fixup_kernel, fgrid, 128, 0, stream, d, n, st_in, st_out, s.acc, s.exc_count, s.ovf, s.exc, s.exc_cap);
+    SSB_LAUNCH_P(ctx, SSB_K_TNC_FIXUP, tnc_fixup_kernel, fgrid, 128, 0, stream, d, n, st_in, st_out, s.acc, s.exc_count, s.ovf, s.exc, s.exc_cap);
     return SSB_OK;
 }
 
