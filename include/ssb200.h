@@ -121,6 +121,93 @@ int ssb_tnc_allreduce(ssb_ctx *ctx, void *nccl_comm, int64_t *d_counts64);
  * complement, fixed order.  Returns bytes written (excluding NUL) or SSB_E_ARG if cap is short. */
 int ssb_tnc_format(const int64_t counts64[64], char *dst, size_t cap);
 
+/* ------------------------------------------------------------------------------------------
+ * Hot path 1: stochastic spike-in.
+ * Replaces the pileup loop of stochasticSpike.c:1129-1623 (read filter read_bam :243-268, RNG
+ * helpers :283-360, overlap handling :363-432, attemptToMutateBase :526-904, write-out
+ * :1272-1285/:1362-1371, target advance :1578-1619) for SAM TEXT input.  The host main keeps the
+ * reference's argv/file handling (stochasticsim_b200/host/stochasticSpike.c) and calls in here.
+ *
+ * One ssb_spike object = one reference genome on one device.  A run takes the alignment lines of
+ * a coordinate-sorted SAM (header removed), the `.spike` targets in FILE order and the seed, and
+ * produces: the output alignment lines (kept reads ordered by end position, bases substituted,
+ * QUAL untouched), one result per target (everything a truth.vcf target / NO_COVERAGE line needs),
+ * the SEQ_ERROR records and the five counters of the stats block (stochasticSpike.c:1668).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssb_spike ssb_spike;
+
+typedef struct ssb_contig {
+    const char    *name;      /* @SQ SN, in header order: index = tid (sam_hdr_name2tid)            */
+    int64_t        len;       /* bases available in `seq`                                            */
+    const uint8_t *seq;       /* host pointer: the contig as faidx_fetch_seq64 returns it (newlines
+                                 stripped, CASE PRESERVED), or NULL when the FASTA lacks the contig */
+} ssb_contig;
+
+/* One valid `.spike` record as getNextTarget() parses it (stochasticSpike.c:98-158, struct :88-94). */
+typedef struct ssb_target {
+    int32_t c_tid;            /* sam_hdr_name2tid(contig), -1 when unknown                           */
+    int32_t reserved;
+    int64_t locus;            /* atol(POS) - 1                                                       */
+    uint8_t base;             /* first byte of the ALT field                                         */
+    uint8_t pad[3];
+    float   af;               /* (float)atof(AF)                                                     */
+} ssb_target;
+
+enum { SSB_T_HIT = 0, SSB_T_NOCOV = 1, SSB_T_NOCOV_SILENT = 2, SSB_T_TAIL = 3 };
+enum { SSB_F_NONE = 0, SSB_F_PASS = 1, SSB_F_MASKED = 2, SSB_F_MASKED_OVL = 3, SSB_F_UNDETECTED = 4 };
+
+typedef struct ssb_target_result {
+    int32_t status;           /* SSB_T_*: HIT = spiked at a covered locus; NOCOV = passed over, line
+                                 printed; NOCOV_SILENT = passed over but stochasticSpike.c:1603 suppresses
+                                 the line; TAIL = left over after the last covered locus (:1630-1646) */
+    int32_t at_tid;           /* covered locus where the target was consumed (HIT: the target)       */
+    int64_t at_pos;
+    int64_t locus_index;      /* ordinal of that covered locus (orders lines inside truth.vcf)       */
+    uint8_t ref_base, mutant_allele, filter, pad;
+    int32_t ref_cnt, mut_cnt;
+    int32_t err_cnt[4];       /* G, C, A, T (the reference's errorAlleleDepths order, :1207)         */
+    int64_t rng_offset;       /* rand() calls consumed before this locus (diagnostic)                */
+} ssb_target_result;
+
+typedef struct ssb_spike_stats {
+    int64_t alignmentCount, numberOfLociCovered, totalFoldCoverage, maxDepth;   /* :1668            */
+    int64_t n_lines, n_kept, in_bytes, out_bytes, n_runs, n_hits, rng_draws;
+    float   ms_parse, ms_sort, ms_emit, ms_cover, ms_gather, ms_rng, ms_chain, ms_patch, ms_total;
+} ssb_spike_stats;
+
+int  ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_contigs, ssb_spike **out);
+void ssb_spike_destroy(ssb_spike *sp);
+
+/* Run on alignment lines already in HBM (d_sam 16-byte aligned).  The output lines are written to
+ * d_out (capacity out_cap >= n + 1 is always enough); *out_bytes gets their size.  results[] has
+ * n_targets entries.  Device work is asynchronous internally but the call returns synchronised.
+ * This is the call bench.py times for `value`. */
+int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t n, uint8_t *d_out, size_t out_cap,
+                         const ssb_target *targets, size_t n_targets, unsigned seed,
+                         ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes);
+
+/* Same, host buffers: copies `sam` in, runs, copies the output lines back into `out`.  This is
+ * what the stochasticSpike main calls, and bench.py's `e2e`. */
+int ssb_spike_run_host(ssb_spike *sp, const uint8_t *sam, size_t n, uint8_t *out, size_t out_cap,
+                       const ssb_target *targets, size_t n_targets, unsigned seed,
+                       ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes);
+
+/* The reference's random stream: rand() #k0 .. #k0+n-1 after srand(seed) (stochasticSpike.c:948,297,334;
+ * glibc TYPE_3 generator), produced on the device by polynomial skip-ahead.  Test / diagnostic hook. */
+int ssb_spike_rand(ssb_spike *sp, unsigned seed, uint64_t k0, size_t n, int32_t *out_host);
+
+/* SEQ_ERROR records of the last run (truth.vcf lines :1494-1557): loci, in covered order, where no
+ * target was spiked and at least one non-reference allele was tallied. */
+typedef struct ssb_seq_error {
+    int32_t tid; int32_t ref_cnt;
+    int64_t pos;
+    int64_t locus_index;
+    int32_t err_cnt[4];       /* G, C, A, T */
+    uint8_t ref_base, pad[7];
+} ssb_seq_error;
+int ssb_spike_seq_error_count(ssb_spike *sp, size_t *count);
+int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

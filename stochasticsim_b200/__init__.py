@@ -7,5 +7,6 @@ bench.py; it contains no computation and NO fallback: if the shared library has 
 """
 from ._lib import lib, SSBError, Context, TncCarry, LIB_PATH, check  # noqa: F401
 from . import tnc  # noqa: F401
+from . import spike  # noqa: F401
 
-__all__ = ["lib", "SSBError", "Context", "TncCarry", "LIB_PATH", "check", "tnc"]
+__all__ = ["lib", "SSBError", "Context", "TncCarry", "LIB_PATH", "check", "tnc", "spike"]

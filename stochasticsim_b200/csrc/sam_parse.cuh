@@ -61,70 +61,136 @@ __device__ __forceinline__ bool seq_char_ok(uint8_t c)
     return ((0x16e34cfu >> (c - 'A')) & 1u) != 0;          // A B C D G H K M N R S T V W Y
 }
 
+// Canonical decimal field ending at '\t' (what htslib prints back): digits only, no leading zero
+// unless the value is 0, value <= maxv.  On success p sits on the terminating tab.
+__device__ __forceinline__ int parse_udec(const Cursor &cur, size_t &p, size_t e, uint64_t maxv, uint64_t &out)
+{
+    size_t p0 = p; uint64_t v = 0;
+    while (p < e) {
+        uint8_t c = cur.at(p);
+        if (c == '\t') break;
+        if (c < '0' || c > '9') return SSB_E_FORMAT;
+        v = v * 10 + (c - '0');
+        if (v > maxv) return SSB_E_FORMAT;
+        p++;
+    }
+    if (p >= e || p == p0) return SSB_E_FORMAT;
+    if (p - p0 > 1 && cur.at(p0) == '0') return SSB_E_FORMAT;
+    out = v;
+    return 0;
+}
+
+// RNAME / RNEXT lookup: index of the first @SQ with that name, -1 if none
+__device__ __forceinline__ int name_lookup(const Cursor &cur, size_t p0, size_t len, const ContigNames &names, int hint)
+{
+    auto same = [&](int c) {
+        uint32_t a = names.off[c], b = names.off[c + 1];
+        if (b - a != len) return false;
+        for (size_t i = 0; i < len; i++) if ((uint8_t)names.text[a + i] != cur.at(p0 + i)) return false;
+        return true;
+    };
+    if (hint >= 0 && hint < names.n && same(hint)) {
+        // the hint is only valid if no EARLIER @SQ carries the same name (sam_hdr_name2tid returns the first)
+        for (int c = 0; c < hint; c++) if (same(c)) return c;
+        return hint;
+    }
+    for (int c = 0; c < names.n; c++) if (same(c)) return c;
+    return -1;
+}
+
+// One optional field [p, q): TAG:TYPE:VALUE in the form htslib prints back unchanged.
+__device__ int aux_ok(const Cursor &cur, size_t p, size_t q)
+{
+    if (q - p < 5 || cur.at(p + 2) != ':' || cur.at(p + 4) != ':') return SSB_E_FORMAT;
+    uint8_t ty = cur.at(p + 3);
+    size_t v = p + 5;
+    auto canon_int = [&](size_t a, size_t b) {
+        if (a < b && cur.at(a) == '-') a++;
+        if (a >= b) return false;
+        if (b - a > 1 && cur.at(a) == '0') return false;
+        if (b - a > 10) return false;
+        for (size_t i = a; i < b; i++) { uint8_t c = cur.at(i); if (c < '0' || c > '9') return false; }
+        return !(b - a == 1 && cur.at(a) == '0' && a > v && cur.at(a - 1) == '-');      // "-0"
+    };
+    switch (ty) {
+    case 'A': return (q - v == 1 && cur.at(v) >= '!' && cur.at(v) <= '~') ? 0 : SSB_E_FORMAT;
+    case 'i': return canon_int(v, q) ? 0 : SSB_E_FORMAT;
+    case 'Z': for (size_t i = v; i < q; i++) { uint8_t c = cur.at(i); if (c < ' ' || c > '~') return SSB_E_FORMAT; } return 0;
+    case 'H': if ((q - v) & 1) return SSB_E_FORMAT;
+              for (size_t i = v; i < q; i++) { uint8_t c = cur.at(i); if (!((c >= '0' && c <= '9') || (c >= 'A' && c <= 'F'))) return SSB_E_FORMAT; } return 0;
+    case 'B': {
+        if (q - v < 1) return SSB_E_FORMAT;
+        uint8_t st = cur.at(v);
+        if (st != 'c' && st != 'C' && st != 's' && st != 'S' && st != 'i' && st != 'I') return SSB_E_FORMAT;   // float arrays: %g round trip not guaranteed
+        size_t a = v + 1;
+        while (a < q) {
+            if (cur.at(a) != ',') return SSB_E_FORMAT;
+            size_t b = a + 1; while (b < q && cur.at(b) != ',') b++;
+            size_t vv = v; (void)vv;
+            size_t s0 = a + 1;
+            if (s0 < b && cur.at(s0) == '-') s0++;
+            if (s0 >= b || (b - s0 > 1 && cur.at(s0) == '0')) return SSB_E_FORMAT;
+            for (size_t i = s0; i < b; i++) { uint8_t c = cur.at(i); if (c < '0' || c > '9') return SSB_E_FORMAT; }
+            a = b;
+        }
+        return 0;
+    }
+    default: return SSB_E_FORMAT;      // 'f' and unknown types are outside the byte-exact pass-through envelope
+    }
+}
+
 // Parses the line starting at `s` (ending at newline position `e`, e == n for an unterminated last
-// line).  Returns 0 or an SSB_E_* code.
+// line).  Returns 0 or an SSB_E_* code.  A line is accepted only if htslib's parse -> format round
+// trip (sam_read1 + sam_write1, stochasticSpike.c:248,273) reproduces it byte for byte, so that the
+// emit stage can pass the original bytes through (DESIGN.md "pass-through envelope").
 __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNames &names, int &tid_cache, SamRec &r)
 {
     size_t p = s;
+    uint64_t v;
     r.line_off = s;
     r.line_len = (uint32_t)(e - s + (e < cur.n ? 1 : 0));
     r.bits = e < cur.n ? 0 : REC_NO_NL;
     for (int k = 0; k < 6; k++) r.pad[k] = 0;
+    if (e - s > 0x7fffffffull) return SSB_E_FORMAT;
     // QNAME
     uint64_t h = 1469598103934665603ull;
-    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; h = (h ^ c) * 1099511628211ull; p++; }
-    if (p >= e || p == s) return SSB_E_FORMAT;
+    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '!' || c > '~') return SSB_E_FORMAT; h = (h ^ c) * 1099511628211ull; p++; }
+    if (p >= e || p == s || p - s > 254) return SSB_E_FORMAT;
     r.qhash = h; r.qname_len = (uint16_t)(p - s);
-    if (p - s > 65535) return SSB_E_FORMAT;
     p++;
-    // FLAG (decimal)
-    uint32_t v = 0; size_t p0 = p;
-    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '0' || c > '9') return SSB_E_FORMAT; v = v * 10 + (c - '0'); p++; }
-    if (p >= e || p == p0 || v > 65535) return SSB_E_FORMAT;
+    // FLAG
+    if (parse_udec(cur, p, e, 65535, v)) return SSB_E_FORMAT;
     r.flag = (uint16_t)v; p++;
     // RNAME
-    p0 = p;
+    size_t p0 = p;
     while (p < e && cur.at(p) != '\t') p++;
     if (p >= e || p == p0) return SSB_E_FORMAT;
-    {
-        size_t len = p - p0;
-        int tid = -1;
-        if (!(len == 1 && cur.at(p0) == '*')) {
-            auto same = [&](int c) {
-                uint32_t a = names.off[c], b = names.off[c + 1];
-                if (b - a != len) return false;
-                for (size_t i = 0; i < len; i++) if ((uint8_t)names.text[a + i] != cur.at(p0 + i)) return false;
-                return true;
-            };
-            if (tid_cache >= 0 && same(tid_cache)) tid = tid_cache;      // consecutive lines share a contig
-            else for (int c = 0; c < names.n; c++) if (same(c)) { tid = c; break; }   // first @SQ with that name (sam_hdr_name2tid)
-            if (tid >= 0) tid_cache = tid;
-        }
-        r.tid = tid;
+    size_t rname0 = p0, rname_len = p - p0;
+    if (rname_len == 1 && cur.at(p0) == '*') r.tid = -1;
+    else {
+        r.tid = name_lookup(cur, p0, rname_len, names, tid_cache);
+        if (r.tid < 0) return SSB_E_FORMAT;          // htslib would warn and print '*': not a pass-through
+        tid_cache = r.tid;
     }
     p++;
     // POS
-    p0 = p; uint64_t pv = 0;
-    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '0' || c > '9') return SSB_E_FORMAT; pv = pv * 10 + (c - '0'); if (pv > 0x7fffffffull) return SSB_E_FORMAT; p++; }
-    if (p >= e || p == p0) return SSB_E_FORMAT;
-    r.pos = (int32_t)pv - 1; p++;
+    if (parse_udec(cur, p, e, 0x7fffffffull, v)) return SSB_E_FORMAT;
+    r.pos = (int32_t)v - 1; p++;
     // MAPQ
-    p0 = p; v = 0;
-    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '0' || c > '9') return SSB_E_FORMAT; v = v * 10 + (c - '0'); if (v > 255) return SSB_E_FORMAT; p++; }
-    if (p >= e || p == p0) return SSB_E_FORMAT;
+    if (parse_udec(cur, p, e, 255, v)) return SSB_E_FORMAT;
     r.mapq = (uint8_t)v; p++;
     // CIGAR
     p0 = p;
     uint64_t rlen = 0, qlen = 0; bool has_cigar = true;
     if (cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { has_cigar = false; p++; }
     else {
-        uint64_t num = 0; bool have = false;
+        uint64_t num = 0; int nd = 0; uint8_t first = 0;
         while (p < e) {
             uint8_t c = cur.at(p);
             if (c == '\t') break;
-            if (c >= '0' && c <= '9') { num = num * 10 + (c - '0'); have = true; if (num > 0x0fffffffull) return SSB_E_FORMAT; }
+            if (c >= '0' && c <= '9') { if (!nd) first = c; num = num * 10 + (c - '0'); nd++; if (num > 0x0fffffffull) return SSB_E_FORMAT; }
             else {
-                if (!have) return SSB_E_FORMAT;
+                if (!nd || (nd > 1 && first == '0')) return SSB_E_FORMAT;
                 switch (c) {
                 case 'M': case '=': case 'X': rlen += num; qlen += num; break;
                 case 'D': case 'N': rlen += num; break;
@@ -132,23 +198,39 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
                 case 'H': case 'P': break;
                 default: return SSB_E_FORMAT;
                 }
-                num = 0; have = false;
+                num = 0; nd = 0;
             }
             p++;
         }
-        if (have) return SSB_E_FORMAT;
+        if (nd) return SSB_E_FORMAT;
     }
     if (p >= e || p == p0 || p - p0 > 65535 || p0 - s > 65535) return SSB_E_FORMAT;
     r.cigar_off = (uint16_t)(p0 - s); r.cigar_len = has_cigar ? (uint16_t)(p - p0) : 0;
-    if ((uint64_t)r.pos + rlen > 0x7fffffffull) return SSB_E_FORMAT;
+    if (r.pos < 0 && rlen) return SSB_E_FORMAT;
+    if ((uint64_t)(r.pos < 0 ? 0 : r.pos) + rlen > 0x7ffffff0ull) return SSB_E_FORMAT;
     r.end = r.pos + (int32_t)rlen;
     p++;
-    // RNEXT, PNEXT, TLEN: not needed, only delimited
-    for (int k = 0; k < 3; k++) { p0 = p; while (p < e && cur.at(p) != '\t') p++; if (p >= e || p == p0) return SSB_E_FORMAT; p++; }
+    // RNEXT: '*', '=' or another @SQ name (the same name spelled out would be printed back as '=')
+    p0 = p;
+    while (p < e && cur.at(p) != '\t') p++;
+    if (p >= e || p == p0) return SSB_E_FORMAT;
+    if (!(p - p0 == 1 && (cur.at(p0) == '*' || cur.at(p0) == '='))) {
+        int mt = name_lookup(cur, p0, p - p0, names, -1);
+        if (mt < 0 || mt == r.tid) return SSB_E_FORMAT;
+    } else if (cur.at(p0) == '=' && r.tid < 0) return SSB_E_FORMAT;
+    (void)rname0;
+    p++;
+    // PNEXT
+    if (parse_udec(cur, p, e, 0x7fffffffull, v)) return SSB_E_FORMAT;
+    p++;
+    // TLEN
+    if (p < e && cur.at(p) == '-') { p++; if (p < e && cur.at(p) == '0') return SSB_E_FORMAT; }
+    if (parse_udec(cur, p, e, 0x7fffffffull, v)) return SSB_E_FORMAT;
+    p++;
     // SEQ
     r.seq_off = (uint32_t)(p - s);
     p0 = p;
-    if (cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { r.l_seq = 0; p++; }
+    if (p < e && cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { r.l_seq = 0; p++; }
     else {
         while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (!seq_char_ok(c)) return SSB_E_FORMAT; p++; }
         r.l_seq = (uint32_t)(p - p0);
@@ -165,13 +247,24 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
         qend = p + r.l_seq;
         if (r.l_seq == 0 || qend > e) return SSB_E_FORMAT;
         if (qend < e && cur.at(qend) != '\t') return SSB_E_FORMAT;  // htslib: "SEQ and QUAL are of different length"
+        for (size_t i = p; i < qend; i++) { uint8_t c = cur.at(i); if (c < '!' || c > '~') return SSB_E_FORMAT; }
     }
-    if (e > s && cur.at(e - 1) == '\r') return SSB_E_FORMAT;          // CRLF input is outside the byte-exact pass-through envelope
-    // read_bam (stochasticSpike.c:253-263) + bam_plp_push's tid/unmapped test
+    // optional fields
+    p = qend;
+    while (p < e) {
+        size_t a = p + 1, q = a;                    // cur.at(p) == '\t'
+        while (q < e && cur.at(q) != '\t') q++;
+        if (aux_ok(cur, a, q)) return SSB_E_FORMAT;
+        p = q;
+    }
+    // read_bam (stochasticSpike.c:253-263) + bam_plp_push's tid test
     bool pass = !(r.flag & (4 | 256 | 512 | 1024)) && r.mapq >= 30 && !((r.flag & 1) && !(r.flag & 2));
     if (pass && r.tid >= 0) {
         r.bits |= REC_PUSHED;
-        if (r.end > r.pos) r.bits |= REC_KEEP;
+        if (r.end > r.pos) {
+            if (r.l_seq == 0) return SSB_E_FORMAT;  // a kept read without SEQ makes the reference read outside its buffer
+            r.bits |= REC_KEEP;
+        }
     }
     return 0;
 }

@@ -1,0 +1,1222 @@
+// spike.cu -- stochastic spike-in on B200 (hot path 1).
+//
+// Replaces the per-locus pileup loop of stochasticSpike.c:1129-1623 for SAM text input, as a
+// per-read / per-target pipeline (legal because of the facts listed in DESIGN.md section 3):
+//
+//   parse      one streaming pass over the SAM text -> 64-byte SamRec per line (sam_parse.cuh)
+//   keep/sort  read_bam filter flags -> kept ordinals (scan), coordinate-sortedness check
+//   mates      per kept read: the next kept read with the same QNAME inside its reference span
+//   cover      union of [pos,end) over kept reads -> covered runs, covered-locus ordinals, stats
+//   order      stable order of kept reads by (tid,end) = the reference's write order (:1272-1285,:1362-1371)
+//   emit       copy every kept line to its output slot
+//   targets    which .spike records hit a covered locus / are passed over (max-plus scan of :1578-1619)
+//   gather     pileup entries (qpos, base, BQ, mate) of the hit targets, in pileup order
+//   rng        glibc rand() stream, generated in parallel by polynomial skip-ahead (rng_glibc.cuh)
+//   chain      the inherently serial part: walk the covered loci consuming selectMutantAllele draws
+//              (:1197), and at each hit target run attemptToMutateBase (:526-904) over its entries
+//   patch      substitute the spiked bases in the emitted text (SEQ only, QUAL untouched)
+//
+// No CPU fallback: every stage above is a CUDA kernel (CUB device scans/sorts are used for plumbing).
+#include "common.cuh"
+#include "spike_types.cuh"
+#include "rng_glibc.cuh"
+#include "sam_parse.cuh"
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace {
+
+constexpr int MAX_PILEUP = 10000;                 // stochasticSpike.c:38
+constexpr int RNG_SEG    = 1024;                  // rand() outputs generated per thread
+constexpr int RNG_TPB    = 256;                   // threads per block of the generator
+constexpr uint64_t RNG_BLOCK = (uint64_t)RNG_SEG * RNG_TPB;
+
+struct DevErr { int code; int pad; unsigned long long where; };
+
+__device__ __forceinline__ void set_err(DevErr *e, int code, unsigned long long where)
+{
+    if (atomicCAS(&e->code, 0, code) == 0) e->where = where;
+}
+
+// ------------------------------------------------------------------------------------------
+// keep flags / sortedness keys
+// ------------------------------------------------------------------------------------------
+__global__ void flags_kernel(const SamRec *__restrict__ recs, size_t n, uint32_t *__restrict__ keep, unsigned long long *__restrict__ pkey)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t bits = recs[i].bits;
+    keep[i] = (bits & REC_KEEP) ? 1u : 0u;
+    // bam_plp_push compares (tid, pos) of every pushed read with the running maximum
+    pkey[i] = (bits & REC_PUSHED) ? (((unsigned long long)(uint32_t)(recs[i].tid + 1) << 32) | (uint32_t)recs[i].pos) : 0ull;
+}
+
+struct MaxOp { template <typename T> __device__ __forceinline__ T operator()(const T &a, const T &b) const { return a > b ? a : b; } };
+
+__global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ kord,
+                               const unsigned long long *__restrict__ pkey, const unsigned long long *__restrict__ pmax,
+                               uint32_t *__restrict__ k_rec, unsigned long long *__restrict__ k_start, unsigned long long *__restrict__ k_end,
+                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ fold, unsigned int *__restrict__ maxspan, DevErr *err)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long span = 0;
+    if (i < n) {
+        if (pkey[i] && pkey[i] < pmax[i]) set_err(err, SSB_E_UNSORTED, recs[i].line_off);
+        if (keep[i]) {
+            const SamRec r = recs[i];
+            const uint32_t o = kord[i];
+            k_rec[o] = (uint32_t)i;
+            k_start[o] = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.pos;
+            k_end[o] = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.end;
+            k_len[o] = r.line_len + ((r.bits & REC_NO_NL) ? 1u : 0u);
+            span = (unsigned long long)(r.end - r.pos);
+        }
+    }
+    // totalFoldCoverage = sum of reference spans of kept reads (stochasticSpike.c:1259)
+    unsigned long long s = span;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    unsigned int m = (unsigned int)span;
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) { if (s) atomicAdd(fold, s); if (m) atomicMax(maxspan, m); }
+}
+
+// ------------------------------------------------------------------------------------------
+// mates: nxt[o] = first kept read after o (file order) with the same QNAME whose start lies inside
+// o's reference span, NO_MATE if none; bit 31 flags "a second such read exists" (then users rescan).
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t NO_MATE = 0x7fffffffu, MATE_MORE = 0x80000000u;
+
+__device__ bool same_qname(const uint8_t *sam, const SamRec &a, const SamRec &b)
+{
+    if (a.qhash != b.qhash || a.qname_len != b.qname_len) return false;
+    const uint8_t *x = sam + a.line_off, *y = sam + b.line_off;
+    for (int i = 0; i < a.qname_len; i++) if (x[i] != y[i]) return false;
+    return true;
+}
+
+__global__ void mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
+                             const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ k_end,
+                             const unsigned long long *__restrict__ k_hash, size_t K, uint32_t *__restrict__ nxt)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= K) return;
+    const unsigned long long lim = k_end[o];       // same tid, pos < end  <=>  start key < end key
+    const unsigned long long h = k_hash[o];
+    uint32_t first = NO_MATE; bool more = false;
+    for (size_t b = o + 1; b < K && k_start[b] < lim; b++) {
+        if (k_hash[b] != h) continue;
+        if (!same_qname(sam, recs[k_rec[o]], recs[k_rec[b]])) continue;
+        if (first == NO_MATE) first = (uint32_t)b; else { more = true; break; }
+    }
+    nxt[o] = first | (more ? MATE_MORE : 0u);
+}
+
+__global__ void khash_kernel(const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec, size_t K, unsigned long long *__restrict__ k_hash)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < K) k_hash[o] = recs[k_rec[o]].qhash;
+}
+
+// ------------------------------------------------------------------------------------------
+// coverage runs
+// ------------------------------------------------------------------------------------------
+__global__ void runflag_kernel(const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ pm, size_t K, uint32_t *__restrict__ flag)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < K) flag[o] = (o == 0 || k_start[o] > pm[o]) ? 1u : 0u;       // new run: other contig, or a gap before this read
+}
+
+__global__ void runs_kernel(const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ k_end,
+                            const unsigned long long *__restrict__ pm, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ rid_incl,
+                            size_t K, CovRun *__restrict__ runs, unsigned long long *__restrict__ run_len)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= K) return;
+    if (flag[o]) {
+        uint32_t r = rid_incl[o] - 1;
+        runs[r].tid = (int32_t)(k_start[o] >> 32);
+        runs[r].start = (int32_t)(uint32_t)k_start[o];
+        if (o > 0) runs[r - 1].end = (int32_t)(uint32_t)pm[o];
+    }
+    if (o == K - 1) {
+        // lexicographic max of (tid,end) over all kept reads = (last contig, end of its last run)
+        const unsigned long long m = pm[o] > k_end[o] ? pm[o] : k_end[o];
+        runs[rid_incl[o] - 1].end = (int32_t)(uint32_t)m;
+    }
+    (void)run_len;
+}
+
+__global__ void runlen_kernel(const CovRun *__restrict__ runs, size_t R, unsigned long long *__restrict__ len)
+{
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) len[r] = (unsigned long long)(runs[r].end - runs[r].start);
+}
+__global__ void runbase_kernel(CovRun *__restrict__ runs, size_t R, const unsigned long long *__restrict__ base)
+{
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) { runs[r].base = (int64_t)base[r]; runs[r].pad = 0; }
+}
+
+// run index containing covered ordinal g (runs sorted by base)
+__device__ __forceinline__ size_t run_of_ordinal(const CovRun *runs, size_t R, int64_t g)
+{
+    size_t lo = 0, hi = R;              // last run with base <= g
+    while (hi - lo > 1) { size_t mid = (lo + hi) >> 1; if (runs[mid].base <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// reference class per covered locus: index into "GCAT" (stochasticSpike.c:340), 4 = anything else
+__device__ __forceinline__ uint8_t ref_class(uint8_t c) { return c == 'G' ? 0 : c == 'C' ? 1 : c == 'A' ? 2 : c == 'T' ? 3 : 4; }
+
+__global__ void cls_kernel(const CovRun *__restrict__ runs, size_t R, int64_t n_cov, const uint8_t *const *__restrict__ contig_seq,
+                           const int64_t *__restrict__ contig_len, uint8_t *__restrict__ cls, DevErr *err)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_cov) return;
+    size_t r = run_of_ordinal(runs, R, g);
+    int tid = runs[r].tid; int64_t x = runs[r].start + (g - runs[r].base);
+    const uint8_t *seq = contig_seq[tid];
+    if (!seq || x >= contig_len[tid]) { set_err(err, SSB_E_REF, (unsigned long long)g); cls[g] = 4; return; }
+    cls[g] = ref_class(seq[x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// output order and emit
+// ------------------------------------------------------------------------------------------
+__global__ void iota_kernel(uint32_t *p, size_t n) { size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
+
+__global__ void outlen_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ k_len, size_t K, unsigned long long *__restrict__ len)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < K) len[o] = k_len[perm[o]];
+}
+
+__global__ void ordoff_kernel(const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ out_off, size_t K, unsigned long long *__restrict__ ord_off)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < K) ord_off[perm[o]] = out_off[o];
+}
+
+// One warp per output line: dst-aligned 4-byte stores, source words funnel-shifted into place.
+__global__ void __launch_bounds__(256)
+emit_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
+            const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ out_off, size_t K, uint8_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t o = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); o < K; o += warps) {
+        const SamRec &r = recs[k_rec[perm[o]]];
+        const uint8_t *src = sam + r.line_off;
+        uint8_t *dst = out + out_off[o];
+        const uint32_t len = r.line_len;
+        // head: bytes up to the first 4-byte aligned destination address
+        uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
+        if (head > len) head = len;
+        if ((uint32_t)lane < head) dst[lane] = src[lane];
+        const uint32_t words = (len - head) >> 2;
+        const uint8_t *s0 = src + head;
+        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+        const uint32_t mis = (uint32_t)((uintptr_t)s0 & 3);
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s0 - mis);
+        if (mis == 0) {
+            for (uint32_t w = lane; w < words; w += 32) d4[w] = s4[w];
+        } else {
+            const uint32_t sh = mis * 8;
+            for (uint32_t w = lane; w < words; w += 32) d4[w] = __funnelshift_r(s4[w], s4[w + 1], sh);
+        }
+        const uint32_t done = head + (words << 2);
+        if (done + lane < len) dst[done + lane] = src[done + lane];       // < 4 tail bytes
+        if (lane == 0 && (r.bits & REC_NO_NL)) dst[len] = '\n';
+    }
+}
+
+__global__ void patch_kernel(const Patch *__restrict__ patches, const unsigned int *__restrict__ n_patches, const SamRec *__restrict__ recs,
+                             const uint32_t *__restrict__ k_rec, const unsigned long long *__restrict__ ord_off, uint8_t *__restrict__ out)
+{
+    unsigned int n = *n_patches;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Patch p = patches[i];
+        out[ord_off[p.ord] + recs[k_rec[p.ord]].seq_off + p.qpos] = (uint8_t)p.base;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// depth
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t upper_bound_u64(const unsigned long long *a, size_t n, unsigned long long key)
+{
+    size_t lo = 0, hi = n;                            // first index with a[i] > key
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ size_t lower_bound_u64(const unsigned long long *a, size_t n, unsigned long long key)
+{
+    size_t lo = 0, hi = n;                            // first index with a[i] >= key
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// maxDepth (stochasticSpike.c:1216): the deepest pileup is reached at some read start
+__global__ void depth_kernel(const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ s_end, size_t K,
+                             unsigned int *__restrict__ max_depth)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int d = 0;
+    if (o < K && (o + 1 == K || k_start[o + 1] != k_start[o])) {          // last read of a group of equal starts
+        const unsigned long long key = k_start[o];
+        size_t ended = upper_bound_u64(s_end, K, key);                     // reads with (tid,end) <= (tid,pos): gone before this locus
+        d = (unsigned int)(o + 1 - ended);
+    }
+    for (int s = 16; s; s >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, s));
+    if ((threadIdx.x & 31) == 0 && d) atomicMax(max_depth, d);
+}
+
+// ------------------------------------------------------------------------------------------
+// targets (stochasticSpike.c:1234-1245, :1578-1619, :1630-1646)
+// ------------------------------------------------------------------------------------------
+struct DevTarget { int32_t c_tid; uint32_t thresh; int64_t locus; uint8_t base; uint8_t pad[7]; };
+
+// first covered ordinal whose (tid,pos) >= (c_tid, locus); n_cov if none
+__device__ int64_t lb_ordinal(const CovRun *runs, size_t R, int64_t n_cov, int32_t c_tid, int64_t locus)
+{
+    if (c_tid < 0) return 0;
+    size_t lo = 0, hi = R;                            // first run with (tid, end-1) >= (c_tid, locus)
+    while (lo < hi) {
+        size_t mid = (lo + hi) >> 1;
+        bool before = runs[mid].tid < c_tid || (runs[mid].tid == c_tid && (int64_t)runs[mid].end - 1 < locus);
+        if (before) lo = mid + 1; else hi = mid;
+    }
+    if (lo == R) return n_cov;
+    const CovRun r = runs[lo];
+    if (r.tid == c_tid && locus > r.start) return r.base + (locus - r.start);
+    return r.base;
+}
+
+__global__ void target_lb_kernel(const DevTarget *__restrict__ tg, size_t T, const CovRun *__restrict__ runs, size_t R, int64_t n_cov, long long *__restrict__ v)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) v[t] = (long long)lb_ordinal(runs, R, n_cov, tg[t].c_tid, tg[t].locus) - (long long)t;
+}
+
+// h_t = t + max_{u<=t} (lb_u - u): every target consumes exactly one covered locus (the if-not-while of :1596-1599)
+__global__ void target_status_kernel(const DevTarget *__restrict__ tg, size_t T, const long long *__restrict__ vmax, const CovRun *__restrict__ runs, size_t R,
+                                     int64_t n_cov, ssb_target_result *__restrict__ res, uint32_t *__restrict__ hitflag)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    ssb_target_result r;
+    memset(&r, 0, sizeof r);
+    long long h = vmax[t] + (long long)t;
+    r.locus_index = h;
+    r.rng_offset = -1;
+    uint32_t hit = 0;
+    if (h >= n_cov) { r.status = SSB_T_TAIL; r.at_tid = -1; r.at_pos = -1; r.locus_index = n_cov; }
+    else {
+        size_t ri = run_of_ordinal(runs, R, h);
+        int tid = runs[ri].tid; int64_t pos = runs[ri].start + (h - runs[ri].base);
+        r.at_tid = tid; r.at_pos = pos;
+        if (tid == tg[t].c_tid && pos == tg[t].locus) { r.status = SSB_T_HIT; hit = 1; r.filter = SSB_F_UNDETECTED; }
+        else r.status = (pos == tg[t].locus) ? SSB_T_NOCOV_SILENT : SSB_T_NOCOV;       // :1603
+    }
+    res[t] = r;
+    hitflag[t] = hit;
+}
+
+__global__ void hits_kernel(const DevTarget *__restrict__ tg, size_t T, const uint32_t *__restrict__ hitflag, const uint32_t *__restrict__ hidx,
+                            const ssb_target_result *__restrict__ res, HitTarget *__restrict__ hits)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T || !hitflag[t]) return;
+    HitTarget h;
+    memset(&h, 0, sizeof h);
+    h.locus_index = res[t].locus_index; h.tid = res[t].at_tid; h.pos = (int32_t)res[t].at_pos;
+    h.target = (uint32_t)t; h.thresh = tg[t].thresh; h.base = tg[t].base;
+    hits[hidx[t]] = h;
+}
+
+// ------------------------------------------------------------------------------------------
+// pileup gather at the hit targets
+// ------------------------------------------------------------------------------------------
+// column geometry of one read at reference position x (htslib resolve_cigar semantics)
+__device__ void column_of(const uint8_t *cig, int cig_len, int32_t rpos, int32_t x, uint32_t &qpos, uint8_t &skip)
+{
+    int64_t ref = rpos; uint32_t y = 0;
+    qpos = 0; skip = 0;
+    uint32_t num = 0;
+    for (int i = 0; i < cig_len; i++) {
+        uint8_t c = cig[i];
+        if (c >= '0' && c <= '9') { num = num * 10 + (c - '0'); continue; }
+        uint32_t l = num; num = 0;
+        if (c == 'M' || c == '=' || c == 'X') { if (x < ref + l) { qpos = y + (uint32_t)(x - ref); return; } ref += l; y += l; }
+        else if (c == 'D' || c == 'N') { if (x < ref + l) { skip = 1; qpos = y; return; } ref += l; }
+        else if (c == 'I' || c == 'S') y += l;
+    }
+}
+
+// candidates of a locus: kept reads [lo, hi) by start; an entry is a candidate whose end lies beyond the locus
+__device__ __forceinline__ void cand_range(const unsigned long long *k_start, size_t K, int32_t tid, int32_t pos, unsigned int maxspan, size_t &lo, size_t &hi)
+{
+    const unsigned long long key = ((unsigned long long)(uint32_t)tid << 32) | (uint32_t)pos;
+    int64_t first = (int64_t)pos - (int64_t)maxspan + 1; if (first < 0) first = 0;
+    lo = lower_bound_u64(k_start, K, ((unsigned long long)(uint32_t)tid << 32) | (uint32_t)first);
+    hi = upper_bound_u64(k_start, K, key);
+}
+
+__global__ void gather_count_kernel(const HitTarget *__restrict__ hits, size_t H, const unsigned long long *__restrict__ k_start,
+                                    const unsigned long long *__restrict__ k_end, size_t K, const unsigned int *__restrict__ maxspan,
+                                    unsigned long long *__restrict__ cnt, DevErr *err)
+{
+    const int lane = threadIdx.x & 31;
+    size_t h = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (h >= H) return;
+    size_t lo, hi; cand_range(k_start, K, hits[h].tid, hits[h].pos, *maxspan, lo, hi);
+    const unsigned long long lim = ((unsigned long long)(uint32_t)hits[h].tid << 32) | (uint32_t)hits[h].pos;
+    unsigned int c = 0;
+    for (size_t i = lo + lane; i < hi; i += 32) c += (k_end[i] > lim) ? 1u : 0u;
+    for (int s = 16; s; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if (lane == 0) { cnt[h] = c; if (c > MAX_PILEUP) set_err(err, SSB_E_DEPTH, (unsigned long long)h); }
+}
+
+__global__ void gather_fill_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
+                                   const HitTarget *__restrict__ hits, size_t H, const unsigned long long *__restrict__ k_start,
+                                   const unsigned long long *__restrict__ k_end, size_t K, const unsigned int *__restrict__ maxspan,
+                                   const unsigned long long *__restrict__ eoff, PlpEntry *__restrict__ ent)
+{
+    const int lane = threadIdx.x & 31;
+    size_t h = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (h >= H) return;
+    const int32_t x = hits[h].pos;
+    size_t lo, hi; cand_range(k_start, K, hits[h].tid, x, *maxspan, lo, hi);
+    const unsigned long long lim = ((unsigned long long)(uint32_t)hits[h].tid << 32) | (uint32_t)x;
+    unsigned long long w = eoff[h];
+    for (size_t base = lo; base < hi; base += 32) {
+        size_t i = base + lane;
+        bool in = i < hi && k_end[i] > lim;
+        unsigned m = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const SamRec &r = recs[k_rec[i]];
+            PlpEntry e;
+            e.ord = (uint32_t)i; e.mate = -1; e.pad = 0;
+            const uint8_t *line = sam + r.line_off;
+            column_of(line + r.cigar_off, r.cigar_len, r.pos, x, e.qpos, e.skip);
+            e.base = line[r.seq_off + e.qpos];
+            e.bq = (r.bits & REC_QUALSTAR) ? (uint8_t)0xff : (uint8_t)(line[r.qual_off + e.qpos] - 33);
+            ent[w + __popc(m & ((1u << lane) - 1u))] = e;
+        }
+        w += __popc(m);
+    }
+}
+
+// mate = index, inside the same pileup, of the first later entry with the same QNAME (findOverlappingMate, :363-383)
+__global__ void gather_mate_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
+                                   const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ k_end,
+                                   const unsigned long long *__restrict__ k_hash, size_t K, const uint32_t *__restrict__ nxt,
+                                   const HitTarget *__restrict__ hits, size_t H, const unsigned long long *__restrict__ eoff, PlpEntry *__restrict__ ent)
+{
+    const int lane = threadIdx.x & 31;
+    size_t h = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (h >= H) return;
+    const unsigned long long e0 = eoff[h], e1 = eoff[h + 1];
+    const unsigned long long lim = ((unsigned long long)(uint32_t)hits[h].tid << 32) | (uint32_t)hits[h].pos;
+    for (unsigned long long j = e0 + lane; j < e1; j += 32) {
+        const uint32_t a = ent[j].ord;
+        uint32_t n1 = nxt[a];
+        uint32_t mate_ord = NO_MATE;
+        if ((n1 & ~MATE_MORE) != NO_MATE) {
+            uint32_t b = n1 & ~MATE_MORE;
+            if (k_start[b] <= lim && k_end[b] > lim) mate_ord = b;          // the first same-name read covers the locus
+            else if ((n1 & MATE_MORE) && k_start[b] <= lim) {
+                // rare: several same-name reads start inside a's span; take the first one that covers the locus
+                for (size_t c = b + 1; c < K && k_start[c] <= lim; c++)
+                    if (k_hash[c] == k_hash[a] && k_end[c] > lim && same_qname(sam, recs[k_rec[a]], recs[k_rec[c]])) { mate_ord = (uint32_t)c; break; }
+            }
+        }
+        if (mate_ord != NO_MATE) {
+            // entries are sorted by ord: binary search inside (j, e1)
+            unsigned long long lo = j + 1, hi = e1;
+            while (lo < hi) { unsigned long long mid = (lo + hi) >> 1; if (ent[mid].ord < mate_ord) lo = mid + 1; else hi = mid; }
+            if (lo < e1 && ent[lo].ord == mate_ord) ent[j].mate = (int32_t)(lo - e0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// glibc rand() stream
+// ------------------------------------------------------------------------------------------
+struct RngTables {
+    uint32_t seg[RNG_TPB][GLIBC_DEG];     // x^(t * RNG_SEG) mod P
+};
+
+// out[k] = rand() #k for k in [0, M): thread (b, t) produces outputs [b*RNG_BLOCK + t*RNG_SEG, +RNG_SEG)
+__global__ void __launch_bounds__(RNG_TPB)
+rng_fill_kernel(const uint32_t *__restrict__ block_poly /* [nblocks][31]: x^(310 + k_base + b*RNG_BLOCK) */, const RngTables *__restrict__ tab,
+                const uint32_t *__restrict__ seedw /* 61 words */, int32_t *__restrict__ out /* out[i] = rand() #(k_base + i) */, unsigned long long M)
+{
+    __shared__ uint32_t s_w[61];
+    __shared__ uint32_t s_bp[GLIBC_DEG];
+    if (threadIdx.x < 61) s_w[threadIdx.x] = seedw[threadIdx.x];
+    if (threadIdx.x < GLIBC_DEG) s_bp[threadIdx.x] = block_poly[(size_t)blockIdx.x * GLIBC_DEG + threadIdx.x];
+    __syncthreads();
+    const unsigned long long k0 = (unsigned long long)blockIdx.x * RNG_BLOCK + (unsigned long long)threadIdx.x * RNG_SEG;
+    if (k0 >= M) return;
+    uint32_t a[GLIBC_DEG], b[GLIBC_DEG], c[GLIBC_DEG], h[GLIBC_DEG];
+    for (int i = 0; i < GLIBC_DEG; i++) { a[i] = s_bp[i]; b[i] = tab->seg[threadIdx.x][i]; }
+    glibc_poly_mulmod(a, b, c);
+    glibc_history(c, s_w, h);                        // h[t] = r[344 + k0 - 31 + t]
+    unsigned long long k = k0;
+    const unsigned long long kend = (k0 + RNG_SEG < M) ? k0 + RNG_SEG : M;
+    while (k < kend) {
+#pragma unroll
+        for (int i = 0; i < GLIBC_DEG; i++) {        // new word replaces r[n-31]; r[n-3] sits three slots back
+            h[i] = h[i] + h[(i + 28) % GLIBC_DEG];
+            if (k < kend) out[k] = (int32_t)(h[i] >> 1);
+            k++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the chain: one warp.  Walks covered loci consuming selectMutantAllele draws and applies the hit
+// targets in order.  Everything the warp decides is uniform across lanes except the entry batches.
+// ------------------------------------------------------------------------------------------
+struct ChainArgs {
+    const uint8_t *cls; int64_t n_cov;
+    const int32_t *R; unsigned long long M;
+    const HitTarget *hits; size_t H;
+    const unsigned long long *eoff; PlpEntry *ent; uint8_t *hflag;
+    ssb_target_result *res;
+    Patch *patches; unsigned int *n_patches; unsigned int patch_cap;
+    const uint8_t *const *contig_seq;
+    unsigned long long *draws_out; DevErr *err;
+};
+
+struct DrawWin { unsigned long long kw; uint32_t e0, e1, ej; };
+struct RefWin { int64_t gw; uint32_t c0, c1, cx; };
+
+__device__ __forceinline__ void load_draws(const ChainArgs &A, unsigned long long kw, DrawWin &W, int lane)
+{
+    unsigned long long k = kw + lane;
+    uint32_t r = k < A.M ? (uint32_t)A.R[k] : 0u;
+    W.kw = kw;
+    W.ej = __ballot_sync(0xffffffffu, r >= GLIBC_CUT4);
+    W.e0 = __ballot_sync(0xffffffffu, r & 1u);
+    W.e1 = __ballot_sync(0xffffffffu, r & 2u);
+}
+__device__ __forceinline__ void load_ref(const ChainArgs &A, int64_t gw, RefWin &W, int lane)
+{
+    int64_t g = gw + lane;
+    uint32_t c = g < A.n_cov ? A.cls[g] : 4u;
+    W.gw = gw;
+    W.cx = __ballot_sync(0xffffffffu, c == 4u);
+    W.c0 = __ballot_sync(0xffffffffu, c & 1u);
+    W.c1 = __ballot_sync(0xffffffffu, c & 2u);
+}
+
+// Consumes the draws of covered loci [g, g_to): per locus, rand() until the pick differs from the
+// reference base (selectMutantAllele/randomNum, stochasticSpike.c:283-302,338-360).  Returns false on stream overrun.
+__device__ bool chain_walk(const ChainArgs &A, int64_t &g, int64_t g_to, unsigned long long &k, DrawWin &D, RefWin &F, int lane)
+{
+    while (g < g_to) {
+        if (g - F.gw >= 32 || g < F.gw) load_ref(A, g, F, lane);
+        if (k - D.kw >= 32 || k < D.kw) { if (k + 32 > A.M) return false; load_draws(A, k, D, lane); }
+        const uint32_t b = (uint32_t)(g - F.gw), a = (uint32_t)(k - D.kw);
+        uint32_t n = 32 - a; if (32 - b < n) n = 32 - b; if ((uint64_t)(g_to - g) < n) n = (uint32_t)(g_to - g);
+        // lock step: draw a+i against locus b+i; bit set = that draw ends that locus
+        const uint32_t term = ((((D.e0 >> a) ^ (F.c0 >> b)) | ((D.e1 >> a) ^ (F.c1 >> b)) | (F.cx >> b)) & ~(D.ej >> a));
+        uint32_t t = __ffs(~term) - 1;                 // trailing ones; 32 when all set (ffs(0) = 0 -> 0xffffffff)
+        if (~term == 0u) t = 32;
+        if (t >= n) { g += n; k += n; continue; }
+        g += t; k += t;
+        // the draw at k repeats the reference base of locus g (or was rejected): keep drawing for this locus
+        const uint32_t bb = b + t;
+        const uint32_t c0 = (F.c0 >> bb) & 1u ? 0xffffffffu : 0u, c1 = (F.c1 >> bb) & 1u ? 0xffffffffu : 0u, cx = (F.cx >> bb) & 1u ? 0xffffffffu : 0u;
+        for (;;) {
+            if (k - D.kw >= 32) { if (k + 32 > A.M) return false; load_draws(A, k, D, lane); }
+            const uint32_t aa = (uint32_t)(k - D.kw);
+            const uint32_t ends = (((D.e0 ^ c0) | (D.e1 ^ c1) | cx) & ~D.ej) >> aa;
+            if (ends == 0u) { k = D.kw + 32; continue; }
+            k += __ffs(ends);                          // the ending draw is consumed too
+            break;
+        }
+        g += 1;
+    }
+    return true;
+}
+
+// one rand() value; lanes agree
+__device__ __forceinline__ bool next_rand(const ChainArgs &A, unsigned long long &k, uint32_t &r)
+{
+    if (k >= A.M) return false;
+    r = (uint32_t)A.R[k++];
+    return true;
+}
+// selectMutantAllele(wild) (:338-360): index into "GCAT" of the pick; wild_idx 4 = not one of GCAT
+__device__ __forceinline__ bool select_allele(const ChainArgs &A, unsigned long long &k, uint32_t wild_idx, uint32_t &pick)
+{
+    for (;;) {
+        uint32_t r;
+        if (!next_rand(A, k, r)) return false;
+        if (r >= GLIBC_CUT4) continue;
+        if ((r & 3u) != wild_idx) { pick = r & 3u; return true; }
+    }
+}
+
+__device__ __forceinline__ int gcat_index(uint8_t b) { return b == 'G' ? 0 : b == 'C' ? 1 : b == 'A' ? 2 : b == 'T' ? 3 : 4; }
+
+// Outcome of one pileup entry at a target locus, computed without side effects so that a warp can
+// evaluate 32 entries speculatively (attemptToMutateBase, stochasticSpike.c:526-904; cases as in SURVEY App. A).
+struct EntryOut {
+    uint32_t draws;        // rand() values consumed
+    uint8_t mark_self, mark_mate, filt /* 0 none, 1 P(ass), 2 K(masked), 3 O(vl) */, tally /* 0 none,1 ref,2 mut,3..6 err G,C,A,T */;
+    uint8_t npatch; uint8_t pbase[2]; uint8_t pmate[2];   // patch i: base pbase[i] on (pmate[i] ? mate : self)
+    bool ok;
+};
+
+__device__ EntryOut entry_eval(const ChainArgs &A, const PlpEntry &e, const PlpEntry *ents, const uint8_t *hflags, uint8_t self_handled,
+                               unsigned long long k, uint32_t thresh, uint8_t F, uint8_t Aallele)
+{
+    EntryOut o; o.draws = 0; o.mark_self = o.mark_mate = o.filt = o.tally = o.npatch = 0; o.ok = true;
+    o.pbase[0] = o.pbase[1] = o.pmate[0] = o.pmate[1] = 0;
+    if (e.skip || e.bq == 0 || self_handled) return o;                               // :1270
+    uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
+    if (e.mate >= 0 && !hflags[e.mate]) { M = ents[e.mate].base; mbq = ents[e.mate].bq; }   // getBaseWithRPOcheck :387-432
+    if (M == 'N') mbq = 0;
+    if (R == 'N') rbq = 0;
+    uint8_t base = R;
+    if (M && M != R && mbq > rbq) base = M;
+    if (base == 'N') { o.mark_self = 1; o.mark_mate = M ? 1 : 0; return o; }         // :584-592
+    const unsigned long long k0 = k;
+    uint32_t r;
+    if (!next_rand(A, k, r)) { o.ok = false; return o; }
+    const bool heads = r < thresh;                                                    // coinToss :332-335
+    auto tally_base = [&](uint8_t b) { int gi = gcat_index(b); o.tally = gi < 4 ? (uint8_t)(3 + gi) : 0; };
+    auto other = [&](uint8_t &d) -> bool {                                            // selectMutantAllele(A)
+        uint32_t pick; if (!select_allele(A, k, (uint32_t)gcat_index(Aallele), pick)) return false;
+        d = (uint8_t)"GCAT"[pick]; return true;
+    };
+    if (!heads) {
+        if (base == F) o.tally = 1;
+        else { tally_base(base); o.mark_self = 1; o.mark_mate = M ? 1 : 0; }
+    } else if (!M && R == F) {                                                        // case 1
+        o.pbase[0] = Aallele; o.pmate[0] = 0; o.npatch = 1; o.tally = 2; o.filt = 1; o.mark_self = 1;
+    } else if (!M) {                                                                  // case 2
+        o.filt = 2;
+        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[0] = d; o.pmate[0] = 0; o.npatch = 1; base = d; }
+        tally_base(base); o.mark_self = 1;
+    } else if (R == F && M == F) {                                                    // case 3
+        o.pbase[0] = Aallele; o.pmate[0] = 0; o.pbase[1] = Aallele; o.pmate[1] = 1; o.npatch = 2;
+        o.mark_self = o.mark_mate = 1; o.tally = 2; o.filt = 1;
+    } else if (R == F) {                                                              // case 4 (M != F)
+        o.pbase[0] = Aallele; o.pmate[0] = 0; o.npatch = 1; o.mark_self = 1;
+        if (M == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[1] = d; o.pmate[1] = 1; o.npatch = 2; if (base == M) base = d; }
+        o.mark_mate = 1; o.filt = 3;
+        if (base == F) o.tally = 2; else tally_base(base);
+    } else if (M == F) {                                                              // case 5 (R != F)
+        o.pbase[0] = Aallele; o.pmate[0] = 1; o.npatch = 1; o.mark_mate = 1;
+        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[1] = d; o.pmate[1] = 0; o.npatch = 2; if (base == R) base = d; }
+        o.mark_self = 1; o.filt = 3;
+        if (base == F) o.tally = 2; else tally_base(base);
+    } else {                                                                          // case 6
+        o.filt = 3;
+        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[o.npatch] = d; o.pmate[o.npatch] = 0; o.npatch++; if (base == R) base = d; }
+        if (M == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[o.npatch] = d; o.pmate[o.npatch] = 1; o.npatch++; if (base == M) base = d; }
+        tally_base(base); o.mark_self = o.mark_mate = 1;
+    }
+    o.draws = (uint32_t)(k - k0);
+    return o;
+}
+
+__global__ void __launch_bounds__(32)
+chain_kernel(ChainArgs A)
+{
+    const int lane = threadIdx.x;
+    int64_t g = 0; unsigned long long k = 0;
+    DrawWin D; RefWin F;
+    D.kw = ~0ull >> 1; F.gw = -1000;                 // force the first loads
+    D.e0 = D.e1 = D.ej = F.c0 = F.c1 = F.cx = 0;
+    for (size_t h = 0; h < A.H; h++) {
+        const HitTarget ht = A.hits[h];
+        if (!chain_walk(A, g, ht.locus_index, k, D, F, lane)) { if (lane == 0) set_err(A.err, SSB_E_STATE, k); return; }
+        // ---- the target locus itself -----------------------------------------------------------
+        const unsigned long long k_at = k;
+        const uint8_t Fb = A.contig_seq[ht.tid][ht.pos];
+        uint32_t pick;
+        if (!select_allele(A, k, A.cls[g], pick)) { if (lane == 0) set_err(A.err, SSB_E_STATE, k); return; }     // :1197
+        uint8_t allele = (uint8_t)"GCAT"[pick];
+        if (ht.base == 'G' || ht.base == 'C' || ht.base == 'A' || ht.base == 'T') allele = ht.base;                // :1199-1203
+        const unsigned long long e0 = A.eoff[h], e1 = A.eoff[h + 1];
+        PlpEntry *ents = A.ent + e0;
+        uint8_t *hf = A.hflag + e0;
+        const uint32_t n = (uint32_t)(e1 - e0);
+        uint32_t ref_cnt = 0, mut_cnt = 0, err0 = 0, err1 = 0, err2 = 0, err3 = 0, fP = 0, fK = 0, fO = 0;
+        uint32_t j0 = 0;
+        while (j0 < n) {
+            const uint32_t j = j0 + lane;
+            const bool in = j < n;
+            PlpEntry e; e.skip = 1; e.bq = 0; e.mate = -1; e.base = 0; e.ord = 0; e.qpos = 0;
+            if (in) e = ents[j];
+            const uint8_t handled = in ? hf[j] : 1;
+            // does this entry toss (or otherwise act)?  needed to give every lane its draw index
+            bool tosses = false;
+            if (in && !e.skip && e.bq != 0 && !handled) {
+                uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
+                if (e.mate >= 0 && !hf[e.mate]) { M = ents[e.mate].base; mbq = ents[e.mate].bq; }
+                if (M == 'N') mbq = 0;
+                if (R == 'N') rbq = 0;
+                uint8_t base = R; if (M && M != R && mbq > rbq) base = M;
+                tosses = base != 'N';
+            }
+            const unsigned tossmask = __ballot_sync(0xffffffffu, tosses);
+            const unsigned long long my_k = k + __popc(tossmask & ((1u << lane) - 1u));
+            EntryOut o = entry_eval(A, e, ents, hf, handled, my_k, ht.thresh, Fb, allele);
+            // a lane "breaks" the speculation of the lanes after it when it used more than its one draw, or
+            // when it marks an entry of this batch as handled
+            const bool marks_in_batch = in && o.mark_mate && e.mate >= 0 && (uint32_t)e.mate < j0 + 32;
+            const bool breaks = !o.ok || o.draws > (tosses ? 1u : 0u) || marks_in_batch;
+            const unsigned bmask = __ballot_sync(0xffffffffu, breaks);
+            const uint32_t last = bmask ? (uint32_t)(__ffs(bmask) - 1) : 31u;         // commit lanes [0, last]
+            if (__ballot_sync(0xffffffffu, !o.ok && (uint32_t)lane <= last)) { if (lane == 0) set_err(A.err, SSB_E_STATE, k); return; }
+            const bool commit = in && (uint32_t)lane <= last;
+            if (commit) {
+                if (o.mark_self) hf[j] = 1;
+                if (o.mark_mate && e.mate >= 0) hf[e.mate] = 1;
+                for (int p = 0; p < o.npatch; p++) {
+                    unsigned int slot = atomicAdd(A.n_patches, 1u);
+                    if (slot < A.patch_cap) {
+                        const PlpEntry &pe = o.pmate[p] ? ents[e.mate] : e;
+                        Patch pt; pt.ord = pe.ord; pt.qpos = pe.qpos; pt.base = o.pbase[p]; pt.pad = (uint32_t)h;
+                        A.patches[slot] = pt;
+                    }
+                }
+            }
+            const uint32_t used = commit ? o.draws : 0u;
+            uint32_t tot = used;
+            for (int s = 16; s; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+            k += tot;
+            ref_cnt += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 1));
+            mut_cnt += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 2));
+            err0 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 3));
+            err1 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 4));
+            err2 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 5));
+            err3 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 6));
+            fP |= __ballot_sync(0xffffffffu, commit && o.filt == 1);
+            fK |= __ballot_sync(0xffffffffu, commit && o.filt == 2);
+            fO |= __ballot_sync(0xffffffffu, commit && o.filt == 3);
+            __syncwarp();
+            j0 += last + 1;
+        }
+        if (lane == 0) {
+            ssb_target_result &r = A.res[ht.target];
+            r.ref_base = Fb; r.mutant_allele = allele;
+            // the filter only moves UNDETECTED -> PASS (cases 1,3), -> MASKED (case 2, unless MASKED_OVL), -> MASKED_OVL (cases 4-6)
+            r.filter = fO ? SSB_F_MASKED_OVL : fK ? SSB_F_MASKED : fP ? SSB_F_PASS : SSB_F_UNDETECTED;
+            r.ref_cnt = (int32_t)ref_cnt; r.mut_cnt = (int32_t)mut_cnt;
+            r.err_cnt[0] = (int32_t)err0; r.err_cnt[1] = (int32_t)err1; r.err_cnt[2] = (int32_t)err2; r.err_cnt[3] = (int32_t)err3;
+            r.rng_offset = (int64_t)k_at;
+        }
+        g += 1;
+    }
+    if (lane == 0) *A.draws_out = k;
+}
+
+// ------------------------------------------------------------------------------------------
+// device arena: one stream-ordered allocation per array, all released at the end of the run
+// ------------------------------------------------------------------------------------------
+struct Arena {
+    ssb_ctx *ctx; cudaStream_t s; std::vector<void *> ptrs; bool failed = false;
+    template <typename T> T *get(size_t n)
+    {
+        void *p = NULL;
+        if (cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), s) != cudaSuccess) { failed = true; cudaGetLastError(); return NULL; }
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+    ~Arena() { for (void *p : ptrs) cudaFreeAsync(p, s); }
+};
+
+inline int grid_for(size_t n, int block) { size_t g = (n + block - 1) / block; return (int)(g ? g : 1); }
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct ssb_spike {
+    ssb_ctx *ctx;
+    int n_contigs;
+    char *d_names; uint32_t *d_name_off;
+    uint8_t **d_seq_ptrs; int64_t *d_lens;
+    std::vector<uint8_t *> d_seqs;
+    RngTables *d_rng_tab;
+    std::vector<ssb_seq_error> seq_errors;
+};
+
+extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_contigs, ssb_spike **out)
+{
+    if (!ctx || !out || n_contigs < 0 || (n_contigs && !contigs)) return SSB_E_ARG;
+    *out = NULL;
+    SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ssb_spike *sp = new ssb_spike();
+    sp->ctx = ctx; sp->n_contigs = n_contigs;
+    std::vector<char> names; std::vector<uint32_t> off; std::vector<int64_t> lens; std::vector<uint8_t *> ptrs;
+    off.push_back(0);
+    for (int i = 0; i < n_contigs; i++) {
+        const char *nm = contigs[i].name ? contigs[i].name : "";
+        names.insert(names.end(), nm, nm + strlen(nm));
+        off.push_back((uint32_t)names.size());
+        uint8_t *d = NULL;
+        if (contigs[i].seq && contigs[i].len > 0) {
+            SSB_CUDA(ctx, cudaMalloc(&d, (size_t)contigs[i].len));
+            SSB_CUDA(ctx, cudaMemcpy(d, contigs[i].seq, (size_t)contigs[i].len, cudaMemcpyHostToDevice));
+        }
+        sp->d_seqs.push_back(d); ptrs.push_back(d); lens.push_back(d ? contigs[i].len : 0);
+    }
+    SSB_CUDA(ctx, cudaMalloc(&sp->d_names, names.size() + 1));
+    SSB_CUDA(ctx, cudaMalloc(&sp->d_name_off, off.size() * sizeof(uint32_t)));
+    SSB_CUDA(ctx, cudaMalloc(&sp->d_seq_ptrs, (ptrs.size() + 1) * sizeof(uint8_t *)));
+    SSB_CUDA(ctx, cudaMalloc(&sp->d_lens, (lens.size() + 1) * sizeof(int64_t)));
+    if (!names.empty()) SSB_CUDA(ctx, cudaMemcpy(sp->d_names, names.data(), names.size(), cudaMemcpyHostToDevice));
+    SSB_CUDA(ctx, cudaMemcpy(sp->d_name_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (n_contigs) {
+        SSB_CUDA(ctx, cudaMemcpy(sp->d_seq_ptrs, ptrs.data(), ptrs.size() * sizeof(uint8_t *), cudaMemcpyHostToDevice));
+        SSB_CUDA(ctx, cudaMemcpy(sp->d_lens, lens.data(), lens.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    // seed-independent skip-ahead table: x^(t*RNG_SEG) mod P, t < RNG_TPB (host integer arithmetic, a few ms)
+    RngTables *tab = new RngTables();
+    uint32_t step[GLIBC_DEG], cur[GLIBC_DEG], tmp[GLIBC_DEG];
+    glibc_poly_xpow(RNG_SEG, step);
+    glibc_poly_xpow(0, cur);
+    for (int t = 0; t < RNG_TPB; t++) {
+        memcpy(tab->seg[t], cur, sizeof cur);
+        glibc_poly_mulmod(cur, step, tmp); memcpy(cur, tmp, sizeof cur);
+    }
+    SSB_CUDA(ctx, cudaMalloc(&sp->d_rng_tab, sizeof(RngTables)));
+    SSB_CUDA(ctx, cudaMemcpy(sp->d_rng_tab, tab, sizeof(RngTables), cudaMemcpyHostToDevice));
+    delete tab;
+    *out = sp;
+    return SSB_OK;
+}
+
+extern "C" void ssb_spike_destroy(ssb_spike *sp)
+{
+    if (!sp) return;
+    cudaSetDevice(sp->ctx->device);
+    cudaStreamSynchronize(sp->ctx->stream);
+    for (uint8_t *d : sp->d_seqs) if (d) cudaFree(d);
+    cudaFree(sp->d_names); cudaFree(sp->d_name_off); cudaFree(sp->d_seq_ptrs); cudaFree(sp->d_lens); cudaFree(sp->d_rng_tab);
+    delete sp;
+}
+
+#define SPK_CHECK_ARENA(ar) do { if ((ar).failed) { snprintf(ctx->err, sizeof ctx->err, "spike: device allocation failed"); return SSB_E_NOMEM; } } while (0)
+
+namespace {
+
+struct Ev { cudaEvent_t e; };
+
+// CUB wrappers: temp storage from the arena
+template <typename T> int scan_sum(Arena &ar, ssb_ctx *ctx, const T *in, T *out, size_t n)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(NULL, bytes, in, out, n, ar.s);
+    void *tmp = ar.get<uint8_t>(bytes); SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, ar.s));
+    ctx->launches += 2;
+    return SSB_OK;
+}
+template <typename T> int scan_sum_incl(Arena &ar, ssb_ctx *ctx, const T *in, T *out, size_t n)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveSum(NULL, bytes, in, out, n, ar.s);
+    void *tmp = ar.get<uint8_t>(bytes); SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cub::DeviceScan::InclusiveSum(tmp, bytes, in, out, n, ar.s));
+    ctx->launches += 2;
+    return SSB_OK;
+}
+template <typename T> int scan_max_excl(Arena &ar, ssb_ctx *ctx, const T *in, T *out, size_t n, T init)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveScan(NULL, bytes, in, out, MaxOp(), init, n, ar.s);
+    void *tmp = ar.get<uint8_t>(bytes); SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cub::DeviceScan::ExclusiveScan(tmp, bytes, in, out, MaxOp(), init, n, ar.s));
+    ctx->launches += 2;
+    return SSB_OK;
+}
+template <typename T> int scan_max_incl(Arena &ar, ssb_ctx *ctx, const T *in, T *out, size_t n)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveScan(NULL, bytes, in, out, MaxOp(), n, ar.s);
+    void *tmp = ar.get<uint8_t>(bytes); SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cub::DeviceScan::InclusiveScan(tmp, bytes, in, out, MaxOp(), n, ar.s));
+    ctx->launches += 2;
+    return SSB_OK;
+}
+
+int dev_error(ssb_ctx *ctx, cudaStream_t s, DevErr *d_err, const char *stage)
+{
+    DevErr e;
+    SSB_CUDA(ctx, cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, s));
+    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (e.code) { snprintf(ctx->err, sizeof ctx->err, "spike/%s: %s (at %llu)", stage, ssb_strerror(e.code), e.where); return e.code; }
+    return SSB_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+} // namespace
+
+extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t n, uint8_t *d_out, size_t out_cap,
+                                    const ssb_target *targets, size_t n_targets, unsigned seed,
+                                    ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes)
+{
+    if (!sp || (!d_sam && n) || (!d_out && n) || (n_targets && (!targets || !results)) || !stats || !out_bytes) return SSB_E_ARG;
+    if (((uintptr_t)d_sam & 15) != 0) return SSB_E_ARG;
+    ssb_ctx *ctx = sp->ctx;
+    SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    memset(stats, 0, sizeof *stats);
+    *out_bytes = 0;
+    sp->seq_errors.clear();
+    stats->in_bytes = (int64_t)n;
+    const size_t T = n_targets;
+    cudaEvent_t ev[12];
+    for (int i = 0; i < 12; i++) SSB_CUDA(ctx, cudaEventCreate(&ev[i]));
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 12; i++) cudaEventDestroy(e[i]); } } evg{ev};
+    Arena ar; ar.ctx = ctx; ar.s = s;
+
+    DevErr *d_err = ar.get<DevErr>(1); SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(DevErr), s));
+    SSB_CUDA(ctx, cudaEventRecord(ev[0], s));
+
+    // ---------------------------------------------------------------- parse
+    size_t N = 0;
+    SamRec *recs = NULL;
+    if (n) {
+        const size_t n_tiles = (n + samparse::TILE - 1) / samparse::TILE;
+        unsigned long long *tile_state = ar.get<unsigned long long>(n_tiles);
+        unsigned int *ticket = ar.get<unsigned int>(1);
+        unsigned long long *d_nlines = ar.get<unsigned long long>(1);
+        SPK_CHECK_ARENA(ar);
+        size_t rec_cap = n / 96 + 4096;
+        SSB_CUDA(ctx, cudaFuncSetAttribute(samparse::parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, samparse::SMEM_BYTES));
+        for (int attempt = 0; attempt < 2; attempt++) {
+            recs = ar.get<SamRec>(rec_cap); SPK_CHECK_ARENA(ar);
+            SSB_CUDA(ctx, cudaMemsetAsync(tile_state, 0, n_tiles * sizeof(unsigned long long), s));
+            SSB_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
+            SSB_CUDA(ctx, cudaMemsetAsync(d_nlines, 0, sizeof(unsigned long long), s));
+            SSB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(DevErr), s));
+            samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs};
+            int grid = (int)(n_tiles < (size_t)ctx->sm_count * 4 ? n_tiles : (size_t)ctx->sm_count * 4);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_PARSE, samparse::parse_kernel, grid, samparse::THREADS, samparse::SMEM_BYTES, s,
+                         d_sam, n, names, recs, rec_cap, tile_state, ticket, d_nlines, reinterpret_cast<SpikeErr *>(d_err));
+            unsigned long long nl = 0; DevErr e;
+            SSB_CUDA(ctx, cudaMemcpyAsync(&nl, d_nlines, sizeof nl, cudaMemcpyDeviceToHost, s));
+            SSB_CUDA(ctx, cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, s));
+            SSB_CUDA(ctx, cudaStreamSynchronize(s));
+            N = (size_t)nl;
+            if (e.code == SSB_E_NOMEM && attempt == 0) { rec_cap = N + 16; continue; }
+            if (e.code) { snprintf(ctx->err, sizeof ctx->err, "spike/parse: %s (SAM body offset %llu)", ssb_strerror(e.code), e.where); return e.code; }
+            break;
+        }
+    }
+    stats->n_lines = (int64_t)N;
+    SSB_CUDA(ctx, cudaEventRecord(ev[1], s));
+
+    // ---------------------------------------------------------------- keep / sortedness / compaction
+    size_t K = 0;
+    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL; unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL;
+    unsigned long long *d_fold = ar.get<unsigned long long>(1); unsigned int *d_maxspan = ar.get<unsigned int>(1), *d_maxdepth = ar.get<unsigned int>(1);
+    SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cudaMemsetAsync(d_fold, 0, sizeof(unsigned long long), s));
+    SSB_CUDA(ctx, cudaMemsetAsync(d_maxspan, 0, sizeof(unsigned int), s));
+    SSB_CUDA(ctx, cudaMemsetAsync(d_maxdepth, 0, sizeof(unsigned int), s));
+    if (N) {
+        uint32_t *keep = ar.get<uint32_t>(N), *kord = ar.get<uint32_t>(N);
+        unsigned long long *pkey = ar.get<unsigned long long>(N), *pmax = ar.get<unsigned long long>(N);
+        SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, flags_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, pkey);
+        int rc;
+        if ((rc = scan_sum(ar, ctx, keep, kord, N))) return rc;
+        if ((rc = scan_max_excl(ar, ctx, pkey, pmax, N, 0ull))) return rc;
+        uint32_t last_ord = 0, last_keep = 0;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&last_ord, kord + N - 1, 4, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(&last_keep, keep + N - 1, 4, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        K = (size_t)last_ord + last_keep;
+        k_rec = ar.get<uint32_t>(K); k_len = ar.get<uint32_t>(K); nxt = ar.get<uint32_t>(K);
+        k_start = ar.get<unsigned long long>(K); k_end = ar.get<unsigned long long>(K); k_hash = ar.get<unsigned long long>(K);
+        SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, compact_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, kord, pkey, pmax, k_rec, k_start, k_end, k_len,
+                     d_fold, d_maxspan, d_err);
+        if ((rc = dev_error(ctx, s, d_err, "sorted"))) return rc;
+    }
+    stats->n_kept = (int64_t)K;
+    stats->alignmentCount = (int64_t)K;                                   // every kept read is written exactly once (:1275,:1365)
+    SSB_CUDA(ctx, cudaEventRecord(ev[2], s));
+
+    // ---------------------------------------------------------------- output order + emit
+    size_t R = 0; int64_t n_cov = 0;
+    CovRun *runs = NULL; uint8_t *cls = NULL;
+    uint32_t *perm = NULL; unsigned long long *s_end = NULL, *out_off = NULL, *ord_off = NULL;
+    unsigned long long total_out = 0;
+    if (K) {
+        int rc;
+        uint32_t *iota = ar.get<uint32_t>(K); perm = ar.get<uint32_t>(K); s_end = ar.get<unsigned long long>(K);
+        unsigned long long *olen = ar.get<unsigned long long>(K); out_off = ar.get<unsigned long long>(K); ord_off = ar.get<unsigned long long>(K);
+        SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, iota_kernel, grid_for(K, 256), 256, 0, s, iota, K);
+        int tid_bits = 1; while ((1 << tid_bits) < sp->n_contigs + 1 && tid_bits < 31) tid_bits++;
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(NULL, bytes, k_end, s_end, iota, perm, K, 0, 32 + tid_bits, s);
+        void *tmp = ar.get<uint8_t>(bytes); SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, bytes, k_end, s_end, iota, perm, K, 0, 32 + tid_bits, s));   // stable: ties keep input order
+        ctx->launches += 8;
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, outlen_kernel, grid_for(K, 256), 256, 0, s, perm, k_len, K, olen);
+        if ((rc = scan_sum(ar, ctx, olen, out_off, K))) return rc;
+        unsigned long long last_off = 0, last_len = 0;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&last_off, out_off + K - 1, 8, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(&last_len, olen + K - 1, 8, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        total_out = last_off + last_len;
+        if (total_out > out_cap) { snprintf(ctx->err, sizeof ctx->err, "spike: output needs %llu bytes, capacity %zu", total_out, out_cap); return SSB_E_ARG; }
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, ordoff_kernel, grid_for(K, 256), 256, 0, s, perm, out_off, K, ord_off);
+        SSB_CUDA(ctx, cudaEventRecord(ev[3], s));
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, emit_kernel, ctx->sm_count * 8, 256, 0, s, d_sam, recs, k_rec, perm, out_off, K, d_out);
+    } else SSB_CUDA(ctx, cudaEventRecord(ev[3], s));
+    *out_bytes = (size_t)total_out;
+    stats->out_bytes = (int64_t)total_out;
+    SSB_CUDA(ctx, cudaEventRecord(ev[4], s));
+
+    // ---------------------------------------------------------------- mates, coverage runs, classes, depth
+    if (K) {
+        int rc;
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, khash_kernel, grid_for(K, 256), 256, 0, s, recs, k_rec, K, k_hash);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, mates_kernel, grid_for(K, 128), 128, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash, K, nxt);
+        unsigned long long *pm = ar.get<unsigned long long>(K); uint32_t *rflag = ar.get<uint32_t>(K), *rid = ar.get<uint32_t>(K);
+        SPK_CHECK_ARENA(ar);
+        if ((rc = scan_max_excl(ar, ctx, k_end, pm, K, 0ull))) return rc;
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, runflag_kernel, grid_for(K, 256), 256, 0, s, k_start, pm, K, rflag);
+        if ((rc = scan_sum_incl(ar, ctx, rflag, rid, K))) return rc;
+        uint32_t nruns = 0;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&nruns, rid + K - 1, 4, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        R = nruns;
+        runs = ar.get<CovRun>(R);
+        unsigned long long *rlen = ar.get<unsigned long long>(R), *rbase = ar.get<unsigned long long>(R);
+        SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, runs_kernel, grid_for(K, 256), 256, 0, s, k_start, k_end, pm, rflag, rid, K, runs, rlen);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, runlen_kernel, grid_for(R, 256), 256, 0, s, runs, R, rlen);
+        if ((rc = scan_sum(ar, ctx, rlen, rbase, R))) return rc;
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, runbase_kernel, grid_for(R, 256), 256, 0, s, runs, R, rbase);
+        unsigned long long lb = 0, ll = 0;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&lb, rbase + R - 1, 8, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(&ll, rlen + R - 1, 8, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        n_cov = (int64_t)(lb + ll);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, depth_kernel, grid_for(K, 256), 256, 0, s, k_start, s_end, K, d_maxdepth);
+    }
+    stats->n_runs = (int64_t)R;
+    stats->numberOfLociCovered = n_cov;
+    SSB_CUDA(ctx, cudaEventRecord(ev[5], s));
+
+    // ---------------------------------------------------------------- targets
+    std::vector<DevTarget> ht(T);
+    for (size_t t = 0; t < T; t++) {
+        ht[t].c_tid = targets[t].c_tid; ht[t].locus = targets[t].locus; ht[t].base = targets[t].base;
+        memset(ht[t].pad, 0, sizeof ht[t].pad);
+        const double thr = (double)targets[t].af * 2147483648.0;          // coinToss: rand() < p * (RAND_MAX + 1.0), p a float promoted to double
+        ht[t].thresh = thr > 0 ? (thr >= 2147483648.0 ? 2147483648u : (uint32_t)ceil(thr)) : 0u;
+    }
+    size_t H = 0;
+    HitTarget *hits = NULL; ssb_target_result *d_res = NULL;
+    if (T) {
+        DevTarget *d_tg = ar.get<DevTarget>(T); d_res = ar.get<ssb_target_result>(T);
+        SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_tg, ht.data(), T * sizeof(DevTarget), cudaMemcpyHostToDevice, s));
+        if (n_cov == 0) {
+            for (size_t t = 0; t < T; t++) { memset(&results[t], 0, sizeof results[t]); results[t].status = SSB_T_TAIL; results[t].at_tid = -1; results[t].at_pos = -1; results[t].rng_offset = -1; }
+            SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        } else {
+            int rc;
+            long long *v = ar.get<long long>(T), *vmax = ar.get<long long>(T);
+            uint32_t *hitflag = ar.get<uint32_t>(T), *hidx = ar.get<uint32_t>(T);
+            SPK_CHECK_ARENA(ar);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, target_lb_kernel, grid_for(T, 256), 256, 0, s, d_tg, T, runs, R, n_cov, v);
+            if ((rc = scan_max_incl(ar, ctx, v, vmax, T))) return rc;
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, target_status_kernel, grid_for(T, 256), 256, 0, s, d_tg, T, vmax, runs, R, n_cov, d_res, hitflag);
+            if ((rc = scan_sum(ar, ctx, hitflag, hidx, T))) return rc;
+            uint32_t lh = 0, lf = 0;
+            SSB_CUDA(ctx, cudaMemcpyAsync(&lh, hidx + T - 1, 4, cudaMemcpyDeviceToHost, s));
+            SSB_CUDA(ctx, cudaMemcpyAsync(&lf, hitflag + T - 1, 4, cudaMemcpyDeviceToHost, s));
+            SSB_CUDA(ctx, cudaStreamSynchronize(s));
+            H = (size_t)lh + lf;
+            hits = ar.get<HitTarget>(H); SPK_CHECK_ARENA(ar);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, hits_kernel, grid_for(T, 256), 256, 0, s, d_tg, T, hitflag, hidx, d_res, hits);
+        }
+    }
+    stats->n_hits = (int64_t)H;
+    SSB_CUDA(ctx, cudaEventRecord(ev[6], s));
+
+    // ---------------------------------------------------------------- gather + rng + chain + patch
+    if (H) {
+        int rc;
+        unsigned long long *cnt = ar.get<unsigned long long>(H + 1), *eoff = ar.get<unsigned long long>(H + 1);
+        SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemsetAsync(cnt, 0, (H + 1) * sizeof(unsigned long long), s));
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, gather_count_kernel, grid_for(H * 32, 128), 128, 0, s, hits, H, k_start, k_end, K, d_maxspan, cnt, d_err);
+        if ((rc = scan_sum(ar, ctx, cnt, eoff, H + 1))) return rc;
+        unsigned long long E = 0; HitTarget last_hit;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&E, eoff + H, 8, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(&last_hit, hits + H - 1, sizeof last_hit, cudaMemcpyDeviceToHost, s));
+        if ((rc = dev_error(ctx, s, d_err, "gather"))) return rc;
+        PlpEntry *ent = ar.get<PlpEntry>(E); uint8_t *hflag = ar.get<uint8_t>(E);
+        Patch *patches = ar.get<Patch>(2 * E + 16); unsigned int *n_patches = ar.get<unsigned int>(1);
+        unsigned long long *d_draws = ar.get<unsigned long long>(1);
+        SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, gather_fill_kernel, grid_for(H * 32, 128), 128, 0, s, d_sam, recs, k_rec, hits, H, k_start, k_end, K, d_maxspan, eoff, ent);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, gather_mate_kernel, grid_for(H * 32, 128), 128, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash, K, nxt, hits, H, eoff, ent);
+        // reference classes of the covered loci the chain walks over (up to the last hit)
+        const int64_t n_walk = last_hit.locus_index + 1;
+        cls = ar.get<uint8_t>((size_t)n_walk + 64); SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, cls_kernel, grid_for((size_t)n_walk, 256), 256, 0, s, runs, R, n_walk, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_lens, cls, d_err);
+        if ((rc = dev_error(ctx, s, d_err, "reference"))) return rc;
+        SSB_CUDA(ctx, cudaEventRecord(ev[7], s));
+
+        uint32_t seedw[61];
+        glibc_seed_window(seed, seedw);
+        uint32_t *d_seedw = ar.get<uint32_t>(61); SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_seedw, seedw, sizeof seedw, cudaMemcpyHostToDevice, s));
+        // draws: ~4/3 per walked locus + one per pileup entry (+ extras); grow and redo if the chain runs out
+        unsigned long long M = (unsigned long long)((double)n_walk * 1.40) + 3 * E + 65536;
+        float ms_rng = 0, ms_chain = 0;
+        for (int attempt = 0; attempt < 6; attempt++) {
+            M = (M + RNG_BLOCK - 1) / RNG_BLOCK * RNG_BLOCK;
+            const size_t nblocks = (size_t)(M / RNG_BLOCK);
+            // per-block polynomials x^(310 + b*RNG_BLOCK) mod P: seed independent, built on the host (31x31 products)
+            std::vector<uint32_t> bp(nblocks * GLIBC_DEG);
+            uint32_t stepb[GLIBC_DEG], cur[GLIBC_DEG], tmpb[GLIBC_DEG];
+            glibc_poly_xpow(RNG_BLOCK, stepb);
+            glibc_poly_xpow(310, cur);
+            for (size_t b = 0; b < nblocks; b++) { memcpy(&bp[b * GLIBC_DEG], cur, sizeof cur); glibc_poly_mulmod(cur, stepb, tmpb); memcpy(cur, tmpb, sizeof cur); }
+            uint32_t *d_bp = ar.get<uint32_t>(bp.size()); int32_t *Rs = ar.get<int32_t>(M + 64);
+            SPK_CHECK_ARENA(ar);
+            SSB_CUDA(ctx, cudaMemcpyAsync(d_bp, bp.data(), bp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            SSB_CUDA(ctx, cudaEventRecord(ev[8], s));
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, d_seedw, Rs, M);
+            SSB_CUDA(ctx, cudaEventRecord(ev[9], s));
+            SSB_CUDA(ctx, cudaMemsetAsync(hflag, 0, E, s));
+            SSB_CUDA(ctx, cudaMemsetAsync(n_patches, 0, sizeof(unsigned int), s));
+            ChainArgs A;
+            A.cls = cls; A.n_cov = n_walk; A.R = Rs; A.M = M; A.hits = hits; A.H = H; A.eoff = eoff; A.ent = ent; A.hflag = hflag;
+            A.res = d_res; A.patches = patches; A.n_patches = n_patches; A.patch_cap = (unsigned int)(2 * E + 16);
+            A.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; A.draws_out = d_draws; A.err = d_err;
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, 1, 32, 0, s, A);
+            SSB_CUDA(ctx, cudaEventRecord(ev[10], s));
+            DevErr e;
+            SSB_CUDA(ctx, cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, s));
+            SSB_CUDA(ctx, cudaStreamSynchronize(s));
+            ms_rng += ev_ms(ev[8], ev[9]); ms_chain += ev_ms(ev[9], ev[10]);
+            if (e.code == SSB_E_STATE) {                                   // the stream was too short: double it and redo the chain
+                SSB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(DevErr), s));
+                M *= 2;
+                if (attempt == 5) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: rand() stream exhausted"); return SSB_E_STATE; }
+                continue;
+            }
+            if (e.code) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: %s", ssb_strerror(e.code)); return e.code; }
+            break;
+        }
+        stats->ms_rng = ms_rng; stats->ms_chain = ms_chain;
+        unsigned long long draws = 0;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&draws, d_draws, 8, cudaMemcpyDeviceToHost, s));
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, patch_kernel, 64, 256, 0, s, patches, n_patches, recs, k_rec, ord_off, d_out);
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        stats->rng_draws = (int64_t)draws;
+    } else {
+        SSB_CUDA(ctx, cudaEventRecord(ev[7], s));
+        SSB_CUDA(ctx, cudaEventRecord(ev[10], s));
+    }
+    SSB_CUDA(ctx, cudaEventRecord(ev[11], s));
+    if (T && n_cov) SSB_CUDA(ctx, cudaMemcpyAsync(results, d_res, T * sizeof(ssb_target_result), cudaMemcpyDeviceToHost, s));
+    unsigned long long fold = 0; unsigned int md = 0;
+    SSB_CUDA(ctx, cudaMemcpyAsync(&fold, d_fold, 8, cudaMemcpyDeviceToHost, s));
+    SSB_CUDA(ctx, cudaMemcpyAsync(&md, d_maxdepth, 4, cudaMemcpyDeviceToHost, s));
+    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+    stats->totalFoldCoverage = (int64_t)fold;
+    stats->maxDepth = (int64_t)md;
+    if (md > MAX_PILEUP) { snprintf(ctx->err, sizeof ctx->err, "spike: pileup depth %u exceeds MAX_PILEUP_SIZE", md); return SSB_E_DEPTH; }
+    stats->ms_parse = ev_ms(ev[0], ev[1]);
+    stats->ms_sort = ev_ms(ev[1], ev[3]);
+    stats->ms_emit = ev_ms(ev[3], ev[4]);
+    stats->ms_cover = ev_ms(ev[4], ev[5]);
+    stats->ms_gather = ev_ms(ev[5], ev[7]);
+    stats->ms_patch = H ? ev_ms(ev[10], ev[11]) : 0;
+    stats->ms_total = ev_ms(ev[0], ev[11]);
+    return SSB_OK;
+}
+
+extern "C" int ssb_spike_run_host(ssb_spike *sp, const uint8_t *sam, size_t n, uint8_t *out, size_t out_cap,
+                                  const ssb_target *targets, size_t n_targets, unsigned seed,
+                                  ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes)
+{
+    if (!sp || (!sam && n) || (!out && n) || !stats || !out_bytes) return SSB_E_ARG;
+    ssb_ctx *ctx = sp->ctx;
+    SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint8_t *d_in = NULL, *d_out = NULL;
+    SSB_CUDA(ctx, cudaMallocAsync((void **)&d_in, n + 64, ctx->stream));
+    SSB_CUDA(ctx, cudaMallocAsync((void **)&d_out, n + 64, ctx->stream));
+    if (n) SSB_CUDA(ctx, cudaMemcpyAsync(d_in, sam, n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = ssb_spike_run_device(sp, d_in, n, d_out, n + 1, targets, n_targets, seed, results, stats, out_bytes);
+    if (rc == SSB_OK) {
+        if (*out_bytes > out_cap) { snprintf(ctx->err, sizeof ctx->err, "spike: output needs %zu bytes, capacity %zu", *out_bytes, out_cap); rc = SSB_E_ARG; }
+        else if (*out_bytes) {
+            cudaError_t e = cudaMemcpyAsync(out, d_out, *out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "spike: copy back: %s", cudaGetErrorString(e)); rc = SSB_E_CUDA; }
+        }
+    }
+    cudaFreeAsync(d_in, ctx->stream); cudaFreeAsync(d_out, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
+// rand() #k0 .. #k0+n-1 of srand(seed) (glibc TYPE_3), generated by the same kernel the spike path uses.
+extern "C" int ssb_spike_rand(ssb_spike *sp, unsigned seed, uint64_t k0, size_t n, int32_t *out_host)
+{
+    if (!sp || (!out_host && n)) return SSB_E_ARG;
+    if (!n) return SSB_OK;
+    ssb_ctx *ctx = sp->ctx;
+    SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    Arena ar; ar.ctx = ctx; ar.s = s;
+    const unsigned long long M = (n + RNG_BLOCK - 1) / RNG_BLOCK * RNG_BLOCK;
+    const size_t nblocks = (size_t)(M / RNG_BLOCK);
+    std::vector<uint32_t> bp(nblocks * GLIBC_DEG);
+    uint32_t stepb[GLIBC_DEG], cur[GLIBC_DEG], tmpb[GLIBC_DEG];
+    glibc_poly_xpow(RNG_BLOCK, stepb);
+    glibc_poly_xpow(310 + k0, cur);
+    for (size_t b = 0; b < nblocks; b++) { memcpy(&bp[b * GLIBC_DEG], cur, sizeof cur); glibc_poly_mulmod(cur, stepb, tmpb); memcpy(cur, tmpb, sizeof cur); }
+    uint32_t seedw[61];
+    glibc_seed_window(seed, seedw);
+    uint32_t *d_bp = ar.get<uint32_t>(bp.size()), *d_seedw = ar.get<uint32_t>(61); int32_t *R = ar.get<int32_t>(M);
+    SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cudaMemcpyAsync(d_bp, bp.data(), bp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    SSB_CUDA(ctx, cudaMemcpyAsync(d_seedw, seedw, sizeof seedw, cudaMemcpyHostToDevice, s));
+    SSB_LAUNCH(ctx, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, d_seedw, R, M);
+    SSB_CUDA(ctx, cudaMemcpyAsync(out_host, R, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+    return SSB_OK;
+}
+
+extern "C" int ssb_spike_seq_error_count(ssb_spike *sp, size_t *count)
+{
+    if (!sp || !count) return SSB_E_ARG;
+    *count = sp->seq_errors.size();
+    return SSB_OK;
+}
+
+extern "C" int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t cap)
+{
+    if (!sp || (!dst && cap)) return SSB_E_ARG;
+    size_t n = sp->seq_errors.size() < cap ? sp->seq_errors.size() : cap;
+    if (n) memcpy(dst, sp->seq_errors.data(), n * sizeof(ssb_seq_error));
+    return SSB_OK;
+}

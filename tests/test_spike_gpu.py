@@ -1,0 +1,142 @@
+"""GPU parity: the spike path of libssb200 (through the C ABI and through the drop-in C main) against the
+oracle restatement -- SAM bytes, truth.vcf and the stats block must be identical."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_bind as ob
+import spike_cases as sc
+import stochasticsim_b200 as ssb
+from stochasticsim_b200 import spike as sp
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "spike_toy")
+FULL_VCF = os.environ.get("SSB_TEST_FULL_VCF", "1") == "1"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ssb.Context(0)
+    yield c
+    c.close()
+
+
+def vcf_cmp(a, b):
+    if FULL_VCF:
+        return a == b
+    return sc.vcf_without_seq_errors(a) == sc.vcf_without_seq_errors(b)
+
+
+def first_diff(a, b):
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            lo = a.rfind(b"\n", 0, i) + 1
+            return "offset %d: want %r got %r" % (i, a[lo:lo + 300], b[lo:lo + 300])
+    return "lengths %d vs %d" % (len(a), len(b))
+
+
+def test_rand_stream_matches_glibc(ctx):
+    with sp.Spike(ctx, ["c"], {"c": b"ACGT"}) as s:
+        for seed in (434, 42, 0, 1, 4294967295):
+            got = s.rand(seed, 0, 70000)
+            assert np.array_equal(got, ob.glibc_rand(seed, 0, 70000)), seed
+        assert list(s.rand(434, 0, 5)) == [43521843, 555289354, 711778510, 1948175914, 749459303]
+        assert int(s.rand(434, 10**6, 1)[0]) == 1066614699
+        assert int(s.rand(434, 10**9, 1)[0]) == 586798013
+        assert int(s.rand(434, 2**32, 1)[0]) == 2013220912
+        assert int(s.rand(434, 5 * 10**9, 1)[0]) == 1050868447
+        got = s.rand(434, 999_000, 600_000)
+        assert np.array_equal(got, ob.glibc_rand(434, 999_000, 600_000))
+
+
+@pytest.mark.parametrize("name", sorted(sc.CASES))
+def test_cli_parity(name, tmp_path, ctx):
+    prefix = sc.generate(name, str(tmp_path))
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    assert want[0] == 0
+    assert got[0] == 0, got[4]
+    assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
+    assert got[1] == want[1], "stats differ: %r vs %r" % (want[1], got[1])
+    assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
+
+
+@pytest.mark.parametrize("seed", [1, 434, 99991])
+def test_seeds(seed, tmp_path, ctx):
+    prefix = sc.generate("overlap_heavy", str(tmp_path), coverage=25, contigs="chr19:8000", spikes=60)
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), seed=seed, cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"), seed=seed)
+    assert got[0] == 0, got[4]
+    assert got[2] == want[2], first_diff(want[2], got[2])
+    assert vcf_cmp(want[3], got[3]), first_diff(want[3], got[3])
+
+
+def test_golden_fixture(tmp_path, ctx):
+    """tests/golden/spike_toy was produced by the unmodified reference over the htslib shim."""
+    for f in ("in.sam", "in.fa", "in.spike"):
+        shutil.copy(os.path.join(GOLD, f), tmp_path / f)
+    r = subprocess.run([sc.PRODUCT, "in.sam", "in.fa", "in.spike", "434", "out.sam"], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    rd = lambda n: open(os.path.join(GOLD, n), "rb").read()
+    assert (tmp_path / "out.sam").read_bytes() == rd("out.sam")
+    assert r.stdout == rd("stdout.txt")
+    assert vcf_cmp(rd("truth.vcf"), (tmp_path / "truth.vcf").read_bytes())
+
+
+def test_abi_run_host(tmp_path, ctx):
+    """The same through the ctypes binding: body in, body out, per-target results."""
+    prefix = sc.generate("plain", str(tmp_path))
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    sam = open(prefix + ".sam", "rb").read()
+    hdr, body, names = sp.split_header(sam)
+    seqs = sp.parse_fasta(open(prefix + ".fa", "rb").read())
+    targets = sp.parse_spike(open(prefix + ".spike", "rb").read(), names)
+    with sp.Spike(ctx, names, seqs) as s:
+        out, res, st = s.run_host(body, targets, 434)
+    assert hdr + out == want[2]
+    assert st.alignmentCount == out.count(b"\n")
+    hits = [r for r in res if r.status == sp.T_HIT]
+    assert len(hits) == st.n_hits > 0
+    assert all(r.rng_offset >= 0 for r in hits)
+
+
+def test_edge_inputs(tmp_path, ctx):
+    prefix = sc.generate("plain", str(tmp_path), contigs="chr19:3000", spikes=10)
+    sam = open(prefix + ".sam", "rb").read()
+    hdr, body, names = sp.split_header(sam)
+    seqs = sp.parse_fasta(open(prefix + ".fa", "rb").read())
+    targets = sp.parse_spike(open(prefix + ".spike", "rb").read(), names)
+    lines = body.split(b"\n")[:-1]
+    with sp.Spike(ctx, names, seqs) as s:
+        # no alignments at all: every target is left over
+        out, res, st = s.run_host(b"", targets, 434)
+        assert out == b"" and all(r.status == sp.T_TAIL for r in res) and st.numberOfLociCovered == 0
+        # no targets: reads pass through in end order
+        out, res, st = s.run_host(body, [], 434)
+        assert sorted(out.split(b"\n")) == sorted(body.split(b"\n"))
+        # a body without the final newline gets one
+        out2, _, _ = s.run_host(body[:-1], [], 434)
+        assert out2 == out
+        # unsorted input is refused (htslib's pileup errors out, stochasticSpike.c:1129)
+        with pytest.raises(ssb.SSBError) as e:
+            s.run_host(b"\n".join(lines[::-1]) + b"\n", targets, 434)
+        assert e.value.code == -6
+        # a malformed line is refused
+        with pytest.raises(ssb.SSBError) as e:
+            s.run_host(body + b"garbage\n", targets, 434)
+        assert e.value.code == -5
+
+
+def test_cli_usage_and_errors(tmp_path, ctx):
+    r = subprocess.run([sc.PRODUCT], capture_output=True)
+    assert r.returncode == 0 and b"Usage" in r.stderr                                     # stochasticSpike.c:938-941
+    prefix = sc.generate("plain", str(tmp_path), contigs="chr19:3000", spikes=5)
+    r = subprocess.run([sc.PRODUCT, "/nonexistent.sam", prefix + ".fa", prefix + ".spike", "1", "o.sam"], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 1 and b"Couldn't open bam" in r.stderr
+    r = subprocess.run([sc.PRODUCT, prefix + ".sam", prefix + ".fa", "/nonexistent.spike", "1", "o.sam"], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 255
