@@ -56,6 +56,13 @@ extern "C" int ssb_ctx_create(int device, ssb_ctx **out)
     }
     for (int i = 0; i < 4; i++)
         if (cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming) != cudaSuccess) { free(ctx); return SSB_E_CUDA; }
+    // keep stream-ordered allocations cached between calls (the spike path allocates its work arrays per run)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     *out = ctx;
     return SSB_OK;
 }

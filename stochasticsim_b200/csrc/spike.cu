@@ -86,7 +86,7 @@ __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const 
 // mates: nxt[o] = first kept read after o (file order) with the same QNAME whose start lies inside
 // o's reference span, NO_MATE if none; bit 31 flags "a second such read exists" (then users rescan).
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t NO_MATE = 0x7fffffffu, MATE_MORE = 0x80000000u;
+constexpr uint32_t NO_MATE = 0x7fffffffu, MATE_MORE = 0x80000000u, PRV_NONE = 0xffffffffu;
 
 __device__ bool same_qname(const uint8_t *sam, const SamRec &a, const SamRec &b)
 {
@@ -98,7 +98,8 @@ __device__ bool same_qname(const uint8_t *sam, const SamRec &a, const SamRec &b)
 
 __global__ void mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
                              const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ k_end,
-                             const unsigned long long *__restrict__ k_hash, size_t K, uint32_t *__restrict__ nxt)
+                             const unsigned long long *__restrict__ k_hash, size_t K, uint32_t *__restrict__ nxt, uint32_t *__restrict__ prv,
+                             uint8_t *__restrict__ cplx)
 {
     size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= K) return;
@@ -108,7 +109,11 @@ __global__ void mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__re
     for (size_t b = o + 1; b < K && k_start[b] < lim; b++) {
         if (k_hash[b] != h) continue;
         if (!same_qname(sam, recs[k_rec[o]], recs[k_rec[b]])) continue;
-        if (first == NO_MATE) first = (uint32_t)b; else { more = true; break; }
+        if (first == NO_MATE) { first = (uint32_t)b; prv[b] = (uint32_t)o; }    // injective: see DESIGN.md (mate links)
+        else {
+            // three or more same-name reads overlap: every member takes the exact brute-force path
+            more = true; cplx[o] = 1; cplx[first] = 1; cplx[b] = 1;
+        }
     }
     nxt[o] = first | (more ? MATE_MORE : 0u);
 }
@@ -166,6 +171,8 @@ __device__ __forceinline__ size_t run_of_ordinal(const CovRun *runs, size_t R, i
     while (hi - lo > 1) { size_t mid = (lo + hi) >> 1; if (runs[mid].base <= g) lo = mid; else hi = mid; }
     return lo;
 }
+
+__device__ __forceinline__ int gcat_index(uint8_t b) { return b == 'G' ? 0 : b == 'C' ? 1 : b == 'A' ? 2 : b == 'T' ? 3 : 4; }
 
 // reference class per covered locus: index into "GCAT" (stochasticSpike.c:340), 4 = anything else
 __device__ __forceinline__ uint8_t ref_class(uint8_t c) { return c == 'G' ? 0 : c == 'C' ? 1 : c == 'A' ? 2 : c == 'T' ? 3 : 4; }
@@ -241,6 +248,13 @@ __global__ void patch_kernel(const Patch *__restrict__ patches, const unsigned i
         out[ord_off[p.ord] + recs[k_rec[p.ord]].seq_off + p.qpos] = (uint8_t)p.base;
     }
 }
+
+// Where an odd patch shares its byte with other patches, the one made at the latest locus must win
+// (the reference applies them in locus order); patch_kernel wrote them in no particular order.
+struct OddPatch;
+__global__ void odd_fix_kernel(const OddPatch *odd_, const unsigned int *n_odd, unsigned int odd_cap, const Patch *__restrict__ patches,
+                               const unsigned int *__restrict__ n_patches, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
+                               const unsigned long long *__restrict__ ord_off, uint8_t *__restrict__ out);
 
 // ------------------------------------------------------------------------------------------
 // depth
@@ -443,6 +457,215 @@ __global__ void gather_mate_kernel(const uint8_t *__restrict__ sam, const SamRec
 }
 
 // ------------------------------------------------------------------------------------------
+// "odd" patches.  getBaseWithRPOcheck (:387-432) takes the mate's base at the mate's qpos without
+// looking at is_del / is_refskip, and for a deleted/skipped column htslib's qpos is the NEXT
+// aligned base.  attemptToMutateBase cases 3-6 can therefore overwrite a base that belongs to a
+// LATER locus, and because the reference edits reads in place every later locus sees it.  Such
+// patches are rare (a mate inside a D/N at a target that tosses heads); they are kept in a small
+// list that the chain and the tally consult so that the result stays bit-exact.
+// ------------------------------------------------------------------------------------------
+struct OddPatch { uint32_t ord, qpos, base, h; int32_t tid, pos; };
+
+__device__ __forceinline__ unsigned long long odd_bit(uint32_t ord) { return 1ull << ((ord * 2654435761u) >> 26); }
+
+// value of (ord,qpos) as seen at locus (tid,pos): the last odd patch made at an earlier locus wins
+__device__ uint8_t odd_view(const OddPatch *odd, unsigned int n_odd, uint32_t ord, uint32_t qpos, int32_t tid, int64_t pos, uint8_t base)
+{
+    for (unsigned int i = 0; i < n_odd; i++)          // list is in target (= locus) order
+        if (odd[i].ord == ord && odd[i].qpos == qpos && (odd[i].tid < tid || (odd[i].tid == tid && odd[i].pos < pos))) base = (uint8_t)odd[i].base;
+    return base;
+}
+
+__global__ void odd_fix_kernel(const OddPatch *odd, const unsigned int *n_odd, unsigned int odd_cap, const Patch *__restrict__ patches,
+                               const unsigned int *__restrict__ n_patches, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
+                               const unsigned long long *__restrict__ ord_off, uint8_t *__restrict__ out)
+{
+    const unsigned int no = min(*n_odd, odd_cap), np = *n_patches;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < no; i += gridDim.x * blockDim.x) {
+        const OddPatch q = odd[i];
+        uint32_t best_h = 0, best_base = q.base; bool any = false;
+        for (unsigned int p = 0; p < np; p++)
+            if (patches[p].ord == q.ord && patches[p].qpos == q.qpos && (!any || patches[p].pad >= best_h)) { any = true; best_h = patches[p].pad; best_base = patches[p].base; }
+        out[ord_off[q.ord] + recs[k_rec[q.ord]].seq_off + q.qpos] = (uint8_t)best_base;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-locus allele tallies at the loci that are not spike targets (stochasticSpike.c:1296-1357), for
+// the SEQ_ERROR lines of truth.vcf (:1494-1557).
+//
+// ref(x) = depth(x) - minus(x): depth comes from the sorted start/end arrays, minus(x) counts the
+// pileup entries at x that do NOT add to refAlleleCnt (deleted/skipped bases, BQ 0, N, mismatches,
+// second mates already handled).  Only those exceptional bases cost an atomic.
+// err64[x] packs the four error-allele counters (G,C,A,T, 16 bits each; depth <= 10000).
+// ------------------------------------------------------------------------------------------
+struct ReadView {
+    const uint8_t *line; const uint8_t *cig; int cig_len; int32_t pos, end; uint32_t seq_off, qual_off, l_seq; bool qual_star;
+    uint32_t ord; int32_t tid; const OddPatch *odd; unsigned int n_odd;      // odd != NULL only for the few reads an odd patch touched
+};
+__device__ __forceinline__ ReadView view_of(const uint8_t *sam, const SamRec &r, uint32_t ord, const OddPatch *odd, unsigned int n_odd, unsigned long long bloom)
+{
+    ReadView v; v.line = sam + r.line_off; v.ord = ord; v.tid = r.tid; v.odd = NULL; v.n_odd = 0;
+    if (n_odd && (bloom & odd_bit(ord))) { v.odd = odd; v.n_odd = n_odd; } v.cig = v.line + r.cigar_off; v.cig_len = r.cigar_len; v.pos = r.pos; v.end = r.end;
+    v.seq_off = r.seq_off; v.qual_off = r.qual_off; v.l_seq = r.l_seq; v.qual_star = (r.bits & REC_QUALSTAR) != 0;
+    return v;
+}
+__device__ __forceinline__ void base_at(const ReadView &v, int32_t x, uint8_t &base, int &bq, bool &skip)
+{
+    uint32_t qpos; uint8_t sk;
+    column_of(v.cig, v.cig_len, v.pos, x, qpos, sk);
+    if (qpos >= v.l_seq) qpos = v.l_seq - 1;        // malformed CIGAR tail (the reference would read out of bounds)
+    base = v.line[v.seq_off + qpos];
+    if (v.odd) base = odd_view(v.odd, v.n_odd, v.ord, qpos, v.tid, x, base);
+    bq = v.qual_star ? 255 : (int)v.line[v.qual_off + qpos] - 33;
+    skip = sk != 0;
+}
+
+struct TallyArgs {
+    const uint8_t *sam; const SamRec *recs; const uint32_t *k_rec; const unsigned long long *k_start, *k_end, *k_hash; size_t K;
+    const uint32_t *nxt, *prv; const uint8_t *cplx; unsigned int maxspan;
+    const CovRun *runs; size_t R; const uint8_t *const *contig_seq; const int64_t *contig_len;
+    unsigned long long *err64; unsigned int *minus; DevErr *err;
+    const OddPatch *odd; const unsigned int *n_odd; const unsigned long long *odd_bloom;
+};
+
+// what entry `self` (index into members) adds at locus x, given the same-name reads that cover x in file order:
+// 0 nothing, 1 ref, 2..5 error allele G,C,A,T   (the j-loop of :1255-1357 restricted to one QNAME)
+__device__ int chain_contribution(const ReadView *mem, int n, int self, int32_t x, uint8_t F)
+{
+    bool handled[8];
+    for (int i = 0; i < n; i++) handled[i] = false;
+    for (int m = 0; m <= self; m++) {
+        uint8_t Rb; int rbq; bool sk;
+        base_at(mem[m], x, Rb, rbq, sk);
+        int contrib = 0;
+        if (!(sk || rbq == 0 || handled[m])) {
+            uint8_t Mb = 0; int mbq = 0;
+            const int mate = m + 1 < n ? m + 1 : -1;                    // first later entry with the same QNAME
+            if (mate >= 0 && !handled[mate]) { bool msk; base_at(mem[mate], x, Mb, mbq, msk); }
+            if (Mb == 'N') mbq = 0;
+            if (Rb == 'N') rbq = 0;
+            uint8_t base = Rb;
+            if (Mb && Mb != Rb && mbq > rbq) base = Mb;
+            if (base == 'N') { handled[m] = true; if (Mb) handled[mate] = true; }
+            else if (base == F) contrib = 1;
+            else { int gi = gcat_index(base); contrib = gi < 4 ? 2 + gi : 0; handled[m] = true; if (Mb) handled[mate] = true; }
+        }
+        if (m == self) return contrib;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ void tally_add(const TallyArgs &A, int64_t g, int contrib)
+{
+    if (contrib == 1) return;
+    atomicAdd(&A.minus[g], 1u);
+    if (contrib >= 2) atomicAdd(&A.err64[g], 1ull << (16 * (contrib - 2)));
+}
+
+__global__ void __launch_bounds__(128)
+tally_kernel(TallyArgs A)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= A.K) return;
+    const SamRec &r = A.recs[A.k_rec[o]];
+    const unsigned int n_odd = *A.n_odd; const unsigned long long bloom = *A.odd_bloom;
+    const ReadView me = view_of(A.sam, r, (uint32_t)o, A.odd, n_odd, bloom);
+    const int tid = r.tid;
+    const uint8_t *ref = A.contig_seq[tid];
+    if (!ref || (int64_t)r.end > A.contig_len[tid]) { set_err(A.err, SSB_E_REF, r.line_off); return; }   // :1181 mplp_get_ref / read past the contig
+    // same-name reads that overlap this one, in file order
+    ReadView mem[8]; int n = 0, self = 0; bool use_chain = false;
+    if (A.cplx[o]) {
+        // exact brute force: every kept read of this contig that can overlap [pos,end) and carries the same QNAME
+        const unsigned long long h = A.k_hash[o];
+        int64_t first = (int64_t)r.pos - (int64_t)A.maxspan + 1; if (first < 0) first = 0;
+        size_t lo = lower_bound_u64(A.k_start, A.K, ((unsigned long long)(uint32_t)tid << 32) | (uint32_t)first);
+        const unsigned long long lim = A.k_end[o];
+        for (size_t b = lo; b < A.K && A.k_start[b] < lim && n < 8; b++) {
+            if (b != o && (A.k_hash[b] != h || !same_qname(A.sam, r, A.recs[A.k_rec[b]]))) continue;
+            if (b != o && (uint32_t)(A.k_end[b]) <= (uint32_t)r.pos) continue;
+            if (b == o) self = n;
+            mem[n++] = view_of(A.sam, A.recs[A.k_rec[b]], (uint32_t)b, A.odd, n_odd, bloom);
+        }
+        use_chain = n > 1;
+    } else {
+        const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
+        if (p != PRV_NONE && (uint32_t)A.k_end[p] > (uint32_t)r.pos) mem[n++] = view_of(A.sam, A.recs[A.k_rec[p]], p, A.odd, n_odd, bloom);
+        self = n; mem[n++] = me;
+        if (q != NO_MATE) mem[n++] = view_of(A.sam, A.recs[A.k_rec[q]], q, A.odd, n_odd, bloom);
+        use_chain = n > 1;
+    }
+    // covered ordinal of this read's first base: reads never span two runs
+    size_t ri; { size_t lo = 0, hi = A.R; while (hi - lo > 1) { size_t mid = (lo + hi) >> 1;
+                   bool le = A.runs[mid].tid < tid || (A.runs[mid].tid == tid && A.runs[mid].start <= r.pos); if (le) lo = mid; else hi = mid; } ri = lo; }
+    const int64_t gbase = A.runs[ri].base - A.runs[ri].start;           // g = gbase + x
+    // walk the CIGAR
+    int64_t x = r.pos; uint32_t y = 0, num = 0;
+    for (int ci = 0; ci < me.cig_len; ci++) {
+        const uint8_t c = me.cig[ci];
+        if (c >= '0' && c <= '9') { num = num * 10 + (c - '0'); continue; }
+        const uint32_t l = num; num = 0;
+        if (c == 'M' || c == '=' || c == 'X') {
+            for (uint32_t t = 0; t < l; t++, x++, y++) {
+                const uint8_t F = ref[x];
+                int contrib;
+                bool overlapped = false;
+                if (use_chain) for (int m = 0; m < n; m++) if (m != self && mem[m].pos <= x && x < mem[m].end) { overlapped = true; break; }
+                if (overlapped) {
+                    ReadView cov[8]; int nc = 0, sc = 0;
+                    for (int m = 0; m < n; m++) if (mem[m].pos <= x && x < mem[m].end) { if (m == self) sc = nc; cov[nc++] = mem[m]; }
+                    contrib = chain_contribution(cov, nc, sc, (int32_t)x, F);
+                } else {
+                    uint8_t b = me.line[me.seq_off + y];
+                    if (me.odd) b = odd_view(me.odd, me.n_odd, me.ord, y, tid, x, b);
+                    const int bq = me.qual_star ? 255 : (int)me.line[me.qual_off + y] - 33;
+                    if (bq == 0 || b == 'N') contrib = 0;
+                    else if (b == F) contrib = 1;
+                    else { int gi = gcat_index(b); contrib = gi < 4 ? 2 + gi : 0; }
+                }
+                tally_add(A, gbase + x, contrib);
+            }
+        } else if (c == 'D' || c == 'N') {
+            for (uint32_t t = 0; t < l; t++, x++) atomicAdd(&A.minus[gbase + x], 1u);      // in the pileup, adds to nothing
+        } else if (c == 'I' || c == 'S') y += l;
+    }
+}
+
+__global__ void tally_clear_hits_kernel(const HitTarget *__restrict__ hits, size_t H, unsigned long long *__restrict__ err64)
+{
+    size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h < H) err64[hits[h].locus_index] = 0;          // a target locus prints its own line (:1406-1470), never SEQ_ERROR
+}
+
+__global__ void tally_flag_kernel(const unsigned long long *__restrict__ err64, int64_t n_cov, uint32_t *__restrict__ flag)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_cov) flag[g] = err64[g] ? 1u : 0u;
+}
+
+__global__ void tally_emit_kernel(const unsigned long long *__restrict__ err64, const unsigned int *__restrict__ minus, const uint32_t *__restrict__ flag,
+                                  const uint32_t *__restrict__ idx, int64_t n_cov, const CovRun *__restrict__ runs, size_t R,
+                                  const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ s_end, size_t K,
+                                  const uint8_t *const *__restrict__ contig_seq, ssb_seq_error *__restrict__ out)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_cov || !flag[g]) return;
+    size_t ri = run_of_ordinal(runs, R, g);
+    const int tid = runs[ri].tid; const int64_t x = runs[ri].start + (g - runs[ri].base);
+    const unsigned long long key = ((unsigned long long)(uint32_t)tid << 32) | (uint32_t)x;
+    const long long depth = (long long)upper_bound_u64(k_start, K, key) - (long long)upper_bound_u64(s_end, K, key);
+    ssb_seq_error e;
+    memset(&e, 0, sizeof e);
+    e.tid = tid; e.pos = x; e.locus_index = g;
+    e.ref_cnt = (int32_t)(depth - (long long)minus[g]);
+    const unsigned long long v = err64[g];
+    for (int i = 0; i < 4; i++) e.err_cnt[i] = (int32_t)((v >> (16 * i)) & 0xffff);
+    e.ref_base = contig_seq[tid][x];
+    out[idx[g]] = e;
+}
+
+// ------------------------------------------------------------------------------------------
 // glibc rand() stream
 // ------------------------------------------------------------------------------------------
 struct RngTables {
@@ -488,6 +711,7 @@ struct ChainArgs {
     const unsigned long long *eoff; PlpEntry *ent; uint8_t *hflag;
     ssb_target_result *res;
     Patch *patches; unsigned int *n_patches; unsigned int patch_cap;
+    OddPatch *odd; unsigned int *n_odd; unsigned int odd_cap; unsigned long long *odd_bloom;
     const uint8_t *const *contig_seq;
     unsigned long long *draws_out; DevErr *err;
 };
@@ -563,7 +787,6 @@ __device__ __forceinline__ bool select_allele(const ChainArgs &A, unsigned long 
     }
 }
 
-__device__ __forceinline__ int gcat_index(uint8_t b) { return b == 'G' ? 0 : b == 'C' ? 1 : b == 'A' ? 2 : b == 'T' ? 3 : 4; }
 
 // Outcome of one pileup entry at a target locus, computed without side effects so that a warp can
 // evaluate 32 entries speculatively (attemptToMutateBase, stochasticSpike.c:526-904; cases as in SURVEY App. A).
@@ -574,14 +797,14 @@ struct EntryOut {
     bool ok;
 };
 
-__device__ EntryOut entry_eval(const ChainArgs &A, const PlpEntry &e, const PlpEntry *ents, const uint8_t *hflags, uint8_t self_handled,
+__device__ EntryOut entry_eval(const ChainArgs &A, const PlpEntry &e, uint8_t mate_base, uint8_t mate_bq, const uint8_t *hflags, uint8_t self_handled,
                                unsigned long long k, uint32_t thresh, uint8_t F, uint8_t Aallele)
 {
     EntryOut o; o.draws = 0; o.mark_self = o.mark_mate = o.filt = o.tally = o.npatch = 0; o.ok = true;
     o.pbase[0] = o.pbase[1] = o.pmate[0] = o.pmate[1] = 0;
     if (e.skip || e.bq == 0 || self_handled) return o;                               // :1270
     uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
-    if (e.mate >= 0 && !hflags[e.mate]) { M = ents[e.mate].base; mbq = ents[e.mate].bq; }   // getBaseWithRPOcheck :387-432
+    if (e.mate >= 0 && !hflags[e.mate]) { M = mate_base; mbq = mate_bq; }                  // getBaseWithRPOcheck :387-432
     if (M == 'N') mbq = 0;
     if (R == 'N') rbq = 0;
     uint8_t base = R;
@@ -634,6 +857,7 @@ chain_kernel(ChainArgs A)
     const int lane = threadIdx.x;
     int64_t g = 0; unsigned long long k = 0;
     DrawWin D; RefWin F;
+    unsigned long long odd_bloom = 0;
     D.kw = ~0ull >> 1; F.gw = -1000;                 // force the first loads
     D.e0 = D.e1 = D.ej = F.c0 = F.c1 = F.cx = 0;
     for (size_t h = 0; h < A.H; h++) {
@@ -652,17 +876,27 @@ chain_kernel(ChainArgs A)
         const uint32_t n = (uint32_t)(e1 - e0);
         uint32_t ref_cnt = 0, mut_cnt = 0, err0 = 0, err1 = 0, err2 = 0, err3 = 0, fP = 0, fK = 0, fO = 0;
         uint32_t j0 = 0;
+        // odd patches made at EARLIER targets (the list only grows at later loci, so it is fixed for this target)
+        __syncwarp();
+        const unsigned int n_odd = min(*(volatile unsigned int *)A.n_odd, A.odd_cap);
+        unsigned long long new_bloom = 0;
         while (j0 < n) {
             const uint32_t j = j0 + lane;
             const bool in = j < n;
             PlpEntry e; e.skip = 1; e.bq = 0; e.mate = -1; e.base = 0; e.ord = 0; e.qpos = 0;
             if (in) e = ents[j];
             const uint8_t handled = in ? hf[j] : 1;
+            uint8_t mate_base = 0, mate_bq = 0; PlpEntry me_; me_.ord = 0; me_.qpos = 0; me_.skip = 0;
+            if (in && e.mate >= 0) { me_ = ents[e.mate]; mate_base = me_.base; mate_bq = me_.bq; }
+            if (n_odd && in) {                        // bases an earlier odd patch rewrote (see OddPatch)
+                if (odd_bloom & odd_bit(e.ord)) e.base = odd_view(A.odd, n_odd, e.ord, e.qpos, ht.tid, ht.pos, e.base);
+                if (e.mate >= 0 && (odd_bloom & odd_bit(me_.ord))) mate_base = odd_view(A.odd, n_odd, me_.ord, me_.qpos, ht.tid, ht.pos, mate_base);
+            }
             // does this entry toss (or otherwise act)?  needed to give every lane its draw index
             bool tosses = false;
             if (in && !e.skip && e.bq != 0 && !handled) {
                 uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
-                if (e.mate >= 0 && !hf[e.mate]) { M = ents[e.mate].base; mbq = ents[e.mate].bq; }
+                if (e.mate >= 0 && !hf[e.mate]) { M = mate_base; mbq = mate_bq; }
                 if (M == 'N') mbq = 0;
                 if (R == 'N') rbq = 0;
                 uint8_t base = R; if (M && M != R && mbq > rbq) base = M;
@@ -670,7 +904,7 @@ chain_kernel(ChainArgs A)
             }
             const unsigned tossmask = __ballot_sync(0xffffffffu, tosses);
             const unsigned long long my_k = k + __popc(tossmask & ((1u << lane) - 1u));
-            EntryOut o = entry_eval(A, e, ents, hf, handled, my_k, ht.thresh, Fb, allele);
+            EntryOut o = entry_eval(A, e, mate_base, mate_bq, hf, handled, my_k, ht.thresh, Fb, allele);
             // a lane "breaks" the speculation of the lanes after it when it used more than its one draw, or
             // when it marks an entry of this batch as handled
             const bool marks_in_batch = in && o.mark_mate && e.mate >= 0 && (uint32_t)e.mate < j0 + 32;
@@ -684,10 +918,16 @@ chain_kernel(ChainArgs A)
                 if (o.mark_mate && e.mate >= 0) hf[e.mate] = 1;
                 for (int p = 0; p < o.npatch; p++) {
                     unsigned int slot = atomicAdd(A.n_patches, 1u);
+                    const PlpEntry &pe = o.pmate[p] ? me_ : e;
                     if (slot < A.patch_cap) {
-                        const PlpEntry &pe = o.pmate[p] ? ents[e.mate] : e;
                         Patch pt; pt.ord = pe.ord; pt.qpos = pe.qpos; pt.base = o.pbase[p]; pt.pad = (uint32_t)h;
                         A.patches[slot] = pt;
+                    }
+                    if (o.pmate[p] && me_.skip) {     // the mate sits in a D/N here: the patch lands on a base of a later locus
+                        unsigned int os = atomicAdd(A.n_odd, 1u);
+                        if (os < A.odd_cap) { OddPatch q; q.ord = pe.ord; q.qpos = pe.qpos; q.base = o.pbase[p]; q.h = (uint32_t)h; q.tid = ht.tid; q.pos = ht.pos; A.odd[os] = q; }
+                        else set_err(A.err, SSB_E_NOMEM, (unsigned long long)h);
+                        new_bloom |= odd_bit(pe.ord);
                     }
                 }
             }
@@ -707,6 +947,9 @@ chain_kernel(ChainArgs A)
             __syncwarp();
             j0 += last + 1;
         }
+        for (int sft = 16; sft; sft >>= 1) new_bloom |= __shfl_xor_sync(0xffffffffu, new_bloom, sft);
+        odd_bloom |= new_bloom;
+        __threadfence();
         if (lane == 0) {
             ssb_target_result &r = A.res[ht.target];
             r.ref_base = Fb; r.mutant_allele = allele;
@@ -718,7 +961,7 @@ chain_kernel(ChainArgs A)
         }
         g += 1;
     }
-    if (lane == 0) *A.draws_out = k;
+    if (lane == 0) { *A.draws_out = k; *A.odd_bloom = odd_bloom; }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -748,7 +991,7 @@ struct ssb_spike {
     uint8_t **d_seq_ptrs; int64_t *d_lens;
     std::vector<uint8_t *> d_seqs;
     RngTables *d_rng_tab;
-    std::vector<ssb_seq_error> seq_errors;
+    ssb_seq_error *d_se; size_t n_se;          // SEQ_ERROR records of the last run (device resident until asked for)
 };
 
 extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_contigs, ssb_spike **out)
@@ -757,7 +1000,7 @@ extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_c
     *out = NULL;
     SSB_CUDA(ctx, cudaSetDevice(ctx->device));
     ssb_spike *sp = new ssb_spike();
-    sp->ctx = ctx; sp->n_contigs = n_contigs;
+    sp->ctx = ctx; sp->n_contigs = n_contigs; sp->d_se = NULL; sp->n_se = 0;
     std::vector<char> names; std::vector<uint32_t> off; std::vector<int64_t> lens; std::vector<uint8_t *> ptrs;
     off.push_back(0);
     for (int i = 0; i < n_contigs; i++) {
@@ -803,6 +1046,7 @@ extern "C" void ssb_spike_destroy(ssb_spike *sp)
     cudaSetDevice(sp->ctx->device);
     cudaStreamSynchronize(sp->ctx->stream);
     for (uint8_t *d : sp->d_seqs) if (d) cudaFree(d);
+    if (sp->d_se) cudaFree(sp->d_se);
     cudaFree(sp->d_names); cudaFree(sp->d_name_off); cudaFree(sp->d_seq_ptrs); cudaFree(sp->d_lens); cudaFree(sp->d_rng_tab);
     delete sp;
 }
@@ -875,7 +1119,8 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     cudaStream_t s = ctx->stream;
     memset(stats, 0, sizeof *stats);
     *out_bytes = 0;
-    sp->seq_errors.clear();
+    if (sp->d_se) { cudaFree(sp->d_se); sp->d_se = NULL; }
+    sp->n_se = 0;
     stats->in_bytes = (int64_t)n;
     const size_t T = n_targets;
     cudaEvent_t ev[12];
@@ -885,6 +1130,11 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
 
     DevErr *d_err = ar.get<DevErr>(1); SPK_CHECK_ARENA(ar);
     SSB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(DevErr), s));
+    const unsigned int odd_cap = 1u << 16;
+    OddPatch *d_odd = ar.get<OddPatch>(odd_cap); unsigned int *d_nodd = ar.get<unsigned int>(1); unsigned long long *d_bloom = ar.get<unsigned long long>(1);
+    SPK_CHECK_ARENA(ar);
+    SSB_CUDA(ctx, cudaMemsetAsync(d_nodd, 0, sizeof(unsigned int), s));
+    SSB_CUDA(ctx, cudaMemsetAsync(d_bloom, 0, sizeof(unsigned long long), s));
     SSB_CUDA(ctx, cudaEventRecord(ev[0], s));
 
     // ---------------------------------------------------------------- parse
@@ -923,7 +1173,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
 
     // ---------------------------------------------------------------- keep / sortedness / compaction
     size_t K = 0;
-    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL; unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL;
+    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL, *prv = NULL; uint8_t *cplx = NULL; unsigned long long *err64 = NULL; unsigned int *minus = NULL; unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL;
     unsigned long long *d_fold = ar.get<unsigned long long>(1); unsigned int *d_maxspan = ar.get<unsigned int>(1), *d_maxdepth = ar.get<unsigned int>(1);
     SPK_CHECK_ARENA(ar);
     SSB_CUDA(ctx, cudaMemsetAsync(d_fold, 0, sizeof(unsigned long long), s));
@@ -990,7 +1240,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     if (K) {
         int rc;
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, khash_kernel, grid_for(K, 256), 256, 0, s, recs, k_rec, K, k_hash);
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, mates_kernel, grid_for(K, 128), 128, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash, K, nxt);
+        prv = ar.get<uint32_t>(K); cplx = ar.get<uint8_t>(K); SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemsetAsync(prv, 0xff, K * sizeof(uint32_t), s));
+        SSB_CUDA(ctx, cudaMemsetAsync(cplx, 0, K, s));
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, mates_kernel, grid_for(K, 128), 128, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash, K, nxt, prv, cplx);
         unsigned long long *pm = ar.get<unsigned long long>(K); uint32_t *rflag = ar.get<uint32_t>(K), *rid = ar.get<uint32_t>(K);
         SPK_CHECK_ARENA(ar);
         if ((rc = scan_max_excl(ar, ctx, k_end, pm, K, 0ull))) return rc;
@@ -1105,7 +1358,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             SSB_CUDA(ctx, cudaEventRecord(ev[9], s));
             SSB_CUDA(ctx, cudaMemsetAsync(hflag, 0, E, s));
             SSB_CUDA(ctx, cudaMemsetAsync(n_patches, 0, sizeof(unsigned int), s));
+            SSB_CUDA(ctx, cudaMemsetAsync(d_nodd, 0, sizeof(unsigned int), s));
+            SSB_CUDA(ctx, cudaMemsetAsync(d_bloom, 0, sizeof(unsigned long long), s));
             ChainArgs A;
+            A.odd = d_odd; A.n_odd = d_nodd; A.odd_cap = odd_cap; A.odd_bloom = d_bloom;
             A.cls = cls; A.n_cov = n_walk; A.R = Rs; A.M = M; A.hits = hits; A.H = H; A.eoff = eoff; A.ent = ent; A.hflag = hflag;
             A.res = d_res; A.patches = patches; A.n_patches = n_patches; A.patch_cap = (unsigned int)(2 * E + 16);
             A.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; A.draws_out = d_draws; A.err = d_err;
@@ -1128,11 +1384,45 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         unsigned long long draws = 0;
         SSB_CUDA(ctx, cudaMemcpyAsync(&draws, d_draws, 8, cudaMemcpyDeviceToHost, s));
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, patch_kernel, 64, 256, 0, s, patches, n_patches, recs, k_rec, ord_off, d_out);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, odd_fix_kernel, 4, 128, 0, s, d_odd, d_nodd, odd_cap, patches, n_patches, recs, k_rec, ord_off, d_out);
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         stats->rng_draws = (int64_t)draws;
     } else {
         SSB_CUDA(ctx, cudaEventRecord(ev[7], s));
         SSB_CUDA(ctx, cudaEventRecord(ev[10], s));
+    }
+    if (n_cov) {
+        int rc;
+        // per-locus tallies of the non-target loci (SEQ_ERROR lines)
+        err64 = ar.get<unsigned long long>((size_t)n_cov + 1); minus = ar.get<unsigned int>((size_t)n_cov + 1);
+        SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemsetAsync(err64, 0, ((size_t)n_cov + 1) * sizeof(unsigned long long), s));
+        SSB_CUDA(ctx, cudaMemsetAsync(minus, 0, ((size_t)n_cov + 1) * sizeof(unsigned int), s));
+        unsigned int h_maxspan = 0;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&h_maxspan, d_maxspan, 4, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        TallyArgs TA;
+        TA.sam = d_sam; TA.recs = recs; TA.k_rec = k_rec; TA.k_start = k_start; TA.k_end = k_end; TA.k_hash = k_hash; TA.K = K;
+        TA.nxt = nxt; TA.prv = prv; TA.cplx = cplx; TA.maxspan = h_maxspan; TA.runs = runs; TA.R = R;
+        TA.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; TA.contig_len = sp->d_lens; TA.err64 = err64; TA.minus = minus; TA.err = d_err;
+        TA.odd = d_odd; TA.n_odd = d_nodd; TA.odd_bloom = d_bloom;
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_kernel, grid_for(K, 128), 128, 0, s, TA);
+        if ((rc = dev_error(ctx, s, d_err, "reference"))) return rc;
+        if (H) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_clear_hits_kernel, grid_for(H, 256), 256, 0, s, hits, H, err64);
+        uint32_t *sflag = ar.get<uint32_t>((size_t)n_cov), *sidx = ar.get<uint32_t>((size_t)n_cov);
+        SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_flag_kernel, grid_for((size_t)n_cov, 256), 256, 0, s, err64, n_cov, sflag);
+        if ((rc = scan_sum(ar, ctx, sflag, sidx, (size_t)n_cov))) return rc;
+        uint32_t li = 0, lf = 0;
+        SSB_CUDA(ctx, cudaMemcpyAsync(&li, sidx + n_cov - 1, 4, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(&lf, sflag + n_cov - 1, 4, cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        sp->n_se = (size_t)li + lf;
+        if (sp->n_se) {
+            SSB_CUDA(ctx, cudaMalloc((void **)&sp->d_se, sp->n_se * sizeof(ssb_seq_error)));
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_emit_kernel, grid_for((size_t)n_cov, 256), 256, 0, s, err64, minus, sflag, sidx, n_cov, runs, R,
+                         k_start, s_end, K, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_se);
+        }
     }
     SSB_CUDA(ctx, cudaEventRecord(ev[11], s));
     if (T && n_cov) SSB_CUDA(ctx, cudaMemcpyAsync(results, d_res, T * sizeof(ssb_target_result), cudaMemcpyDeviceToHost, s));
@@ -1209,14 +1499,19 @@ extern "C" int ssb_spike_rand(ssb_spike *sp, unsigned seed, uint64_t k0, size_t 
 extern "C" int ssb_spike_seq_error_count(ssb_spike *sp, size_t *count)
 {
     if (!sp || !count) return SSB_E_ARG;
-    *count = sp->seq_errors.size();
+    *count = sp->n_se;
     return SSB_OK;
 }
 
 extern "C" int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t cap)
 {
     if (!sp || (!dst && cap)) return SSB_E_ARG;
-    size_t n = sp->seq_errors.size() < cap ? sp->seq_errors.size() : cap;
-    if (n) memcpy(dst, sp->seq_errors.data(), n * sizeof(ssb_seq_error));
+    ssb_ctx *ctx = sp->ctx;
+    size_t n = sp->n_se < cap ? sp->n_se : cap;
+    if (n) {
+        SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+        SSB_CUDA(ctx, cudaMemcpyAsync(dst, sp->d_se, n * sizeof(ssb_seq_error), cudaMemcpyDeviceToHost, ctx->stream));
+        SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return SSB_OK;
 }
