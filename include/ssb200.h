@@ -172,6 +172,7 @@ typedef struct ssb_target_result {
 typedef struct ssb_spike_stats {
     int64_t alignmentCount, numberOfLociCovered, totalFoldCoverage, maxDepth;   /* :1668            */
     int64_t n_lines, n_kept, in_bytes, out_bytes, n_runs, n_hits, rng_draws;
+    int64_t chain_mode;       /* chunks the RNG chain ran as: 1 = serial, P > 1 = P parallel chunk maps      */
     float   ms_parse, ms_sort, ms_emit, ms_cover, ms_gather, ms_rng, ms_chain, ms_patch, ms_total;
 } ssb_spike_stats;
 

@@ -665,304 +665,7 @@ __global__ void tally_emit_kernel(const unsigned long long *__restrict__ err64, 
     out[idx[g]] = e;
 }
 
-// ------------------------------------------------------------------------------------------
-// glibc rand() stream
-// ------------------------------------------------------------------------------------------
-struct RngTables {
-    uint32_t seg[RNG_TPB][GLIBC_DEG];     // x^(t * RNG_SEG) mod P
-};
-
-// out[k] = rand() #k for k in [0, M): thread (b, t) produces outputs [b*RNG_BLOCK + t*RNG_SEG, +RNG_SEG)
-__global__ void __launch_bounds__(RNG_TPB)
-rng_fill_kernel(const uint32_t *__restrict__ block_poly /* [nblocks][31]: x^(310 + k_base + b*RNG_BLOCK) */, const RngTables *__restrict__ tab,
-                const uint32_t *__restrict__ seedw /* 61 words */, int32_t *__restrict__ out /* out[i] = rand() #(k_base + i) */, unsigned long long M)
-{
-    __shared__ uint32_t s_w[61];
-    __shared__ uint32_t s_bp[GLIBC_DEG];
-    if (threadIdx.x < 61) s_w[threadIdx.x] = seedw[threadIdx.x];
-    if (threadIdx.x < GLIBC_DEG) s_bp[threadIdx.x] = block_poly[(size_t)blockIdx.x * GLIBC_DEG + threadIdx.x];
-    __syncthreads();
-    const unsigned long long k0 = (unsigned long long)blockIdx.x * RNG_BLOCK + (unsigned long long)threadIdx.x * RNG_SEG;
-    if (k0 >= M) return;
-    uint32_t a[GLIBC_DEG], b[GLIBC_DEG], c[GLIBC_DEG], h[GLIBC_DEG];
-    for (int i = 0; i < GLIBC_DEG; i++) { a[i] = s_bp[i]; b[i] = tab->seg[threadIdx.x][i]; }
-    glibc_poly_mulmod(a, b, c);
-    glibc_history(c, s_w, h);                        // h[t] = r[344 + k0 - 31 + t]
-    unsigned long long k = k0;
-    const unsigned long long kend = (k0 + RNG_SEG < M) ? k0 + RNG_SEG : M;
-    while (k < kend) {
-#pragma unroll
-        for (int i = 0; i < GLIBC_DEG; i++) {        // new word replaces r[n-31]; r[n-3] sits three slots back
-            h[i] = h[i] + h[(i + 28) % GLIBC_DEG];
-            if (k < kend) out[k] = (int32_t)(h[i] >> 1);
-            k++;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// the chain: one warp.  Walks covered loci consuming selectMutantAllele draws and applies the hit
-// targets in order.  Everything the warp decides is uniform across lanes except the entry batches.
-// ------------------------------------------------------------------------------------------
-struct ChainArgs {
-    const uint8_t *cls; int64_t n_cov;
-    const int32_t *R; unsigned long long M;
-    const HitTarget *hits; size_t H;
-    const unsigned long long *eoff; PlpEntry *ent; uint8_t *hflag;
-    ssb_target_result *res;
-    Patch *patches; unsigned int *n_patches; unsigned int patch_cap;
-    OddPatch *odd; unsigned int *n_odd; unsigned int odd_cap; unsigned long long *odd_bloom;
-    const uint8_t *const *contig_seq;
-    unsigned long long *draws_out; DevErr *err;
-};
-
-struct DrawWin { unsigned long long kw; uint32_t e0, e1, ej; };
-struct RefWin { int64_t gw; uint32_t c0, c1, cx; };
-
-__device__ __forceinline__ void load_draws(const ChainArgs &A, unsigned long long kw, DrawWin &W, int lane)
-{
-    unsigned long long k = kw + lane;
-    uint32_t r = k < A.M ? (uint32_t)A.R[k] : 0u;
-    W.kw = kw;
-    W.ej = __ballot_sync(0xffffffffu, r >= GLIBC_CUT4);
-    W.e0 = __ballot_sync(0xffffffffu, r & 1u);
-    W.e1 = __ballot_sync(0xffffffffu, r & 2u);
-}
-__device__ __forceinline__ void load_ref(const ChainArgs &A, int64_t gw, RefWin &W, int lane)
-{
-    int64_t g = gw + lane;
-    uint32_t c = g < A.n_cov ? A.cls[g] : 4u;
-    W.gw = gw;
-    W.cx = __ballot_sync(0xffffffffu, c == 4u);
-    W.c0 = __ballot_sync(0xffffffffu, c & 1u);
-    W.c1 = __ballot_sync(0xffffffffu, c & 2u);
-}
-
-// Consumes the draws of covered loci [g, g_to): per locus, rand() until the pick differs from the
-// reference base (selectMutantAllele/randomNum, stochasticSpike.c:283-302,338-360).  Returns false on stream overrun.
-__device__ bool chain_walk(const ChainArgs &A, int64_t &g, int64_t g_to, unsigned long long &k, DrawWin &D, RefWin &F, int lane)
-{
-    while (g < g_to) {
-        if (g - F.gw >= 32 || g < F.gw) load_ref(A, g, F, lane);
-        if (k - D.kw >= 32 || k < D.kw) { if (k + 32 > A.M) return false; load_draws(A, k, D, lane); }
-        const uint32_t b = (uint32_t)(g - F.gw), a = (uint32_t)(k - D.kw);
-        uint32_t n = 32 - a; if (32 - b < n) n = 32 - b; if ((uint64_t)(g_to - g) < n) n = (uint32_t)(g_to - g);
-        // lock step: draw a+i against locus b+i; bit set = that draw ends that locus
-        const uint32_t term = ((((D.e0 >> a) ^ (F.c0 >> b)) | ((D.e1 >> a) ^ (F.c1 >> b)) | (F.cx >> b)) & ~(D.ej >> a));
-        uint32_t t = __ffs(~term) - 1;                 // trailing ones; 32 when all set (ffs(0) = 0 -> 0xffffffff)
-        if (~term == 0u) t = 32;
-        if (t >= n) { g += n; k += n; continue; }
-        g += t; k += t;
-        // the draw at k repeats the reference base of locus g (or was rejected): keep drawing for this locus
-        const uint32_t bb = b + t;
-        const uint32_t c0 = (F.c0 >> bb) & 1u ? 0xffffffffu : 0u, c1 = (F.c1 >> bb) & 1u ? 0xffffffffu : 0u, cx = (F.cx >> bb) & 1u ? 0xffffffffu : 0u;
-        for (;;) {
-            if (k - D.kw >= 32) { if (k + 32 > A.M) return false; load_draws(A, k, D, lane); }
-            const uint32_t aa = (uint32_t)(k - D.kw);
-            const uint32_t ends = (((D.e0 ^ c0) | (D.e1 ^ c1) | cx) & ~D.ej) >> aa;
-            if (ends == 0u) { k = D.kw + 32; continue; }
-            k += __ffs(ends);                          // the ending draw is consumed too
-            break;
-        }
-        g += 1;
-    }
-    return true;
-}
-
-// one rand() value; lanes agree
-__device__ __forceinline__ bool next_rand(const ChainArgs &A, unsigned long long &k, uint32_t &r)
-{
-    if (k >= A.M) return false;
-    r = (uint32_t)A.R[k++];
-    return true;
-}
-// selectMutantAllele(wild) (:338-360): index into "GCAT" of the pick; wild_idx 4 = not one of GCAT
-__device__ __forceinline__ bool select_allele(const ChainArgs &A, unsigned long long &k, uint32_t wild_idx, uint32_t &pick)
-{
-    for (;;) {
-        uint32_t r;
-        if (!next_rand(A, k, r)) return false;
-        if (r >= GLIBC_CUT4) continue;
-        if ((r & 3u) != wild_idx) { pick = r & 3u; return true; }
-    }
-}
-
-
-// Outcome of one pileup entry at a target locus, computed without side effects so that a warp can
-// evaluate 32 entries speculatively (attemptToMutateBase, stochasticSpike.c:526-904; cases as in SURVEY App. A).
-struct EntryOut {
-    uint32_t draws;        // rand() values consumed
-    uint8_t mark_self, mark_mate, filt /* 0 none, 1 P(ass), 2 K(masked), 3 O(vl) */, tally /* 0 none,1 ref,2 mut,3..6 err G,C,A,T */;
-    uint8_t npatch; uint8_t pbase[2]; uint8_t pmate[2];   // patch i: base pbase[i] on (pmate[i] ? mate : self)
-    bool ok;
-};
-
-__device__ EntryOut entry_eval(const ChainArgs &A, const PlpEntry &e, uint8_t mate_base, uint8_t mate_bq, const uint8_t *hflags, uint8_t self_handled,
-                               unsigned long long k, uint32_t thresh, uint8_t F, uint8_t Aallele)
-{
-    EntryOut o; o.draws = 0; o.mark_self = o.mark_mate = o.filt = o.tally = o.npatch = 0; o.ok = true;
-    o.pbase[0] = o.pbase[1] = o.pmate[0] = o.pmate[1] = 0;
-    if (e.skip || e.bq == 0 || self_handled) return o;                               // :1270
-    uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
-    if (e.mate >= 0 && !hflags[e.mate]) { M = mate_base; mbq = mate_bq; }                  // getBaseWithRPOcheck :387-432
-    if (M == 'N') mbq = 0;
-    if (R == 'N') rbq = 0;
-    uint8_t base = R;
-    if (M && M != R && mbq > rbq) base = M;
-    if (base == 'N') { o.mark_self = 1; o.mark_mate = M ? 1 : 0; return o; }         // :584-592
-    const unsigned long long k0 = k;
-    uint32_t r;
-    if (!next_rand(A, k, r)) { o.ok = false; return o; }
-    const bool heads = r < thresh;                                                    // coinToss :332-335
-    auto tally_base = [&](uint8_t b) { int gi = gcat_index(b); o.tally = gi < 4 ? (uint8_t)(3 + gi) : 0; };
-    auto other = [&](uint8_t &d) -> bool {                                            // selectMutantAllele(A)
-        uint32_t pick; if (!select_allele(A, k, (uint32_t)gcat_index(Aallele), pick)) return false;
-        d = (uint8_t)"GCAT"[pick]; return true;
-    };
-    if (!heads) {
-        if (base == F) o.tally = 1;
-        else { tally_base(base); o.mark_self = 1; o.mark_mate = M ? 1 : 0; }
-    } else if (!M && R == F) {                                                        // case 1
-        o.pbase[0] = Aallele; o.pmate[0] = 0; o.npatch = 1; o.tally = 2; o.filt = 1; o.mark_self = 1;
-    } else if (!M) {                                                                  // case 2
-        o.filt = 2;
-        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[0] = d; o.pmate[0] = 0; o.npatch = 1; base = d; }
-        tally_base(base); o.mark_self = 1;
-    } else if (R == F && M == F) {                                                    // case 3
-        o.pbase[0] = Aallele; o.pmate[0] = 0; o.pbase[1] = Aallele; o.pmate[1] = 1; o.npatch = 2;
-        o.mark_self = o.mark_mate = 1; o.tally = 2; o.filt = 1;
-    } else if (R == F) {                                                              // case 4 (M != F)
-        o.pbase[0] = Aallele; o.pmate[0] = 0; o.npatch = 1; o.mark_self = 1;
-        if (M == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[1] = d; o.pmate[1] = 1; o.npatch = 2; if (base == M) base = d; }
-        o.mark_mate = 1; o.filt = 3;
-        if (base == F) o.tally = 2; else tally_base(base);
-    } else if (M == F) {                                                              // case 5 (R != F)
-        o.pbase[0] = Aallele; o.pmate[0] = 1; o.npatch = 1; o.mark_mate = 1;
-        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[1] = d; o.pmate[1] = 0; o.npatch = 2; if (base == R) base = d; }
-        o.mark_self = 1; o.filt = 3;
-        if (base == F) o.tally = 2; else tally_base(base);
-    } else {                                                                          // case 6
-        o.filt = 3;
-        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[o.npatch] = d; o.pmate[o.npatch] = 0; o.npatch++; if (base == R) base = d; }
-        if (M == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[o.npatch] = d; o.pmate[o.npatch] = 1; o.npatch++; if (base == M) base = d; }
-        tally_base(base); o.mark_self = o.mark_mate = 1;
-    }
-    o.draws = (uint32_t)(k - k0);
-    return o;
-}
-
-__global__ void __launch_bounds__(32)
-chain_kernel(ChainArgs A)
-{
-    const int lane = threadIdx.x;
-    int64_t g = 0; unsigned long long k = 0;
-    DrawWin D; RefWin F;
-    unsigned long long odd_bloom = 0;
-    D.kw = ~0ull >> 1; F.gw = -1000;                 // force the first loads
-    D.e0 = D.e1 = D.ej = F.c0 = F.c1 = F.cx = 0;
-    for (size_t h = 0; h < A.H; h++) {
-        const HitTarget ht = A.hits[h];
-        if (!chain_walk(A, g, ht.locus_index, k, D, F, lane)) { if (lane == 0) set_err(A.err, SSB_E_STATE, k); return; }
-        // ---- the target locus itself -----------------------------------------------------------
-        const unsigned long long k_at = k;
-        const uint8_t Fb = A.contig_seq[ht.tid][ht.pos];
-        uint32_t pick;
-        if (!select_allele(A, k, A.cls[g], pick)) { if (lane == 0) set_err(A.err, SSB_E_STATE, k); return; }     // :1197
-        uint8_t allele = (uint8_t)"GCAT"[pick];
-        if (ht.base == 'G' || ht.base == 'C' || ht.base == 'A' || ht.base == 'T') allele = ht.base;                // :1199-1203
-        const unsigned long long e0 = A.eoff[h], e1 = A.eoff[h + 1];
-        PlpEntry *ents = A.ent + e0;
-        uint8_t *hf = A.hflag + e0;
-        const uint32_t n = (uint32_t)(e1 - e0);
-        uint32_t ref_cnt = 0, mut_cnt = 0, err0 = 0, err1 = 0, err2 = 0, err3 = 0, fP = 0, fK = 0, fO = 0;
-        uint32_t j0 = 0;
-        // odd patches made at EARLIER targets (the list only grows at later loci, so it is fixed for this target)
-        __syncwarp();
-        const unsigned int n_odd = min(*(volatile unsigned int *)A.n_odd, A.odd_cap);
-        unsigned long long new_bloom = 0;
-        while (j0 < n) {
-            const uint32_t j = j0 + lane;
-            const bool in = j < n;
-            PlpEntry e; e.skip = 1; e.bq = 0; e.mate = -1; e.base = 0; e.ord = 0; e.qpos = 0;
-            if (in) e = ents[j];
-            const uint8_t handled = in ? hf[j] : 1;
-            uint8_t mate_base = 0, mate_bq = 0; PlpEntry me_; me_.ord = 0; me_.qpos = 0; me_.skip = 0;
-            if (in && e.mate >= 0) { me_ = ents[e.mate]; mate_base = me_.base; mate_bq = me_.bq; }
-            if (n_odd && in) {                        // bases an earlier odd patch rewrote (see OddPatch)
-                if (odd_bloom & odd_bit(e.ord)) e.base = odd_view(A.odd, n_odd, e.ord, e.qpos, ht.tid, ht.pos, e.base);
-                if (e.mate >= 0 && (odd_bloom & odd_bit(me_.ord))) mate_base = odd_view(A.odd, n_odd, me_.ord, me_.qpos, ht.tid, ht.pos, mate_base);
-            }
-            // does this entry toss (or otherwise act)?  needed to give every lane its draw index
-            bool tosses = false;
-            if (in && !e.skip && e.bq != 0 && !handled) {
-                uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
-                if (e.mate >= 0 && !hf[e.mate]) { M = mate_base; mbq = mate_bq; }
-                if (M == 'N') mbq = 0;
-                if (R == 'N') rbq = 0;
-                uint8_t base = R; if (M && M != R && mbq > rbq) base = M;
-                tosses = base != 'N';
-            }
-            const unsigned tossmask = __ballot_sync(0xffffffffu, tosses);
-            const unsigned long long my_k = k + __popc(tossmask & ((1u << lane) - 1u));
-            EntryOut o = entry_eval(A, e, mate_base, mate_bq, hf, handled, my_k, ht.thresh, Fb, allele);
-            // a lane "breaks" the speculation of the lanes after it when it used more than its one draw, or
-            // when it marks an entry of this batch as handled
-            const bool marks_in_batch = in && o.mark_mate && e.mate >= 0 && (uint32_t)e.mate < j0 + 32;
-            const bool breaks = !o.ok || o.draws > (tosses ? 1u : 0u) || marks_in_batch;
-            const unsigned bmask = __ballot_sync(0xffffffffu, breaks);
-            const uint32_t last = bmask ? (uint32_t)(__ffs(bmask) - 1) : 31u;         // commit lanes [0, last]
-            if (__ballot_sync(0xffffffffu, !o.ok && (uint32_t)lane <= last)) { if (lane == 0) set_err(A.err, SSB_E_STATE, k); return; }
-            const bool commit = in && (uint32_t)lane <= last;
-            if (commit) {
-                if (o.mark_self) hf[j] = 1;
-                if (o.mark_mate && e.mate >= 0) hf[e.mate] = 1;
-                for (int p = 0; p < o.npatch; p++) {
-                    unsigned int slot = atomicAdd(A.n_patches, 1u);
-                    const PlpEntry &pe = o.pmate[p] ? me_ : e;
-                    if (slot < A.patch_cap) {
-                        Patch pt; pt.ord = pe.ord; pt.qpos = pe.qpos; pt.base = o.pbase[p]; pt.pad = (uint32_t)h;
-                        A.patches[slot] = pt;
-                    }
-                    if (o.pmate[p] && me_.skip) {     // the mate sits in a D/N here: the patch lands on a base of a later locus
-                        unsigned int os = atomicAdd(A.n_odd, 1u);
-                        if (os < A.odd_cap) { OddPatch q; q.ord = pe.ord; q.qpos = pe.qpos; q.base = o.pbase[p]; q.h = (uint32_t)h; q.tid = ht.tid; q.pos = ht.pos; A.odd[os] = q; }
-                        else set_err(A.err, SSB_E_NOMEM, (unsigned long long)h);
-                        new_bloom |= odd_bit(pe.ord);
-                    }
-                }
-            }
-            const uint32_t used = commit ? o.draws : 0u;
-            uint32_t tot = used;
-            for (int s = 16; s; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
-            k += tot;
-            ref_cnt += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 1));
-            mut_cnt += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 2));
-            err0 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 3));
-            err1 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 4));
-            err2 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 5));
-            err3 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 6));
-            fP |= __ballot_sync(0xffffffffu, commit && o.filt == 1);
-            fK |= __ballot_sync(0xffffffffu, commit && o.filt == 2);
-            fO |= __ballot_sync(0xffffffffu, commit && o.filt == 3);
-            __syncwarp();
-            j0 += last + 1;
-        }
-        for (int sft = 16; sft; sft >>= 1) new_bloom |= __shfl_xor_sync(0xffffffffu, new_bloom, sft);
-        odd_bloom |= new_bloom;
-        __threadfence();
-        if (lane == 0) {
-            ssb_target_result &r = A.res[ht.target];
-            r.ref_base = Fb; r.mutant_allele = allele;
-            // the filter only moves UNDETECTED -> PASS (cases 1,3), -> MASKED (case 2, unless MASKED_OVL), -> MASKED_OVL (cases 4-6)
-            r.filter = fO ? SSB_F_MASKED_OVL : fK ? SSB_F_MASKED : fP ? SSB_F_PASS : SSB_F_UNDETECTED;
-            r.ref_cnt = (int32_t)ref_cnt; r.mut_cnt = (int32_t)mut_cnt;
-            r.err_cnt[0] = (int32_t)err0; r.err_cnt[1] = (int32_t)err1; r.err_cnt[2] = (int32_t)err2; r.err_cnt[3] = (int32_t)err3;
-            r.rng_offset = (int64_t)k_at;
-        }
-        g += 1;
-    }
-    if (lane == 0) { *A.draws_out = k; *A.odd_bloom = odd_bloom; }
-}
+#include "spike_chain.cuh"
 
 // ------------------------------------------------------------------------------------------
 // device arena: one stream-ordered allocation per array, all released at the end of the run
@@ -1338,10 +1041,61 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         glibc_seed_window(seed, seedw);
         uint32_t *d_seedw = ar.get<uint32_t>(61); SPK_CHECK_ARENA(ar);
         SSB_CUDA(ctx, cudaMemcpyAsync(d_seedw, seedw, sizeof seedw, cudaMemcpyHostToDevice, s));
-        // draws: ~4/3 per walked locus + one per pileup entry (+ extras); grow and redo if the chain runs out
-        unsigned long long M = (unsigned long long)((double)n_walk * 1.40) + 3 * E + 65536;
+        // reference class bit planes
+        const size_t cwords = (size_t)((n_walk + 31) >> 5) + 160;
+        uint32_t *pc0 = ar.get<uint32_t>(cwords), *pc1 = ar.get<uint32_t>(cwords), *pcx = ar.get<uint32_t>(cwords);
+        SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemsetAsync(pc0, 0, cwords * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pc1, 0, cwords * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pcx, 0xff, cwords * 4, s));
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, cls_pack_kernel, grid_for(((size_t)n_walk + 31) & ~(size_t)31, 256), 256, 0, s, cls, n_walk, pc0, pc1, pcx);
+
+        // ---- expected draws per chunk: window centres / widths, and the stream length
+        const char *env_serial = getenv("SSB_CHAIN_SERIAL");
+        int P = 1; int64_t Lc = n_walk;
+        const char *env_chunk = getenv("SSB_CHAIN_CHUNK");                 // loci per chunk (testing / tuning)
+        if (!(env_serial && env_serial[0] == '1') && (n_walk >= (1 << 20) || env_chunk)) {
+            Lc = n_walk / 512; if (Lc < 32768) Lc = 32768;
+            if (env_chunk && atoll(env_chunk) >= 64) Lc = atoll(env_chunk);
+            Lc = (Lc + 31) & ~(int64_t)31;
+            P = (int)((n_walk + Lc - 1) / Lc);
+            if (P < 2) { P = 1; Lc = n_walk; }
+        }
+        double *d_mean = ar.get<double>((size_t)P), *d_var = ar.get<double>((size_t)P);
+        SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemsetAsync(d_mean, 0, P * sizeof(double), s)); SSB_CUDA(ctx, cudaMemsetAsync(d_var, 0, P * sizeof(double), s));
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, chunk_stats_kernel, grid_for((size_t)P * 32, 128), 128, 0, s, pcx, n_walk, Lc, P, d_mean, d_var);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, expect_kernel, grid_for(H * 32, 128), 128, 0, s, hits, H, eoff, ent, (const uint8_t *const *)sp->d_seq_ptrs, Lc, d_mean, d_var);
+        std::vector<double> h_mean(P), h_var(P);
+        SSB_CUDA(ctx, cudaMemcpyAsync(h_mean.data(), d_mean, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(h_var.data(), d_var, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        std::vector<ChunkWin> h_win(P);
+        std::vector<ChunkDesc> h_chunks(P);
+        double cm = 0, cv = 0; unsigned long long woff = 0, wmax = 0;
+        for (int j = 0; j < P; j++) {
+            const double half = j == 0 ? 0.0 : 6.0 * sqrt(cv) + 48.0;
+            double lo = cm - half; if (lo < 0) lo = 0;
+            h_win[j].klo = (unsigned long long)lo; h_win[j].W = j == 0 ? 1u : (uint32_t)(cm + half - (double)h_win[j].klo) + 2u; h_win[j].pad = 0;
+            h_win[j].off = woff; woff += h_win[j].W; if (h_win[j].W > wmax) wmax = h_win[j].W;
+            h_chunks[j].g0 = (int64_t)j * Lc; h_chunks[j].g1 = (int64_t)(j + 1) * Lc < n_walk ? (int64_t)(j + 1) * Lc : n_walk;
+            h_chunks[j].k_in = 0; h_chunks[j].k_out = ~0ull;
+            cm += h_mean[j]; cv += h_var[j];
+        }
+        // the stream must cover the top of the last window (and everything a lone walker can reach)
+        unsigned long long M = (unsigned long long)(cm + 8.0 * sqrt(cv)) + 3 * E + (1u << 17);
         float ms_rng = 0, ms_chain = 0;
-        for (int attempt = 0; attempt < 6; attempt++) {
+        unsigned int *d_flags = ar.get<unsigned int>(1);
+        ChunkWin *d_win = ar.get<ChunkWin>((size_t)P); ChunkDesc *d_chunks = ar.get<ChunkDesc>((size_t)P), *d_serial = ar.get<ChunkDesc>(1);
+        uint32_t *d_ncls = ar.get<uint32_t>((size_t)P);
+        unsigned long long *kbuf = NULL; uint32_t *lobuf = NULL;
+        if (P > 1) { kbuf = ar.get<unsigned long long>(2 * woff); lobuf = ar.get<uint32_t>(2 * woff); }
+        SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_win, h_win.data(), P * sizeof(ChunkWin), cudaMemcpyHostToDevice, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_chunks, h_chunks.data(), P * sizeof(ChunkDesc), cudaMemcpyHostToDevice, s));
+        ChunkDesc serial_cd; serial_cd.g0 = 0; serial_cd.g1 = n_walk; serial_cd.k_in = 0; serial_cd.k_out = ~0ull;
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_serial, &serial_cd, sizeof serial_cd, cudaMemcpyHostToDevice, s));
+        bool parallel = P > 1;
+        stats->n_runs = (int64_t)R;
+        for (int attempt = 0; attempt < 8; attempt++) {
             M = (M + RNG_BLOCK - 1) / RNG_BLOCK * RNG_BLOCK;
             const size_t nblocks = (size_t)(M / RNG_BLOCK);
             // per-block polynomials x^(310 + b*RNG_BLOCK) mod P: seed independent, built on the host (31x31 products)
@@ -1350,34 +1104,62 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             glibc_poly_xpow(RNG_BLOCK, stepb);
             glibc_poly_xpow(310, cur);
             for (size_t b = 0; b < nblocks; b++) { memcpy(&bp[b * GLIBC_DEG], cur, sizeof cur); glibc_poly_mulmod(cur, stepb, tmpb); memcpy(cur, tmpb, sizeof cur); }
+            const size_t ewords = (size_t)(M >> 5) + 160;
             uint32_t *d_bp = ar.get<uint32_t>(bp.size()); int32_t *Rs = ar.get<int32_t>(M + 64);
+            uint32_t *pe0 = ar.get<uint32_t>(ewords), *pe1 = ar.get<uint32_t>(ewords), *pej = ar.get<uint32_t>(ewords);
             SPK_CHECK_ARENA(ar);
             SSB_CUDA(ctx, cudaMemcpyAsync(d_bp, bp.data(), bp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            SSB_CUDA(ctx, cudaMemsetAsync(pe0 + (M >> 5), 0, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pe1 + (M >> 5), 0, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pej + (M >> 5), 0, 160 * 4, s));
             SSB_CUDA(ctx, cudaEventRecord(ev[8], s));
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, d_seedw, Rs, M);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, d_seedw, Rs, M, pe0, pe1, pej);
             SSB_CUDA(ctx, cudaEventRecord(ev[9], s));
-            SSB_CUDA(ctx, cudaMemsetAsync(hflag, 0, E, s));
-            SSB_CUDA(ctx, cudaMemsetAsync(n_patches, 0, sizeof(unsigned int), s));
-            SSB_CUDA(ctx, cudaMemsetAsync(d_nodd, 0, sizeof(unsigned int), s));
-            SSB_CUDA(ctx, cudaMemsetAsync(d_bloom, 0, sizeof(unsigned long long), s));
             ChainArgs A;
+            A.e0 = pe0; A.e1 = pe1; A.ej = pej; A.R = Rs; A.M = M; A.c0 = pc0; A.c1 = pc1; A.cx = pcx; A.n_walk = n_walk;
+            A.hits = hits; A.H = H; A.eoff = eoff; A.ent = ent; A.hflag = hflag; A.res = d_res;
+            A.patches = patches; A.n_patches = n_patches; A.patch_cap = (unsigned int)(2 * E + 16);
             A.odd = d_odd; A.n_odd = d_nodd; A.odd_cap = odd_cap; A.odd_bloom = d_bloom;
-            A.cls = cls; A.n_cov = n_walk; A.R = Rs; A.M = M; A.hits = hits; A.H = H; A.eoff = eoff; A.ent = ent; A.hflag = hflag;
-            A.res = d_res; A.patches = patches; A.n_patches = n_patches; A.patch_cap = (unsigned int)(2 * E + 16);
-            A.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; A.draws_out = d_draws; A.err = d_err;
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, 1, 32, 0, s, A);
+            A.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; A.err = d_err;
+            unsigned int flags = 0, n_odd_h = 0;
+            auto reset_apply = [&]() -> int {
+                SSB_CUDA(ctx, cudaMemsetAsync(hflag, 0, E, s));
+                SSB_CUDA(ctx, cudaMemsetAsync(n_patches, 0, sizeof(unsigned int), s));
+                SSB_CUDA(ctx, cudaMemsetAsync(d_nodd, 0, sizeof(unsigned int), s));
+                SSB_CUDA(ctx, cudaMemsetAsync(d_bloom, 0, sizeof(unsigned long long), s));
+                SSB_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(unsigned int), s));
+                return SSB_OK;
+            };
+            if ((rc = reset_apply())) return rc;
+            if (parallel) {
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, P, P1_THREADS, 0, s, A, Lc, d_win, kbuf, lobuf, woff, d_ncls, d_flags);
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, P, d_win, kbuf, lobuf, d_ncls, d_chunks, d_flags);
+                SSB_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
+                SSB_CUDA(ctx, cudaStreamSynchronize(s));
+                if (!flags) {
+                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, grid_for((size_t)P * 32, 128), 128, 0, s, A, d_chunks, P, d_draws, d_flags);
+                    SSB_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
+                    SSB_CUDA(ctx, cudaMemcpyAsync(&n_odd_h, d_nodd, 4, cudaMemcpyDeviceToHost, s));
+                    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+                }
+                if (flags & CHAIN_OVERRUN) { M *= 2; continue; }
+                if (flags || n_odd_h) {               // window miss / too complex / odd patches: the plain serial chain decides
+                    parallel = false;
+                    if ((rc = reset_apply())) return rc;
+                }
+            }
+            if (!parallel) {
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, 1, 32, 0, s, A, d_serial, 1, d_draws, d_flags);
+                SSB_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
+                SSB_CUDA(ctx, cudaStreamSynchronize(s));
+                if (flags & CHAIN_OVERRUN) { M *= 2; continue; }
+            }
             SSB_CUDA(ctx, cudaEventRecord(ev[10], s));
             DevErr e;
             SSB_CUDA(ctx, cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, s));
             SSB_CUDA(ctx, cudaStreamSynchronize(s));
             ms_rng += ev_ms(ev[8], ev[9]); ms_chain += ev_ms(ev[9], ev[10]);
-            if (e.code == SSB_E_STATE) {                                   // the stream was too short: double it and redo the chain
-                SSB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(DevErr), s));
-                M *= 2;
-                if (attempt == 5) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: rand() stream exhausted"); return SSB_E_STATE; }
-                continue;
-            }
             if (e.code) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: %s", ssb_strerror(e.code)); return e.code; }
+            if (attempt == 7 && (flags & CHAIN_OVERRUN)) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: rand() stream exhausted"); return SSB_E_STATE; }
+            stats->chain_mode = parallel ? P : 1;
             break;
         }
         stats->ms_rng = ms_rng; stats->ms_chain = ms_chain;
@@ -1490,7 +1272,7 @@ extern "C" int ssb_spike_rand(ssb_spike *sp, unsigned seed, uint64_t k0, size_t 
     SPK_CHECK_ARENA(ar);
     SSB_CUDA(ctx, cudaMemcpyAsync(d_bp, bp.data(), bp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     SSB_CUDA(ctx, cudaMemcpyAsync(d_seedw, seedw, sizeof seedw, cudaMemcpyHostToDevice, s));
-    SSB_LAUNCH(ctx, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, d_seedw, R, M);
+    SSB_LAUNCH(ctx, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, d_seedw, R, M, (uint32_t *)NULL, (uint32_t *)NULL, (uint32_t *)NULL);
     SSB_CUDA(ctx, cudaMemcpyAsync(out_host, R, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     SSB_CUDA(ctx, cudaStreamSynchronize(s));
     return SSB_OK;

@@ -1,0 +1,554 @@
+// spike_chain.cuh -- the reference's random stream and everything that consumes it in order.
+// (Included by spike.cu inside its anonymous namespace.)
+//
+// The reference draws from ONE glibc rand() stream: one selectMutantAllele(ref[pos]) per covered locus
+// (stochasticSpike.c:1197; it redraws while the pick equals the reference base, :350-354) plus the coin tosses
+// and extra picks of attemptToMutateBase at every target (:526-904).  The offset at which a target tosses is
+// therefore the end of a data-dependent walk over every covered locus before it.
+//
+// B200 formulation:
+//   rng_fill      the stream itself is generated in parallel by polynomial skip-ahead (rng_glibc.cuh); next to
+//                 the raw values it writes three bit planes (class bit 0, class bit 1, rejected-by-randomNum).
+//   cls_pack      the reference classes of the covered loci as three bit planes (bit 0, bit 1, "not GCAT").
+//   walk_loci     lock step of draw k+i against locus g+i on 32-bit words: term = ((e0^c0)|(e1^c1)|cx) & ~ej says
+//                 which draws end their locus; the run of trailing ones advances both cursors, a zero starts
+//                 the "repeat draw" loop of that locus.  ~4 loci per iteration.
+//   phase 1       the walk is a monotone map k_in -> k_out per chunk of loci, and walkers that meet stay
+//                 together.  Each chunk (one block) simulates EVERY start offset of a +-6 sigma window around
+//                 the expected offset (mean 4/3 draw per GCAT locus, variance 4/9) and drops duplicates at
+//                 geometrically spaced checkpoints: W walkers shrink like W/sqrt(loci), so a chunk costs
+//                 ~1.7 W sqrt(L) walker-steps instead of W L.  Targets inside a chunk are dry-run per walker.
+//   phase 2       one warp composes the chunk maps in order (a table lookup per chunk): exact start offset of
+//                 every chunk.
+//   phase 3       one warp per chunk repeats the walk from its exact offset and applies the targets for real
+//                 (speculative 32-entry batches).  Exit offsets must equal the next chunk's start (checked).
+//   fallback      a window miss, an inconsistent exit, a dry-run that was too complex, or any "odd patch"
+//                 (which changes bases later targets see) reruns phase 3 as ONE chunk = the plain serial chain.
+#pragma once
+
+// ------------------------------------------------------------------------------------------
+// glibc rand() stream
+// ------------------------------------------------------------------------------------------
+struct RngTables {
+    uint32_t seg[RNG_TPB][GLIBC_DEG];     // x^(t * RNG_SEG) mod P
+};
+
+// out[i] = rand() #(k_base + i) for i in [0, M): thread (b, t) produces outputs [b*RNG_BLOCK + t*RNG_SEG, +RNG_SEG).
+// e0/e1/ej (optional): bit planes of the same outputs, bit i of word w <-> output 32w + i.
+__global__ void __launch_bounds__(RNG_TPB)
+rng_fill_kernel(const uint32_t *__restrict__ block_poly /* [nblocks][31]: x^(310 + k_base + b*RNG_BLOCK) */, const RngTables *__restrict__ tab,
+                const uint32_t *__restrict__ seedw /* 61 words */, int32_t *__restrict__ out, unsigned long long M,
+                uint32_t *__restrict__ e0, uint32_t *__restrict__ e1, uint32_t *__restrict__ ej)
+{
+    __shared__ uint32_t s_w[61];
+    __shared__ uint32_t s_bp[GLIBC_DEG];
+    if (threadIdx.x < 61) s_w[threadIdx.x] = seedw[threadIdx.x];
+    if (threadIdx.x < GLIBC_DEG) s_bp[threadIdx.x] = block_poly[(size_t)blockIdx.x * GLIBC_DEG + threadIdx.x];
+    __syncthreads();
+    const unsigned long long k0 = (unsigned long long)blockIdx.x * RNG_BLOCK + (unsigned long long)threadIdx.x * RNG_SEG;
+    if (k0 >= M) return;
+    uint32_t a[GLIBC_DEG], b[GLIBC_DEG], c[GLIBC_DEG], h[GLIBC_DEG];
+    for (int i = 0; i < GLIBC_DEG; i++) { a[i] = s_bp[i]; b[i] = tab->seg[threadIdx.x][i]; }
+    glibc_poly_mulmod(a, b, c);
+    glibc_history(c, s_w, h);                        // h[t] = r[344 + k0 - 31 + t]
+    unsigned long long k = k0;
+    const unsigned long long kend = (k0 + RNG_SEG < M) ? k0 + RNG_SEG : M;
+    uint32_t w0 = 0, w1 = 0, wj = 0;
+    while (k < kend) {
+#pragma unroll
+        for (int i = 0; i < GLIBC_DEG; i++) {        // new word replaces r[n-31]; r[n-3] sits three slots back
+            h[i] = h[i] + h[(i + 28) % GLIBC_DEG];
+            if (k < kend) {
+                const uint32_t r = h[i] >> 1;
+                out[k] = (int32_t)r;
+                const uint32_t bit = (uint32_t)(k & 31);
+                w0 |= (r & 1u) << bit; w1 |= ((r >> 1) & 1u) << bit; wj |= (r >= GLIBC_CUT4 ? 1u : 0u) << bit;
+                if (bit == 31 || k + 1 == kend) {
+                    if (e0) { e0[k >> 5] = w0; e1[k >> 5] = w1; ej[k >> 5] = wj; }
+                    w0 = w1 = wj = 0;
+                }
+            }
+            k++;
+        }
+    }
+}
+
+// reference classes of covered loci [0, n) -> bit planes (bit 0, bit 1, "other")
+__global__ void cls_pack_kernel(const uint8_t *__restrict__ cls, int64_t n, uint32_t *__restrict__ c0, uint32_t *__restrict__ c1, uint32_t *__restrict__ cx)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = g < n ? cls[g] : 4u;
+    const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1u), b1 = __ballot_sync(0xffffffffu, c & 2u), bx = __ballot_sync(0xffffffffu, c == 4u);
+    if ((threadIdx.x & 31) == 0 && (g >> 5) <= ((n + 31) >> 5)) { c0[g >> 5] = b0; c1[g >> 5] = b1; cx[g >> 5] = bx; }
+}
+
+// ------------------------------------------------------------------------------------------
+// shared state of the chain kernels
+// ------------------------------------------------------------------------------------------
+struct ChainArgs {
+    const uint32_t *e0, *e1, *ej; const int32_t *R; unsigned long long M;      // draws [0, M), M a multiple of 32 (+2 words of padding)
+    const uint32_t *c0, *c1, *cx; int64_t n_walk;                               // covered loci [0, n_walk)
+    const HitTarget *hits; size_t H;
+    const unsigned long long *eoff; PlpEntry *ent; uint8_t *hflag;
+    ssb_target_result *res;
+    Patch *patches; unsigned int *n_patches; unsigned int patch_cap;
+    OddPatch *odd; unsigned int *n_odd; unsigned int odd_cap; unsigned long long *odd_bloom;
+    const uint8_t *const *contig_seq;
+    DevErr *err;
+};
+
+struct ChunkDesc { int64_t g0, g1; unsigned long long k_in, k_out; };            // k_out = ~0: unknown (no check)
+enum { CHAIN_OVERRUN = 1, CHAIN_MISS = 2, CHAIN_COMPLEX = 4, CHAIN_INCONSISTENT = 8 };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Consumes the draws of covered loci [g, g_to): per locus, rand() until the pick differs from the reference base
+// (selectMutantAllele / randomNum, stochasticSpike.c:283-302, 338-360).  false = the stream is too short.
+template <bool PF>
+__device__ __forceinline__ bool walk_loci(const ChainArgs &A, int64_t &g, const int64_t g_to, unsigned long long &k)
+{
+    while (g < g_to) {
+        const uint32_t a = (uint32_t)(k & 31), b = (uint32_t)(g & 31);
+        const size_t we = (size_t)(k >> 5), wc = (size_t)(g >> 5);
+        if (k + 64 > A.M) return false;
+        if (PF) {
+            if ((we & 31) == 0) { prefetch_l2(A.e0 + we + 64); prefetch_l2(A.e1 + we + 64); prefetch_l2(A.ej + we + 64); }
+            if ((wc & 31) == 0) { prefetch_l2(A.c0 + wc + 64); prefetch_l2(A.c1 + wc + 64); prefetch_l2(A.cx + wc + 64); }
+        }
+        const uint32_t e0 = A.e0[we] >> a, e1 = A.e1[we] >> a, ej = A.ej[we] >> a;
+        const uint32_t c0 = A.c0[wc] >> b, c1 = A.c1[wc] >> b, cx = A.cx[wc] >> b;
+        uint32_t n = 32 - a; if (32 - b < n) n = 32 - b; if ((uint64_t)(g_to - g) < n) n = (uint32_t)(g_to - g);
+        const uint32_t term = ((e0 ^ c0) | (e1 ^ c1) | cx) & ~ej;       // bit i: draw k+i ends locus g+i
+        const uint32_t t = (~term) ? (uint32_t)(__ffs(~term) - 1) : 32u;
+        if (t >= n) { g += n; k += n; continue; }
+        g += t; k += t;
+        // draw k repeats the reference base of locus g (or was rejected): keep drawing for this locus
+        const uint32_t m0 = ((c0 >> t) & 1u) ? 0xffffffffu : 0u, m1 = ((c1 >> t) & 1u) ? 0xffffffffu : 0u, mx = ((cx >> t) & 1u) ? 0xffffffffu : 0u;
+        for (;;) {
+            if (k + 64 > A.M) return false;
+            const size_t w = (size_t)(k >> 5);
+            const uint32_t ends = (((A.e0[w] ^ m0) | (A.e1[w] ^ m1) | mx) & ~A.ej[w]) >> (uint32_t)(k & 31);
+            if (ends == 0u) { k = (unsigned long long)(w + 1) << 5; continue; }
+            k += (unsigned long long)__ffs(ends);                       // the ending draw is consumed too
+            break;
+        }
+        g += 1;
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool next_rand(const ChainArgs &A, unsigned long long &k, uint32_t &r)
+{
+    if (k + 64 > A.M) return false;
+    r = (uint32_t)A.R[k++];
+    return true;
+}
+// selectMutantAllele(wild) (:338-360): index into "GCAT" of the pick; wild_idx 4 = not one of GCAT
+__device__ __forceinline__ bool select_allele(const ChainArgs &A, unsigned long long &k, uint32_t wild_idx, uint32_t &pick)
+{
+    for (;;) {
+        uint32_t r;
+        if (!next_rand(A, k, r)) return false;
+        if (r >= GLIBC_CUT4) continue;
+        if ((r & 3u) != wild_idx) { pick = r & 3u; return true; }
+    }
+}
+__device__ __forceinline__ uint32_t locus_class(const ChainArgs &A, int64_t g)
+{
+    const size_t w = (size_t)(g >> 5); const uint32_t b = (uint32_t)(g & 31);
+    if ((A.cx[w] >> b) & 1u) return 4u;
+    return ((A.c0[w] >> b) & 1u) | (((A.c1[w] >> b) & 1u) << 1);
+}
+
+// Outcome of one pileup entry at a target locus, computed without side effects so that it can be evaluated
+// speculatively (attemptToMutateBase, stochasticSpike.c:526-904; cases as in SURVEY App. A).
+struct EntryOut {
+    uint32_t draws;        // rand() values consumed
+    uint8_t mark_self, mark_mate, filt /* 0 none, 1 P(ass), 2 K(masked), 3 O(vl) */, tally /* 0 none,1 ref,2 mut,3..6 err G,C,A,T */;
+    uint8_t npatch; uint8_t pbase[2]; uint8_t pmate[2];   // patch i: base pbase[i] on (pmate[i] ? mate : self)
+    bool ok;
+};
+
+__device__ EntryOut entry_eval(const ChainArgs &A, const PlpEntry &e, uint8_t mate_base, uint8_t mate_bq, bool mate_handled, bool self_handled,
+                               unsigned long long k, uint32_t thresh, uint8_t F, uint8_t Aallele)
+{
+    EntryOut o; o.draws = 0; o.mark_self = o.mark_mate = o.filt = o.tally = o.npatch = 0; o.ok = true;
+    o.pbase[0] = o.pbase[1] = o.pmate[0] = o.pmate[1] = 0;
+    if (e.skip || e.bq == 0 || self_handled) return o;                               // :1270
+    uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
+    if (e.mate >= 0 && !mate_handled) { M = mate_base; mbq = mate_bq; }               // getBaseWithRPOcheck :387-432
+    if (M == 'N') mbq = 0;
+    if (R == 'N') rbq = 0;
+    uint8_t base = R;
+    if (M && M != R && mbq > rbq) base = M;
+    if (base == 'N') { o.mark_self = 1; o.mark_mate = M ? 1 : 0; return o; }         // :584-592
+    const unsigned long long k0 = k;
+    uint32_t r;
+    if (!next_rand(A, k, r)) { o.ok = false; return o; }
+    const bool heads = r < thresh;                                                    // coinToss :332-335
+    auto tally_base = [&](uint8_t b) { int gi = gcat_index(b); o.tally = gi < 4 ? (uint8_t)(3 + gi) : 0; };
+    auto other = [&](uint8_t &d) -> bool {                                            // selectMutantAllele(A)
+        uint32_t pick; if (!select_allele(A, k, (uint32_t)gcat_index(Aallele), pick)) return false;
+        d = (uint8_t)"GCAT"[pick]; return true;
+    };
+    if (!heads) {
+        if (base == F) o.tally = 1;
+        else { tally_base(base); o.mark_self = 1; o.mark_mate = M ? 1 : 0; }
+    } else if (!M && R == F) {                                                        // case 1
+        o.pbase[0] = Aallele; o.pmate[0] = 0; o.npatch = 1; o.tally = 2; o.filt = 1; o.mark_self = 1;
+    } else if (!M) {                                                                  // case 2
+        o.filt = 2;
+        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[0] = d; o.pmate[0] = 0; o.npatch = 1; base = d; }
+        tally_base(base); o.mark_self = 1;
+    } else if (R == F && M == F) {                                                    // case 3
+        o.pbase[0] = Aallele; o.pmate[0] = 0; o.pbase[1] = Aallele; o.pmate[1] = 1; o.npatch = 2;
+        o.mark_self = o.mark_mate = 1; o.tally = 2; o.filt = 1;
+    } else if (R == F) {                                                              // case 4 (M != F)
+        o.pbase[0] = Aallele; o.pmate[0] = 0; o.npatch = 1; o.mark_self = 1;
+        if (M == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[1] = d; o.pmate[1] = 1; o.npatch = 2; if (base == M) base = d; }
+        o.mark_mate = 1; o.filt = 3;
+        if (base == F) o.tally = 2; else tally_base(base);
+    } else if (M == F) {                                                              // case 5 (R != F)
+        o.pbase[0] = Aallele; o.pmate[0] = 1; o.npatch = 1; o.mark_mate = 1;
+        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[1] = d; o.pmate[1] = 0; o.npatch = 2; if (base == R) base = d; }
+        o.mark_self = 1; o.filt = 3;
+        if (base == F) o.tally = 2; else tally_base(base);
+    } else {                                                                          // case 6
+        o.filt = 3;
+        if (R == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[o.npatch] = d; o.pmate[o.npatch] = 0; o.npatch++; if (base == R) base = d; }
+        if (M == Aallele) { uint8_t d; if (!other(d)) { o.ok = false; return o; } o.pbase[o.npatch] = d; o.pmate[o.npatch] = 1; o.npatch++; if (base == M) base = d; }
+        tally_base(base); o.mark_self = o.mark_mate = 1;
+    }
+    o.draws = (uint32_t)(k - k0);
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// expected draws (mean, variance) per chunk: centres and widths of the phase-1 windows
+// ------------------------------------------------------------------------------------------
+__global__ void chunk_stats_kernel(const uint32_t *__restrict__ cx, int64_t n_walk, int64_t L, int P, double *__restrict__ mean, double *__restrict__ var)
+{
+    // one warp per chunk: count the loci whose reference base is not one of GCAT (exactly one draw each)
+    const int lane = threadIdx.x & 31;
+    const int j = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (j >= P) return;
+    const int64_t g0 = (int64_t)j * L, g1 = (g0 + L < n_walk) ? g0 + L : n_walk;
+    long long nx = 0;
+    for (int64_t w = (g0 >> 5) + lane; w <= ((g1 - 1) >> 5); w += 32) {
+        uint32_t v = cx[w];
+        const int64_t lo = w << 5;
+        if (lo < g0) v &= ~0u << (uint32_t)(g0 - lo);
+        if (lo + 32 > g1) v &= (g1 - lo >= 32) ? ~0u : ((1u << (uint32_t)(g1 - lo)) - 1u);
+        nx += __popc(v);
+    }
+    for (int s = 16; s; s >>= 1) nx += __shfl_xor_sync(0xffffffffu, nx, s);
+    if (lane == 0) {
+        const double n4 = (double)((g1 - g0) - nx);
+        atomicAdd(&mean[j], n4 * (4.0 / 3.0) + (double)nx);
+        atomicAdd(&var[j], n4 * (4.0 / 9.0));
+    }
+}
+
+// one warp per hit target: expected number of toss draws and its variance
+__global__ void expect_kernel(const HitTarget *__restrict__ hits, size_t H, const unsigned long long *__restrict__ eoff, const PlpEntry *__restrict__ ent,
+                              const uint8_t *const *__restrict__ contig_seq, int64_t L, double *__restrict__ mean, double *__restrict__ var)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t h = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (h >= H) return;
+    const HitTarget ht = hits[h];
+    const uint8_t F = contig_seq[ht.tid][ht.pos];
+    const double p = (double)ht.thresh / 2147483648.0;
+    const PlpEntry *e = ent + eoff[h];
+    const uint32_t n = (uint32_t)(eoff[h + 1] - eoff[h]);
+    double m = 0, v = 0;
+    for (uint32_t j = lane; j < n; j += 32) {
+        const PlpEntry x = e[j];
+        if (x.skip || x.bq == 0) continue;
+        uint8_t R = x.base, M = 0; int rbq = x.bq, mbq = 0;
+        if (x.mate >= 0) { M = e[x.mate].base; mbq = e[x.mate].bq; }
+        if (M == 'N') mbq = 0;
+        if (R == 'N') rbq = 0;
+        uint8_t base = R; if (M && M != R && mbq > rbq) base = M;
+        if (base == 'N') continue;
+        m += 1.0;
+        if (x.mate >= 0) {
+            // the mate tosses too only if this entry comes up tails on the reference base (:619-620)
+            const PlpEntry y = e[x.mate];
+            if (!(y.skip || y.bq == 0 || y.base == 'N')) {
+                const double q = (base == F) ? (1.0 - p) : 0.0;
+                m -= (1.0 - q); v += q * (1.0 - q);                 // the mate was counted as a sure toss in its own iteration
+            }
+        }
+        v += 0.02;                                                  // extra picks when a read already carries the mutant allele
+    }
+    for (int s = 16; s; s >>= 1) { m += __shfl_xor_sync(0xffffffffu, m, s); v += __shfl_xor_sync(0xffffffffu, v, s); }
+    if (lane == 0) {
+        const int j = (int)(ht.locus_index / L);
+        atomicAdd(&mean[j], m); atomicAdd(&var[j], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1: chunk maps
+// ------------------------------------------------------------------------------------------
+constexpr int DRY_MARKS = 48;
+
+// attemptToMutateBase over the whole pileup of hit h, counting draws only.  0 ok, else CHAIN_* bits.
+__device__ int dry_apply(const ChainArgs &A, size_t h, int64_t g, unsigned long long &k)
+{
+    const HitTarget ht = A.hits[h];
+    const uint8_t Fb = A.contig_seq[ht.tid][ht.pos];
+    uint32_t pick;
+    if (!select_allele(A, k, locus_class(A, g), pick)) return CHAIN_OVERRUN;                                 // :1197
+    uint8_t allele = (uint8_t)"GCAT"[pick];
+    if (ht.base == 'G' || ht.base == 'C' || ht.base == 'A' || ht.base == 'T') allele = ht.base;           // :1199-1203
+    const PlpEntry *ents = A.ent + A.eoff[h];
+    const uint32_t n = (uint32_t)(A.eoff[h + 1] - A.eoff[h]);
+    int32_t marks[DRY_MARKS]; int nm = 0;
+    for (uint32_t j = 0; j < n; j++) {
+        const PlpEntry e = ents[j];
+        if (e.skip || e.bq == 0) continue;
+        bool handled = false;
+        for (int i = 0; i < nm; i++) handled |= marks[i] == (int32_t)j;
+        if (handled) continue;
+        uint8_t mb = 0, mq = 0; bool mh = false;
+        if (e.mate >= 0) { const PlpEntry y = ents[e.mate]; mb = y.base; mq = y.bq; for (int i = 0; i < nm; i++) mh |= marks[i] == e.mate; }
+        const EntryOut o = entry_eval(A, e, mb, mq, mh, false, k, ht.thresh, Fb, allele);
+        if (!o.ok) return CHAIN_OVERRUN;
+        k += o.draws;
+        if (o.mark_mate && e.mate >= 0) { if (nm == DRY_MARKS) return CHAIN_COMPLEX; marks[nm++] = e.mate; }
+    }
+    return 0;
+}
+
+__device__ __forceinline__ size_t first_hit_at_or_after(const HitTarget *hits, size_t H, int64_t g)
+{
+    size_t lo = 0, hi = H;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (hits[mid].locus_index < g) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// walk [g, g_to) including the targets inside, counting draws only
+__device__ int dry_walk(const ChainArgs &A, int64_t g, const int64_t g_to, size_t h, unsigned long long &k)
+{
+    while (h < A.H && A.hits[h].locus_index < g_to) {
+        const int64_t gt = A.hits[h].locus_index;
+        if (!walk_loci<false>(A, g, gt, k)) return CHAIN_OVERRUN;
+        const int rc = dry_apply(A, h, gt, k);
+        if (rc) return rc;
+        g = gt + 1; h++;
+    }
+    if (!walk_loci<false>(A, g, g_to, k)) return CHAIN_OVERRUN;
+    return 0;
+}
+
+struct ChunkWin { unsigned long long klo; uint32_t W; uint32_t pad; unsigned long long off; };   // start offsets klo .. klo+W-1; off = slot in the walker buffers
+
+constexpr int P1_THREADS = 256;
+
+// One block per chunk.  kbuf/lobuf: two ping-pong halves of `stride` slots each.
+// On exit: n_cls[j] survivors, (lo, k_out) pairs in half 0 of the chunk's slots, sorted by lo.
+__global__ void __launch_bounds__(P1_THREADS)
+phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned long long *__restrict__ kbuf, uint32_t *__restrict__ lobuf,
+              unsigned long long stride, uint32_t *__restrict__ n_cls, unsigned int *__restrict__ flags)
+{
+    __shared__ uint32_t s_warp[P1_THREADS / 32];
+    __shared__ int s_bad;
+    const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const ChunkWin cw = win[j];
+    const int64_t g0 = (int64_t)j * L, g1 = (g0 + L < A.n_walk) ? g0 + L : A.n_walk;
+    unsigned long long *kb[2] = {kbuf + cw.off, kbuf + stride + cw.off};
+    uint32_t *lb[2] = {lobuf + cw.off, lobuf + stride + cw.off};
+    uint32_t alive = cw.W;
+    for (uint32_t i = tid; i < alive; i += P1_THREADS) { kb[0][i] = cw.klo + i; lb[0][i] = i; }
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    int cur = 0;
+    int64_t g = g0, step = 64;
+    while (g < g1) {
+        int64_t gc = g + step; if (gc > g1 || g1 - gc < step / 2) gc = g1;
+        const size_t h0 = first_hit_at_or_after(A.hits, A.H, g);
+        int bad = 0;
+        for (uint32_t i = tid; i < alive; i += P1_THREADS) {
+            unsigned long long k = kb[cur][i];
+            bad |= dry_walk(A, g, gc, h0, k);
+            kb[cur][i] = k;
+        }
+        if (bad) atomicOr(&s_bad, bad);
+        __syncthreads();
+        if (s_bad) { if (tid == 0) atomicOr(flags, (unsigned int)s_bad); return; }
+        // drop walkers that met their left neighbour (they stay together from here on); order is kept
+        uint32_t total = 0;
+        for (uint32_t base = 0; base < alive; base += P1_THREADS) {
+            const uint32_t i = base + tid;
+            bool keep = false; unsigned long long k = 0; uint32_t lo = 0;
+            if (i < alive) { k = kb[cur][i]; lo = lb[cur][i]; keep = (i == 0) || (kb[cur][i - 1] != k); }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_warp[wid] = __popc(m);
+            __syncthreads();
+            uint32_t before = 0, tile_total = 0;
+            for (int w = 0; w < P1_THREADS / 32; w++) { const uint32_t c = s_warp[w]; if (w < wid) before += c; tile_total += c; }
+            if (keep) { const uint32_t o = total + before + __popc(m & ((1u << lane) - 1u)); kb[cur ^ 1][o] = k; lb[cur ^ 1][o] = lo; }
+            total += tile_total;
+            __syncthreads();
+        }
+        alive = total; cur ^= 1;
+        g = gc; step *= 4;
+        __syncthreads();
+    }
+    if (cur != 0) {                                    // results always in half 0
+        for (uint32_t i = tid; i < alive; i += P1_THREADS) { kb[0][i] = kb[1][i]; lb[0][i] = lb[1][i]; }
+    }
+    if (tid == 0) n_cls[j] = alive;
+}
+
+// phase 2: one warp walks the chunk maps in order.  entry[j] = exact draw offset at the start of chunk j.
+__global__ void __launch_bounds__(32)
+compose_kernel(int P, const ChunkWin *__restrict__ win, const unsigned long long *__restrict__ kbuf, const uint32_t *__restrict__ lobuf,
+               const uint32_t *__restrict__ n_cls, ChunkDesc *__restrict__ chunks, unsigned int *__restrict__ flags)
+{
+    const int lane = threadIdx.x;
+    unsigned long long k = 0;
+    for (int j = 0; j < P; j++) {
+        const ChunkWin cw = win[j];
+        if (lane == 0) chunks[j].k_in = k;
+        if (k < cw.klo || k - cw.klo >= cw.W) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_MISS); return; }
+        const uint32_t idx = (uint32_t)(k - cw.klo), n = n_cls[j];
+        const uint32_t *lo = lobuf + cw.off; const unsigned long long *ko = kbuf + cw.off;
+        // last survivor with lo <= idx
+        uint32_t best = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            const bool le = i < n && lo[i] <= idx;
+            const unsigned m = __ballot_sync(0xffffffffu, le);
+            if (m) best = base + 31 - __clz(m);
+            if (m != 0xffffffffu) break;
+        }
+        k = ko[best];
+        if (lane == 0) chunks[j].k_out = k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 3 / serial chain: one warp per chunk, exact
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+chain_kernel(ChainArgs A, const ChunkDesc *__restrict__ chunks, int n_chunks, unsigned long long *__restrict__ draws_out, unsigned int *__restrict__ flags)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= n_chunks) return;
+    const ChunkDesc cd = chunks[c];
+    int64_t g = cd.g0; unsigned long long k = cd.k_in;
+    unsigned long long odd_bloom = 0;
+    size_t h = first_hit_at_or_after(A.hits, A.H, g);
+    for (; h < A.H && A.hits[h].locus_index < cd.g1; h++) {
+        const HitTarget ht = A.hits[h];
+        if (!walk_loci<true>(A, g, ht.locus_index, k)) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_OVERRUN); return; }
+        // ---- the target locus itself -----------------------------------------------------------
+        const unsigned long long k_at = k;
+        const uint8_t Fb = A.contig_seq[ht.tid][ht.pos];
+        uint32_t pick;
+        if (!select_allele(A, k, locus_class(A, g), pick)) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_OVERRUN); return; }     // :1197
+        uint8_t allele = (uint8_t)"GCAT"[pick];
+        if (ht.base == 'G' || ht.base == 'C' || ht.base == 'A' || ht.base == 'T') allele = ht.base;                // :1199-1203
+        const unsigned long long e0 = A.eoff[h], e1 = A.eoff[h + 1];
+        PlpEntry *ents = A.ent + e0;
+        uint8_t *hf = A.hflag + e0;
+        const uint32_t n = (uint32_t)(e1 - e0);
+        uint32_t ref_cnt = 0, mut_cnt = 0, err0 = 0, err1 = 0, err2 = 0, err3 = 0, fP = 0, fK = 0, fO = 0;
+        uint32_t j0 = 0;
+        // odd patches made at EARLIER targets (the list only grows at later loci, so it is fixed for this target)
+        __syncwarp();
+        const unsigned int n_odd = min(*(volatile unsigned int *)A.n_odd, A.odd_cap);
+        unsigned long long new_bloom = 0;
+        while (j0 < n) {
+            const uint32_t j = j0 + lane;
+            const bool in = j < n;
+            PlpEntry e; e.skip = 1; e.bq = 0; e.mate = -1; e.base = 0; e.ord = 0; e.qpos = 0;
+            if (in) e = ents[j];
+            const bool handled = in ? hf[j] != 0 : true;
+            uint8_t mate_base = 0, mate_bq = 0; PlpEntry me_; me_.ord = 0; me_.qpos = 0; me_.skip = 0;
+            bool mate_handled = false;
+            if (in && e.mate >= 0) { me_ = ents[e.mate]; mate_base = me_.base; mate_bq = me_.bq; mate_handled = hf[e.mate] != 0; }
+            if (n_odd && in) {                        // bases an earlier odd patch rewrote (see OddPatch)
+                if (odd_bloom & odd_bit(e.ord)) e.base = odd_view(A.odd, n_odd, e.ord, e.qpos, ht.tid, ht.pos, e.base);
+                if (e.mate >= 0 && (odd_bloom & odd_bit(me_.ord))) mate_base = odd_view(A.odd, n_odd, me_.ord, me_.qpos, ht.tid, ht.pos, mate_base);
+            }
+            // does this entry toss?  needed to give every lane its draw index
+            bool tosses = false;
+            if (in && !e.skip && e.bq != 0 && !handled) {
+                uint8_t R = e.base, M = 0; int rbq = e.bq, mbq = 0;
+                if (e.mate >= 0 && !mate_handled) { M = mate_base; mbq = mate_bq; }
+                if (M == 'N') mbq = 0;
+                if (R == 'N') rbq = 0;
+                uint8_t base = R; if (M && M != R && mbq > rbq) base = M;
+                tosses = base != 'N';
+            }
+            const unsigned tossmask = __ballot_sync(0xffffffffu, tosses);
+            const unsigned long long my_k = k + __popc(tossmask & ((1u << lane) - 1u));
+            EntryOut o = entry_eval(A, e, mate_base, mate_bq, mate_handled, handled, my_k, ht.thresh, Fb, allele);
+            // a lane "breaks" the speculation of the lanes after it when it used more than its one draw, or
+            // when it marks an entry of this batch as handled
+            const bool marks_in_batch = in && o.mark_mate && e.mate >= 0 && (uint32_t)e.mate < j0 + 32;
+            const bool breaks = !o.ok || o.draws > (tosses ? 1u : 0u) || marks_in_batch;
+            const unsigned bmask = __ballot_sync(0xffffffffu, breaks);
+            const uint32_t last = bmask ? (uint32_t)(__ffs(bmask) - 1) : 31u;         // commit lanes [0, last]
+            if (__ballot_sync(0xffffffffu, !o.ok && (uint32_t)lane <= last)) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_OVERRUN); return; }
+            const bool commit = in && (uint32_t)lane <= last;
+            if (commit) {
+                if (o.mark_self) hf[j] = 1;
+                if (o.mark_mate && e.mate >= 0) hf[e.mate] = 1;
+                for (int p = 0; p < o.npatch; p++) {
+                    unsigned int slot = atomicAdd(A.n_patches, 1u);
+                    const PlpEntry &pe = o.pmate[p] ? me_ : e;
+                    if (slot < A.patch_cap) {
+                        Patch pt; pt.ord = pe.ord; pt.qpos = pe.qpos; pt.base = o.pbase[p]; pt.pad = (uint32_t)h;
+                        A.patches[slot] = pt;
+                    }
+                    if (o.pmate[p] && me_.skip) {     // the mate sits in a D/N here: the patch lands on a base of a later locus
+                        unsigned int os = atomicAdd(A.n_odd, 1u);
+                        if (os < A.odd_cap) { OddPatch q; q.ord = pe.ord; q.qpos = pe.qpos; q.base = o.pbase[p]; q.h = (uint32_t)h; q.tid = ht.tid; q.pos = ht.pos; A.odd[os] = q; }
+                        else set_err(A.err, SSB_E_NOMEM, (unsigned long long)h);
+                        new_bloom |= odd_bit(pe.ord);
+                    }
+                }
+            }
+            const uint32_t used = commit ? o.draws : 0u;
+            uint32_t tot = used;
+            for (int s = 16; s; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+            k += tot;
+            ref_cnt += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 1));
+            mut_cnt += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 2));
+            err0 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 3));
+            err1 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 4));
+            err2 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 5));
+            err3 += __popc(__ballot_sync(0xffffffffu, commit && o.tally == 6));
+            fP |= __ballot_sync(0xffffffffu, commit && o.filt == 1);
+            fK |= __ballot_sync(0xffffffffu, commit && o.filt == 2);
+            fO |= __ballot_sync(0xffffffffu, commit && o.filt == 3);
+            __syncwarp();
+            j0 += last + 1;
+        }
+        for (int sft = 16; sft; sft >>= 1) new_bloom |= __shfl_xor_sync(0xffffffffu, new_bloom, sft);
+        odd_bloom |= new_bloom;
+        __threadfence();
+        if (lane == 0) {
+            ssb_target_result &r = A.res[ht.target];
+            r.ref_base = Fb; r.mutant_allele = allele;
+            // the filter only moves UNDETECTED -> PASS (cases 1,3), -> MASKED (case 2, unless MASKED_OVL), -> MASKED_OVL (cases 4-6)
+            r.filter = fO ? SSB_F_MASKED_OVL : fK ? SSB_F_MASKED : fP ? SSB_F_PASS : SSB_F_UNDETECTED;
+            r.ref_cnt = (int32_t)ref_cnt; r.mut_cnt = (int32_t)mut_cnt;
+            r.err_cnt[0] = (int32_t)err0; r.err_cnt[1] = (int32_t)err1; r.err_cnt[2] = (int32_t)err2; r.err_cnt[3] = (int32_t)err3;
+            r.rng_offset = (int64_t)k_at;
+        }
+        g += 1;
+    }
+    if (cd.k_out != ~0ull) {
+        // finish the chunk and compare with what phase 1/2 predicted
+        if (!walk_loci<true>(A, g, cd.g1, k)) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_OVERRUN); return; }
+        if (k != cd.k_out && lane == 0) atomicOr(flags, (unsigned int)CHAIN_INCONSISTENT);
+    }
+    if (lane == 0) { if (c == n_chunks - 1) *draws_out = k; if (n_chunks == 1) *A.odd_bloom = odd_bloom; }
+}

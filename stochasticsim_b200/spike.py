@@ -28,7 +28,7 @@ class TargetResult(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("alignmentCount", "numberOfLociCovered", "totalFoldCoverage", "maxDepth",
-                                          "n_lines", "n_kept", "in_bytes", "out_bytes", "n_runs", "n_hits", "rng_draws")] + \
+                                          "n_lines", "n_kept", "in_bytes", "out_bytes", "n_runs", "n_hits", "rng_draws", "chain_mode")] + \
                [(n, C.c_float) for n in ("ms_parse", "ms_sort", "ms_emit", "ms_cover", "ms_gather", "ms_rng", "ms_chain",
                                           "ms_patch", "ms_total")]
 

@@ -76,6 +76,31 @@ def test_seeds(seed, tmp_path, ctx):
     assert vcf_cmp(want[3], got[3]), first_diff(want[3], got[3])
 
 
+@pytest.mark.parametrize("name,chunk", [("plain", 512), ("deep_lowvaf", 256), ("mask_n_ref", 1024), ("overlap_heavy", 512), ("two_contigs_window", 640)])
+def test_parallel_chain_matches_serial(name, chunk, tmp_path, ctx, monkeypatch):
+    """The chunked chain (windows of candidate offsets, merging walkers, composed maps) against the oracle, and
+    against the one-warp serial chain: same SAM, same per-target results, same draw count."""
+    prefix = sc.generate(name, str(tmp_path))
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    sam = open(prefix + ".sam", "rb").read()
+    hdr, body, names = sp.split_header(sam)
+    seqs = sp.parse_fasta(open(prefix + ".fa", "rb").read())
+    targets = sp.parse_spike(open(prefix + ".spike", "rb").read(), names)
+    with sp.Spike(ctx, names, seqs) as s:
+        monkeypatch.setenv("SSB_CHAIN_SERIAL", "1")
+        out_s, res_s, st_s = s.run_host(body, targets, 434)
+        monkeypatch.delenv("SSB_CHAIN_SERIAL")
+        monkeypatch.setenv("SSB_CHAIN_CHUNK", str(chunk))
+        out_p, res_p, st_p = s.run_host(body, targets, 434)
+    assert st_s.chain_mode == 1
+    assert hdr + out_s == want[2] and hdr + out_p == want[2]
+    assert st_p.rng_draws == st_s.rng_draws
+    key = lambda r: (r.status, r.at_pos, r.filter, r.ref_cnt, r.mut_cnt, tuple(r.err_cnt), r.rng_offset, r.mutant_allele)
+    assert [key(r) for r in res_p] == [key(r) for r in res_s]
+    if name in ("plain", "deep_lowvaf", "mask_n_ref"):
+        assert st_p.chain_mode > 1, "expected the chunked chain to be used"
+
+
 def test_golden_fixture(tmp_path, ctx):
     """tests/golden/spike_toy was produced by the unmodified reference over the htslib shim."""
     for f in ("in.sam", "in.fa", "in.spike"):
