@@ -17,10 +17,10 @@
 
 namespace samparse {
 
-constexpr int TILE      = 32768;
-constexpr int OVERHANG  = 8192;
-constexpr int THREADS   = 256;
-constexpr int MAX_LINES = 2048;                 // a valid SAM line has >= 22 bytes -> <= 1490 per tile
+constexpr int TILE      = 16384;
+constexpr int OVERHANG  = 4096;
+constexpr int THREADS   = 128;
+constexpr int MAX_LINES = 1024;                 // a valid SAM line has >= 22 bytes -> <= 745 per tile
 constexpr int CHUNKS    = TILE / 16;            // 16-byte chunks per tile
 constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64;
 
@@ -139,6 +139,39 @@ __device__ int aux_ok(const Cursor &cur, size_t p, size_t q)
     }
 }
 
+// ---- SWAR helpers for the long fields (SEQ, QUAL) of a line that sits in the staged shared-memory window ----
+
+// unaligned 32-bit read from shared memory; reads one aligned word past `off` (always inside the dynamic smem block)
+__device__ __forceinline__ uint32_t lds_u32(const uint8_t *text, uint32_t off)
+{
+    const uint32_t a = off & 3u;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(text + (off - a));
+    return __funnelshift_r(p[0], p[1], a * 8);
+}
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t d)          // 0x80 in every byte of d that is zero (exact)
+{
+    return ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d | 0x7f7f7f7fu);
+}
+// bytes of the word that are NOT printable ('!'..'~'): 0x80 flags
+__device__ __forceinline__ uint32_t nonprint_bytes(uint32_t w)
+{
+    return (w | ~(w + 0x5f5f5f5fu) | (w + 0x01010101u)) & 0x80808080u;     // >= 0x80, < 0x21, > 0x7e  (the adds cannot carry across bytes once w < 0x80)
+}
+// bytes of the word that are not one of A C G T N (low three bits 1 3 7 4 6 select the only candidate): 0x80 flags
+__device__ __forceinline__ uint32_t non_acgtn_bytes(uint32_t w)
+{
+    const uint32_t TLO = 0x43014101u, THI = 0x474E0154u;       // index: 0->01 1->'A' 2->01 3->'C' 4->'T' 5->01 6->'N' 7->'G'
+    const uint32_t sidx = w & 0x07070707u;
+    const uint32_t e0 = __byte_perm(TLO, THI, sidx), e1 = __byte_perm(TLO, THI, sidx >> 16);
+    const uint32_t e = __byte_perm(e0, e1, 0x6420);
+    return ~zero_bytes(w ^ e) & 0x80808080u;
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    return x;
+}
+
 // Parses the line starting at `s` (ending at newline position `e`, e == n for an unterminated last
 // line).  Returns 0 or an SSB_E_* code.  A line is accepted only if htslib's parse -> format round
 // trip (sam_read1 + sam_write1, stochasticSpike.c:248,273) reproduces it byte for byte, so that the
@@ -153,10 +186,10 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
     for (int k = 0; k < 6; k++) r.pad[k] = 0;
     if (e - s > 0x7fffffffull) return SSB_E_FORMAT;
     // QNAME
-    uint64_t h = 1469598103934665603ull;
-    while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (c < '!' || c > '~') return SSB_E_FORMAT; h = (h ^ c) * 1099511628211ull; p++; }
+    uint32_t h1 = 2166136261u, h2 = 0x9747b28cu;
+    while (p < e) { uint32_t c = cur.at(p); if (c == '\t') break; if (c < '!' || c > '~') return SSB_E_FORMAT; h1 = (h1 ^ c) * 16777619u; h2 = (h2 + c) * 0x85ebca6bu; p++; }
     if (p >= e || p == s || p - s > 254) return SSB_E_FORMAT;
-    r.qhash = h; r.qname_len = (uint16_t)(p - s);
+    r.qhash = ((uint64_t)h1 << 32) | (h2 ^ (h2 >> 15)); r.qname_len = (uint16_t)(p - s);
     p++;
     // FLAG
     if (parse_udec(cur, p, e, 65535, v)) return SSB_E_FORMAT;
@@ -181,8 +214,8 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
     r.mapq = (uint8_t)v; p++;
     // CIGAR
     p0 = p;
-    uint64_t rlen = 0, qlen = 0; bool has_cigar = true;
-    if (cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { has_cigar = false; p++; }
+    uint64_t rlen = 0, qlen = 0; bool has_cigar = true, simple = true;
+    if (cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { has_cigar = false; simple = false; p++; }
     else {
         uint64_t num = 0; int nd = 0; uint8_t first = 0;
         while (p < e) {
@@ -193,9 +226,9 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
                 if (!nd || (nd > 1 && first == '0')) return SSB_E_FORMAT;
                 switch (c) {
                 case 'M': case '=': case 'X': rlen += num; qlen += num; break;
-                case 'D': case 'N': rlen += num; break;
-                case 'I': case 'S': qlen += num; break;
-                case 'H': case 'P': break;
+                case 'D': case 'N': rlen += num; simple = false; break;
+                case 'I': case 'S': qlen += num; simple = false; break;
+                case 'H': case 'P': simple = false; break;
                 default: return SSB_E_FORMAT;
                 }
                 num = 0; nd = 0;
@@ -204,6 +237,7 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
         }
         if (nd) return SSB_E_FORMAT;
     }
+    if (simple) r.bits |= REC_SIMPLE;
     if (p >= e || p == p0 || p - p0 > 65535 || p0 - s > 65535) return SSB_E_FORMAT;
     r.cigar_off = (uint16_t)(p0 - s); r.cigar_len = has_cigar ? (uint16_t)(p - p0) : 0;
     if (r.pos < 0 && rlen) return SSB_E_FORMAT;
@@ -227,14 +261,28 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
     if (p < e && cur.at(p) == '-') { p++; if (p < e && cur.at(p) == '0') return SSB_E_FORMAT; }
     if (parse_udec(cur, p, e, 0x7fffffffull, v)) return SSB_E_FORMAT;
     p++;
-    // SEQ
+    // SEQ: with a CIGAR its length is the CIGAR's query length, so the field is validated a word at a time
     r.seq_off = (uint32_t)(p - s);
     p0 = p;
+    const bool in_smem = e <= cur.lim && s >= cur.base;
     if (p < e && cur.at(p) == '*' && p + 1 < e && cur.at(p + 1) == '\t') { r.l_seq = 0; p++; }
-    else {
+    else if (has_cigar && in_smem && qlen > 0 && p + qlen < e) {
+        const uint32_t L = (uint32_t)qlen, off = (uint32_t)(p - cur.base);
+        uint32_t badw = 0;
+        for (uint32_t w = 0; w < L; w += 4) {
+            uint32_t x = lds_u32(cur.smem, off + w);
+            const uint32_t rem = L - w;
+            if (rem < 4) x = (x & ((1u << (8 * rem)) - 1u)) | (0x41414141u << (8 * rem));
+            if (non_acgtn_bytes(x)) { for (int k = 0; k < 4; k++) if (!seq_char_ok((uint8_t)(x >> (8 * k)))) badw = 1; }   // other IUPAC codes, '='
+        }
+        if (badw) return SSB_E_FORMAT;
+        p += L;
+        if (cur.at(p) != '\t') return SSB_E_FORMAT;               // htslib: "CIGAR and query sequence are of different length"
+        r.l_seq = L;
+    } else {
         while (p < e) { uint8_t c = cur.at(p); if (c == '\t') break; if (!seq_char_ok(c)) return SSB_E_FORMAT; p++; }
         r.l_seq = (uint32_t)(p - p0);
-        if (has_cigar && qlen != r.l_seq) return SSB_E_FORMAT;      // htslib: "CIGAR and query sequence are of different length"
+        if (has_cigar && qlen != r.l_seq) return SSB_E_FORMAT;
     }
     if (p >= e || p == p0) return SSB_E_FORMAT;
     p++;
@@ -247,7 +295,17 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
         qend = p + r.l_seq;
         if (r.l_seq == 0 || qend > e) return SSB_E_FORMAT;
         if (qend < e && cur.at(qend) != '\t') return SSB_E_FORMAT;  // htslib: "SEQ and QUAL are of different length"
-        for (size_t i = p; i < qend; i++) { uint8_t c = cur.at(i); if (c < '!' || c > '~') return SSB_E_FORMAT; }
+        if (in_smem) {
+            const uint32_t L = r.l_seq, off = (uint32_t)(p - cur.base);
+            uint32_t badw = 0;
+            for (uint32_t w = 0; w < L; w += 4) {
+                uint32_t x = lds_u32(cur.smem, off + w);
+                const uint32_t rem = L - w;
+                if (rem < 4) x = (x & ((1u << (8 * rem)) - 1u)) | (0x21212121u << (8 * rem));
+                badw |= nonprint_bytes(x);
+            }
+            if (badw) return SSB_E_FORMAT;
+        } else for (size_t i = p; i < qend; i++) { uint8_t c = cur.at(i); if (c < '!' || c > '~') return SSB_E_FORMAT; }
     }
     // optional fields
     p = qend;
@@ -269,6 +327,181 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
     return 0;
 }
 
+
+
+// ---- the same parser for a line that lies completely inside the staged shared-memory window: 32-bit offsets, direct
+// ---- shared-memory reads, word-at-a-time validation of the long fields.  L = first byte of the line, len = bytes
+// ---- without the newline.  Accepts / rejects exactly what parse_line() does.
+__device__ __forceinline__ int smem_udec(const uint8_t *L, uint32_t &p, uint32_t len, uint32_t maxv, uint32_t &out)
+{
+    const uint32_t p0 = p; uint32_t v = 0;
+    while (p < len) {
+        const uint32_t c = L[p];
+        if (c == '\t') break;
+        const uint32_t d = c - '0';
+        if (d > 9u) return SSB_E_FORMAT;
+        if (p - p0 >= 10) return SSB_E_FORMAT;                     // more than 10 digits cannot fit
+        if (v > 214748364u || (v == 214748364u && d > 7u)) return SSB_E_FORMAT;
+        v = v * 10u + d;
+        p++;
+    }
+    if (p >= len || p == p0 || v > maxv) return SSB_E_FORMAT;
+    if (p - p0 > 1 && L[p0] == '0') return SSB_E_FORMAT;
+    out = v;
+    return 0;
+}
+
+// words of the field [a, a+n) of the line: `bad` accumulates the flagged bytes.  CHECK(x) returns 0x80 flags.
+template <typename CHECK>
+__device__ __forceinline__ uint32_t smem_check_field(const uint8_t *L, uint32_t a, uint32_t n, uint32_t filler, CHECK check)
+{
+    uint32_t bad = 0, i = 0;
+    // bytes up to the first 4-byte aligned address, then aligned words, then the tail
+    const uint32_t mis = (uint32_t)((4u - ((uint32_t)(uintptr_t)(L + a) & 3u)) & 3u);
+    if (mis) {
+        const uint32_t take = mis < n ? mis : n;
+        uint32_t x = filler;
+        for (uint32_t k = 0; k < take; k++) x = (x & ~(0xffu << (8 * k))) | ((uint32_t)L[a + k] << (8 * k));
+        bad |= check(x);
+        i = take;
+    }
+    const uint32_t *W = reinterpret_cast<const uint32_t *>(L + a + i);
+    const uint32_t nw = (n - i) >> 2;
+    for (uint32_t w = 0; w < nw; w++) bad |= check(W[w]);
+    i += nw << 2;
+    if (i < n) {
+        uint32_t x = filler;
+        for (uint32_t k = 0; i + k < n; k++) x = (x & ~(0xffu << (8 * k))) | ((uint32_t)L[a + i + k] << (8 * k));
+        bad |= check(x);
+    }
+    return bad;
+}
+
+__device__ int parse_line_smem(const Cursor &cur, const uint8_t *L, uint32_t len, size_t s, bool has_nl, const ContigNames &names, int &tid_cache, SamRec &r)
+{
+    uint32_t p = 0, v;
+    r.line_off = s;
+    r.line_len = len + (has_nl ? 1u : 0u);
+    r.bits = has_nl ? 0 : REC_NO_NL;
+    for (int k = 0; k < 6; k++) r.pad[k] = 0;
+    // QNAME: printable, hashed with two 32-bit FNV-1a streams
+    uint32_t h1 = 2166136261u, h2 = 0x9747b28cu;
+    while (p < len) { const uint32_t c = L[p]; if (c == '\t') break; if (c - '!' > (uint32_t)('~' - '!')) return SSB_E_FORMAT; h1 = (h1 ^ c) * 16777619u; h2 = (h2 + c) * 0x85ebca6bu; p++; }
+    if (p >= len || p == 0 || p > 254) return SSB_E_FORMAT;
+    r.qhash = ((uint64_t)h1 << 32) | (h2 ^ (h2 >> 15)); r.qname_len = (uint16_t)p;
+    p++;
+    if (smem_udec(L, p, len, 65535u, v)) return SSB_E_FORMAT;
+    r.flag = (uint16_t)v; p++;
+    // RNAME
+    uint32_t p0 = p;
+    while (p < len && L[p] != '\t') p++;
+    if (p >= len || p == p0) return SSB_E_FORMAT;
+    if (p - p0 == 1 && L[p0] == '*') r.tid = -1;
+    else {
+        r.tid = name_lookup(cur, s + p0, p - p0, names, tid_cache);
+        if (r.tid < 0) return SSB_E_FORMAT;
+        tid_cache = r.tid;
+    }
+    p++;
+    if (smem_udec(L, p, len, 0x7fffffffu, v)) return SSB_E_FORMAT;
+    r.pos = (int32_t)v - 1; p++;
+    if (smem_udec(L, p, len, 255u, v)) return SSB_E_FORMAT;
+    r.mapq = (uint8_t)v; p++;
+    // CIGAR
+    p0 = p;
+    uint32_t rlen = 0, qlen = 0; bool has_cigar = true, simple = true;
+    if (L[p] == '*' && p + 1 < len && L[p + 1] == '\t') { has_cigar = false; simple = false; p++; }
+    else {
+        uint32_t num = 0; int nd = 0; uint32_t first = 0;
+        while (p < len) {
+            const uint32_t c = L[p];
+            if (c == '\t') break;
+            const uint32_t d = c - '0';
+            if (d <= 9u) { if (!nd) first = c; num = num * 10u + d; nd++; if (nd > 9 || num > 0x0fffffffu) return SSB_E_FORMAT; }
+            else {
+                if (!nd || (nd > 1 && first == '0')) return SSB_E_FORMAT;
+                switch (c) {
+                case 'M': case '=': case 'X': rlen += num; qlen += num; break;
+                case 'D': case 'N': rlen += num; simple = false; break;
+                case 'I': case 'S': qlen += num; simple = false; break;
+                case 'H': case 'P': simple = false; break;
+                default: return SSB_E_FORMAT;
+                }
+                if (rlen > 0x7ffffff0u || qlen > 0x7ffffff0u) return SSB_E_FORMAT;
+                num = 0; nd = 0;
+            }
+            p++;
+        }
+        if (nd) return SSB_E_FORMAT;
+    }
+    if (simple) r.bits |= REC_SIMPLE;
+    if (p >= len || p == p0 || p - p0 > 65535 || p0 > 65535) return SSB_E_FORMAT;
+    r.cigar_off = (uint16_t)p0; r.cigar_len = has_cigar ? (uint16_t)(p - p0) : 0;
+    if (r.pos < 0 && rlen) return SSB_E_FORMAT;
+    if ((uint64_t)(r.pos < 0 ? 0 : r.pos) + rlen > 0x7ffffff0ull) return SSB_E_FORMAT;
+    r.end = r.pos + (int32_t)rlen;
+    p++;
+    // RNEXT
+    p0 = p;
+    while (p < len && L[p] != '\t') p++;
+    if (p >= len || p == p0) return SSB_E_FORMAT;
+    if (!(p - p0 == 1 && (L[p0] == '*' || L[p0] == '='))) {
+        const int mt = name_lookup(cur, s + p0, p - p0, names, -1);
+        if (mt < 0 || mt == r.tid) return SSB_E_FORMAT;
+    } else if (L[p0] == '=' && r.tid < 0) return SSB_E_FORMAT;
+    p++;
+    if (smem_udec(L, p, len, 0x7fffffffu, v)) return SSB_E_FORMAT;   // PNEXT
+    p++;
+    if (p < len && L[p] == '-') { p++; if (p < len && L[p] == '0') return SSB_E_FORMAT; }
+    if (smem_udec(L, p, len, 0x7fffffffu, v)) return SSB_E_FORMAT;   // TLEN
+    p++;
+    // SEQ
+    r.seq_off = p;
+    p0 = p;
+    if (p < len && L[p] == '*' && p + 1 < len && L[p + 1] == '\t') { r.l_seq = 0; p++; }
+    else if (has_cigar && qlen > 0 && p + qlen < len) {
+        const uint32_t bad = smem_check_field(L, p, qlen, 0x41414141u, [](uint32_t x) { return non_acgtn_bytes(x); });
+        if (bad) for (uint32_t i = 0; i < qlen; i++) if (!seq_char_ok(L[p + i])) return SSB_E_FORMAT;    // other IUPAC codes, '='
+        p += qlen;
+        if (L[p] != '\t') return SSB_E_FORMAT;                      // htslib: "CIGAR and query sequence are of different length"
+        r.l_seq = qlen;
+    } else {
+        while (p < len) { const uint8_t c = L[p]; if (c == '\t') break; if (!seq_char_ok(c)) return SSB_E_FORMAT; p++; }
+        r.l_seq = p - p0;
+        if (has_cigar && qlen != r.l_seq) return SSB_E_FORMAT;
+    }
+    if (p >= len || p == p0) return SSB_E_FORMAT;
+    p++;
+    // QUAL
+    r.qual_off = p;
+    if (p >= len) return SSB_E_FORMAT;
+    uint32_t qend;
+    if (L[p] == '*' && (p + 1 == len || L[p + 1] == '\t')) { r.bits |= REC_QUALSTAR; qend = p + 1; }
+    else {
+        qend = p + r.l_seq;
+        if (r.l_seq == 0 || qend > len) return SSB_E_FORMAT;
+        if (qend < len && L[qend] != '\t') return SSB_E_FORMAT;     // htslib: "SEQ and QUAL are of different length"
+        if (smem_check_field(L, p, r.l_seq, 0x21212121u, [](uint32_t x) { return nonprint_bytes(x); })) return SSB_E_FORMAT;
+    }
+    // optional fields
+    for (size_t q = s + qend; q < s + len;) {
+        size_t a = q + 1, b = a;
+        while (b < s + len && cur.at(b) != '\t') b++;
+        if (aux_ok(cur, a, b)) return SSB_E_FORMAT;
+        q = b;
+    }
+    // read_bam (stochasticSpike.c:253-263) + bam_plp_push's tid test
+    const bool pass = !(r.flag & (4 | 256 | 512 | 1024)) && r.mapq >= 30 && !((r.flag & 1) && !(r.flag & 2));
+    if (pass && r.tid >= 0) {
+        r.bits |= REC_PUSHED;
+        if (r.end > r.pos) {
+            if (r.l_seq == 0) return SSB_E_FORMAT;
+            r.bits |= REC_KEEP;
+        }
+    }
+    return 0;
+}
+
 __global__ void __launch_bounds__(THREADS)
 parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamRec *__restrict__ recs, size_t rec_cap,
              unsigned long long *__restrict__ tile_state, unsigned int *__restrict__ ticket,
@@ -282,6 +515,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
     __shared__ unsigned int s_warp_tot[THREADS / 32];
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_first;
+    __shared__ unsigned long long s_last_end;
 
     const size_t n_tiles = (n + TILE - 1) / TILE;
     const int tid_ = threadIdx.x, lane = tid_ & 31, wid = tid_ >> 5;
@@ -343,25 +577,37 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         const uint32_t first = s_first;
         uint32_t my_base = first + warp_base + incl - cnt;
         const uint32_t n_here = first + total;
-        // 3. decoupled look-back for the global index of this tile's first line
-        if (tid_ == 0) {
+        // 3. decoupled look-back for the global index of this tile's first line.  The frontier of known inclusive
+        //    prefixes moves one window per L2 round trip, so the window is wide: warp 0 inspects 256 predecessors per hop.
+        if (wid == 0) {
             unsigned long long excl = 0;
-            if (tile == 0) {
-                atomicExch(&tile_state[0], ST_INC | (unsigned long long)n_here);
-            } else {
-                atomicExch(&tile_state[tile], ST_AGG | (unsigned long long)n_here);
-                size_t j = tile - 1;
+            volatile unsigned long long *ts = tile_state;
+            if (tile == 0) { if (lane == 0) atomicExch(&tile_state[0], ST_INC | (unsigned long long)n_here); }
+            else {
+                if (lane == 0) atomicExch(&tile_state[tile], ST_AGG | (unsigned long long)n_here);
+                long long j = (long long)tile - 1;
                 for (;;) {
-                    unsigned long long v;
-                    do { v = atomicAdd(&tile_state[j], 0ull); } while ((v & ST_MASK) == 0);
-                    excl += v & ~ST_MASK;
-                    if ((v & ST_MASK) == ST_INC) break;
-                    j--;
+                    const long long hi = j - 8 * lane;                     // this lane looks at tiles hi, hi-1, .. hi-7
+                    unsigned long long sum = 0; bool has_inc = false;
+                    for (int k = 0; k < 8 && !has_inc; k++) {
+                        const long long idx = hi - k;
+                        unsigned long long v = ST_INC;                     // before tile 0: inclusive prefix 0
+                        if (idx >= 0) { do { v = ts[idx]; } while ((v & ST_MASK) == 0); }
+                        sum += v & ~ST_MASK;
+                        has_inc = (v & ST_MASK) == ST_INC;
+                    }
+                    const unsigned inc = __ballot_sync(0xffffffffu, has_inc);
+                    const int first = inc ? __ffs(inc) - 1 : 31;           // nearest lane that met an inclusive prefix
+                    unsigned long long c = lane <= first ? sum : 0ull;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    excl += c;
+                    if (inc) break;
+                    j -= 256;
                 }
-                atomicExch(&tile_state[tile], ST_INC | (excl + n_here));
+                if (lane == 0) atomicExch(&tile_state[tile], ST_INC | (excl + n_here));
             }
-            s_base = excl;
-            if (tile == n_tiles - 1) *n_lines_out = excl + n_here;
+            if (lane == 0) { s_base = excl; if (tile == n_tiles - 1) *n_lines_out = excl + n_here; }
         }
         if (n_here > MAX_LINES) {                                      // > 2048 lines in 32 KiB cannot be SAM
             if (tid_ == 0 && atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = T0;
@@ -379,16 +625,29 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         }
         __syncthreads();
         const unsigned long long gbase = s_base;
-        // 4. one line per thread
+        // 4. one line per thread.  The last line of the tile ends in the overhang (or beyond): warp 0 finds its newline.
         Cursor cur{text, body, T0, stage_end, n};
+        if (wid == 0 && n_here > 0) {
+            size_t e = T0 + starts[n_here - 1] + lane;
+            for (;;) {
+                const bool hit = e >= n || cur.at(e) == '\n';
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) { e = e - lane + (__ffs(m) - 1); break; }
+                e += 32;
+            }
+            if (lane == 0) s_last_end = e > n ? n : e;
+        }
+        __syncthreads();
         for (uint32_t i = tid_; i < n_here; i += THREADS) {
             size_t s = T0 + starts[i];
             size_t e;
             if (i + 1 < n_here) e = T0 + starts[i + 1] - 1;
-            else { e = s; while (e < n && cur.at(e) != '\n') e++; }   // last line of the tile: find its newline in the overhang
+            else e = s_last_end;
             SamRec r;
-            int rc = parse_line(cur, s, e, names, tid_cache, r);
-            if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = s; r.bits = 0; r.tid = -1; r.pos = 0; r.end = 0; }
+            int rc;
+            if (e <= stage_end && e - s < 0x40000000ull) rc = parse_line_smem(cur, text + (s - T0), (uint32_t)(e - s), s, e < n, names, tid_cache, r);
+            else rc = parse_line(cur, s, e, names, tid_cache, r);
+            if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = s; memset(&r, 0, sizeof r); r.line_off = s; r.tid = -1; }
             unsigned long long gi = gbase + i;
             if (gi < rec_cap) recs[gi] = r;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;

@@ -502,10 +502,11 @@ __global__ void odd_fix_kernel(const OddPatch *odd, const unsigned int *n_odd, u
 struct ReadView {
     const uint8_t *line; const uint8_t *cig; int cig_len; int32_t pos, end; uint32_t seq_off, qual_off, l_seq; bool qual_star;
     uint32_t ord; int32_t tid; const OddPatch *odd; unsigned int n_odd;      // odd != NULL only for the few reads an odd patch touched
+    bool simple;                                                             // CIGAR of M/=/X only: qpos = x - pos
 };
 __device__ __forceinline__ ReadView view_of(const uint8_t *sam, const SamRec &r, uint32_t ord, const OddPatch *odd, unsigned int n_odd, unsigned long long bloom)
 {
-    ReadView v; v.line = sam + r.line_off; v.ord = ord; v.tid = r.tid; v.odd = NULL; v.n_odd = 0;
+    ReadView v; v.line = sam + r.line_off; v.ord = ord; v.tid = r.tid; v.odd = NULL; v.n_odd = 0; v.simple = (r.bits & REC_SIMPLE) != 0;
     if (n_odd && (bloom & odd_bit(ord))) { v.odd = odd; v.n_odd = n_odd; } v.cig = v.line + r.cigar_off; v.cig_len = r.cigar_len; v.pos = r.pos; v.end = r.end;
     v.seq_off = r.seq_off; v.qual_off = r.qual_off; v.l_seq = r.l_seq; v.qual_star = (r.bits & REC_QUALSTAR) != 0;
     return v;
@@ -513,7 +514,8 @@ __device__ __forceinline__ ReadView view_of(const uint8_t *sam, const SamRec &r,
 __device__ __forceinline__ void base_at(const ReadView &v, int32_t x, uint8_t &base, int &bq, bool &skip)
 {
     uint32_t qpos; uint8_t sk;
-    column_of(v.cig, v.cig_len, v.pos, x, qpos, sk);
+    if (v.simple) { qpos = (uint32_t)(x - v.pos); sk = 0; }
+    else column_of(v.cig, v.cig_len, v.pos, x, qpos, sk);
     if (qpos >= v.l_seq) qpos = v.l_seq - 1;        // malformed CIGAR tail (the reference would read out of bounds)
     base = v.line[v.seq_off + qpos];
     if (v.odd) base = odd_view(v.odd, v.n_odd, v.ord, qpos, v.tid, x, base);
@@ -563,6 +565,105 @@ __device__ __forceinline__ void tally_add(const TallyArgs &A, int64_t g, int con
     if (contrib >= 2) atomicAdd(&A.err64[g], 1ull << (16 * (contrib - 2)));
 }
 
+// A read takes the fast tally when every query base aligns 1:1 to the reference (CIGAR of M/=/X only), the only reads
+// that share its QNAME inside its span are its direct neighbours in the mate chain and are just as simple, and no odd
+// patch touched any of them.
+__device__ __forceinline__ bool tally_simple_read(const TallyArgs &A, size_t o, unsigned int n_odd, unsigned long long bloom)
+{
+    if (!(A.recs[A.k_rec[o]].bits & REC_SIMPLE) || A.cplx[o]) return false;
+    if (n_odd && (bloom & odd_bit((uint32_t)o))) return false;
+    return true;
+}
+__device__ __forceinline__ bool tally_is_fast(const TallyArgs &A, size_t o, const SamRec &r, unsigned int n_odd, unsigned long long bloom)
+{
+    if (!tally_simple_read(A, o, n_odd, bloom)) return false;
+    const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
+    if (p != PRV_NONE && !tally_simple_read(A, p, n_odd, bloom)) return false;
+    if (q != NO_MATE && !tally_simple_read(A, q, n_odd, bloom)) return false;
+    (void)r;
+    return true;
+}
+
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t *p)
+{
+    const uint32_t a = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p - a);
+    return __funnelshift_r(__ldg(q), __ldg(q + 1), a * 8);
+}
+
+// 0x80 flags of the bytes of a simple read that are not plain "reference base with BQ > 0" at query offset w..w+3
+__device__ __forceinline__ uint32_t exc_word(const uint8_t *seq, const uint8_t *qual, bool qstar, uint32_t w, uint32_t refw)
+{
+    const uint32_t sq = ldg_u32_unaligned(seq + w);
+    const uint32_t ql = qstar ? 0x7e7e7e7eu : ldg_u32_unaligned(qual + w);
+    return (~samparse::zero_bytes(sq ^ refw) | samparse::zero_bytes(ql ^ 0x21212121u)) & 0x80808080u;
+}
+
+// One warp per read: SEQ, QUAL and the reference compared four bytes per lane; only bytes that differ from the
+// reference or have BQ 0 -- in this read or in an overlapping mate -- are evaluated one by one.
+__global__ void __launch_bounds__(256)
+tally_fast_kernel(TallyArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (o >= A.K) return;
+    const SamRec &r = A.recs[A.k_rec[o]];
+    const unsigned int n_odd = *A.n_odd; const unsigned long long bloom = *A.odd_bloom;
+    if (!tally_is_fast(A, o, r, n_odd, bloom)) return;
+    const int tid = r.tid;
+    const uint8_t *ref = A.contig_seq[tid];
+    if (!ref || (int64_t)r.end > A.contig_len[tid]) { if (lane == 0) set_err(A.err, SSB_E_REF, r.line_off); return; }
+    size_t ri; { size_t lo = 0, hi = A.R; while (hi - lo > 1) { size_t mid = (lo + hi) >> 1;
+                   bool le = A.runs[mid].tid < tid || (A.runs[mid].tid == tid && A.runs[mid].start <= r.pos); if (le) lo = mid; else hi = mid; } ri = lo; }
+    const int64_t gbase = A.runs[ri].base - A.runs[ri].start + r.pos;    // covered ordinal of query offset 0
+    const uint8_t *seq = A.sam + r.line_off + r.seq_off, *qual = A.sam + r.line_off + r.qual_off, *rf = ref + r.pos;
+    const bool qstar = (r.bits & REC_QUALSTAR) != 0;
+    const uint32_t L = r.l_seq;
+    // mate chain neighbours (same QNAME, spans overlap): [p?, me, q?]
+    ReadView mem[3]; int n = 0, self = 0;
+    const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
+    if (p != PRV_NONE && (uint32_t)A.k_end[p] > (uint32_t)r.pos) mem[n++] = view_of(A.sam, A.recs[A.k_rec[p]], p, NULL, 0, 0);
+    self = n; mem[n++] = view_of(A.sam, r, (uint32_t)o, NULL, 0, 0);
+    if (q != NO_MATE) mem[n++] = view_of(A.sam, A.recs[A.k_rec[q]], q, NULL, 0, 0);
+    for (uint32_t w = lane * 4; w < L; w += 128) {
+        const uint32_t rw = ldg_u32_unaligned(rf + w);
+        uint32_t exc = exc_word(seq, qual, qstar, w, rw);
+        const int32_t x0 = r.pos + (int32_t)w;
+        for (int m = 0; m < n; m++) {
+            if (m == self) continue;
+            const ReadView &v = mem[m];
+            if (x0 + 3 < v.pos || x0 >= v.end) continue;              // no byte of this word under the mate
+            if (x0 >= v.pos && x0 + 4 <= v.end) exc |= exc_word(v.line + v.seq_off, v.line + v.qual_off, v.qual_star, (uint32_t)(x0 - v.pos), rw);
+            else exc = 0x80808080u;                                    // the mate starts or ends inside this word: look at every byte
+        }
+        const uint32_t rem = L - w;
+        if (rem < 4) exc &= (1u << (8 * rem)) - 1u;
+        if (!exc) continue;
+        const uint32_t sq = ldg_u32_unaligned(seq + w);
+        const uint32_t ql = qstar ? 0x7e7e7e7eu : ldg_u32_unaligned(qual + w);
+        while (exc) {
+            const int k = (__ffs(exc) - 1) >> 3; exc &= exc - 1;
+            const int32_t x = x0 + k;
+            const uint8_t F = (uint8_t)(rw >> (8 * k));
+            int contrib;
+            bool overlapped = false;
+            for (int m = 0; m < n; m++) if (m != self && mem[m].pos <= x && x < mem[m].end) overlapped = true;
+            if (overlapped) {
+                ReadView cov[3]; int nc = 0, sc = 0;
+                for (int m = 0; m < n; m++) if (mem[m].pos <= x && x < mem[m].end) { if (m == self) sc = nc; cov[nc++] = mem[m]; }
+                contrib = chain_contribution(cov, nc, sc, x, F);
+            } else {
+                const uint8_t b = (uint8_t)(sq >> (8 * k));
+                const int bq = qstar ? 255 : (int)((ql >> (8 * k)) & 0xff) - 33;
+                if (bq == 0 || b == 'N') contrib = 0;
+                else if (b == F) contrib = 1;
+                else { const int gi = gcat_index(b); contrib = gi < 4 ? 2 + gi : 0; }
+            }
+            tally_add(A, gbase + w + k, contrib);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 tally_kernel(TallyArgs A)
 {
@@ -570,6 +671,7 @@ tally_kernel(TallyArgs A)
     if (o >= A.K) return;
     const SamRec &r = A.recs[A.k_rec[o]];
     const unsigned int n_odd = *A.n_odd; const unsigned long long bloom = *A.odd_bloom;
+    if (tally_is_fast(A, o, r, n_odd, bloom)) return;                  // done by tally_fast_kernel
     const ReadView me = view_of(A.sam, r, (uint32_t)o, A.odd, n_odd, bloom);
     const int tid = r.tid;
     const uint8_t *ref = A.contig_seq[tid];
@@ -822,7 +924,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     cudaStream_t s = ctx->stream;
     memset(stats, 0, sizeof *stats);
     *out_bytes = 0;
-    if (sp->d_se) { cudaFree(sp->d_se); sp->d_se = NULL; }
+    if (sp->d_se) { cudaFreeAsync(sp->d_se, ctx->stream); sp->d_se = NULL; }
     sp->n_se = 0;
     stats->in_bytes = (int64_t)n;
     const size_t T = n_targets;
@@ -858,7 +960,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             SSB_CUDA(ctx, cudaMemsetAsync(d_nlines, 0, sizeof(unsigned long long), s));
             SSB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(DevErr), s));
             samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs};
-            int grid = (int)(n_tiles < (size_t)ctx->sm_count * 4 ? n_tiles : (size_t)ctx->sm_count * 4);
+            int grid = (int)(n_tiles < (size_t)ctx->sm_count * 8 ? n_tiles : (size_t)ctx->sm_count * 8);
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_PARSE, samparse::parse_kernel, grid, samparse::THREADS, samparse::SMEM_BYTES, s,
                          d_sam, n, names, recs, rec_cap, tile_state, ticket, d_nlines, reinterpret_cast<SpikeErr *>(d_err));
             unsigned long long nl = 0; DevErr e;
@@ -1188,6 +1290,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         TA.nxt = nxt; TA.prv = prv; TA.cplx = cplx; TA.maxspan = h_maxspan; TA.runs = runs; TA.R = R;
         TA.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; TA.contig_len = sp->d_lens; TA.err64 = err64; TA.minus = minus; TA.err = d_err;
         TA.odd = d_odd; TA.n_odd = d_nodd; TA.odd_bloom = d_bloom;
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_fast_kernel, grid_for(K * 32, 256), 256, 0, s, TA);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_kernel, grid_for(K, 128), 128, 0, s, TA);
         if ((rc = dev_error(ctx, s, d_err, "reference"))) return rc;
         if (H) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_clear_hits_kernel, grid_for(H, 256), 256, 0, s, hits, H, err64);
@@ -1201,7 +1304,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         sp->n_se = (size_t)li + lf;
         if (sp->n_se) {
-            SSB_CUDA(ctx, cudaMalloc((void **)&sp->d_se, sp->n_se * sizeof(ssb_seq_error)));
+            SSB_CUDA(ctx, cudaMallocAsync((void **)&sp->d_se, sp->n_se * sizeof(ssb_seq_error), s));
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_emit_kernel, grid_for((size_t)n_cov, 256), 256, 0, s, err64, minus, sflag, sidx, n_cov, runs, R,
                          k_start, s_end, K, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_se);
         }

@@ -31,7 +31,8 @@ enum : uint8_t {
     REC_KEEP     = 1,      // passes read_bam (stochasticSpike.c:243-268), tid >= 0, reference length > 0
     REC_QUALSTAR = 2,      // QUAL is '*'
     REC_NO_NL    = 4,      // last line of the body without a trailing '\n'
-    REC_PUSHED   = 8       // passes read_bam and tid >= 0 (takes part in the sortedness check)
+    REC_PUSHED   = 8,      // passes read_bam and tid >= 0 (takes part in the sortedness check)
+    REC_SIMPLE   = 16      // CIGAR holds only M/=/X: query offset q aligns to reference position pos + q
 };
 
 // device error word: first error wins
