@@ -1174,7 +1174,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         std::vector<ChunkDesc> h_chunks(P);
         double cm = 0, cv = 0; unsigned long long woff = 0, wmax = 0;
         for (int j = 0; j < P; j++) {
-            const double half = j == 0 ? 0.0 : 6.0 * sqrt(cv) + 48.0;
+            const double half = j == 0 ? 0.0 : 5.0 * sqrt(cv) + 48.0;        // +-5 sigma: a miss (3e-7 per chunk) falls back to the serial chain
             double lo = cm - half; if (lo < 0) lo = 0;
             h_win[j].klo = (unsigned long long)lo; h_win[j].W = j == 0 ? 1u : (uint32_t)(cm + half - (double)h_win[j].klo) + 2u; h_win[j].pad = 0;
             h_win[j].off = woff; woff += h_win[j].W; if (h_win[j].W > wmax) wmax = h_win[j].W;
@@ -1211,7 +1211,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             uint32_t *pe0 = ar.get<uint32_t>(ewords), *pe1 = ar.get<uint32_t>(ewords), *pej = ar.get<uint32_t>(ewords);
             SPK_CHECK_ARENA(ar);
             SSB_CUDA(ctx, cudaMemcpyAsync(d_bp, bp.data(), bp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-            SSB_CUDA(ctx, cudaMemsetAsync(pe0 + (M >> 5), 0, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pe1 + (M >> 5), 0, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pej + (M >> 5), 0, 160 * 4, s));
+            SSB_CUDA(ctx, cudaMemsetAsync(pe0 + (M >> 5), 0xAA, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pe1 + (M >> 5), 0xCC, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pej + (M >> 5), 0, 160 * 4, s));   // all four classes in every nibble: see walk_loci
             SSB_CUDA(ctx, cudaEventRecord(ev[8], s));
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, d_seedw, Rs, M, pe0, pe1, pej);
             SSB_CUDA(ctx, cudaEventRecord(ev[9], s));
@@ -1232,7 +1232,15 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             };
             if ((rc = reset_apply())) return rc;
             if (parallel) {
-                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, P, P1_THREADS, 0, s, A, Lc, d_win, kbuf, lobuf, woff, d_ncls, d_flags);
+                unsigned long long *d_dbg = NULL;
+                if (getenv("SSB_CHAIN_DEBUG")) { d_dbg = ar.get<unsigned long long>(4); SPK_CHECK_ARENA(ar); SSB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, 32, s)); }
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, P, P1_THREADS, 0, s, A, Lc, d_win, kbuf, lobuf, woff, d_ncls, d_flags, d_dbg);
+                if (d_dbg) {
+                    unsigned long long h_dbg[4];
+                    SSB_CUDA(ctx, cudaMemcpyAsync(h_dbg, d_dbg, 32, cudaMemcpyDeviceToHost, s));
+                    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+                    fprintf(stderr, "[chain] P=%d L=%lld walkers=%llu walker-loci=%llu rounds=%llu final survivors: sum %llu max %llu\n", P, (long long)Lc, woff, h_dbg[0], h_dbg[3], h_dbg[1], h_dbg[2]);
+                }
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, P, d_win, kbuf, lobuf, d_ncls, d_chunks, d_flags);
                 SSB_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
                 SSB_CUDA(ctx, cudaStreamSynchronize(s));

@@ -104,37 +104,57 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 
 // Consumes the draws of covered loci [g, g_to): per locus, rand() until the pick differs from the reference base
 // (selectMutantAllele / randomNum, stochasticSpike.c:283-302, 338-360).  false = the stream is too short.
+// Cursors are kept as 32-bit offsets from word-aligned bases.  Instead of testing the end of the stream in the
+// loop, word indices are clamped into the padding behind the planes, which holds all four classes in every nibble
+// (e0 = 0xAAAAAAAA, e1 = 0xCCCCCCCC, ej = 0): a walker that runs off the end still terminates, and is caught by the
+// single test at the end.
 template <bool PF>
 __device__ __forceinline__ bool walk_loci(const ChainArgs &A, int64_t &g, const int64_t g_to, unsigned long long &k)
 {
     while (g < g_to) {
-        const uint32_t a = (uint32_t)(k & 31), b = (uint32_t)(g & 31);
-        const size_t we = (size_t)(k >> 5), wc = (size_t)(g >> 5);
         if (k + 64 > A.M) return false;
-        if (PF) {
-            if ((we & 31) == 0) { prefetch_l2(A.e0 + we + 64); prefetch_l2(A.e1 + we + 64); prefetch_l2(A.ej + we + 64); }
-            if ((wc & 31) == 0) { prefetch_l2(A.c0 + wc + 64); prefetch_l2(A.c1 + wc + 64); prefetch_l2(A.cx + wc + 64); }
+        const unsigned long long kb = k & ~31ull; const int64_t gb = g & ~(int64_t)31;
+        const uint32_t *__restrict__ E0 = A.e0 + (kb >> 5), *__restrict__ E1 = A.e1 + (kb >> 5), *__restrict__ EJ = A.ej + (kb >> 5);
+        const uint32_t *__restrict__ C0 = A.c0 + (gb >> 5), *__restrict__ C1 = A.c1 + (gb >> 5), *__restrict__ CX = A.cx + (gb >> 5);
+        uint32_t kr = (uint32_t)(k - kb), gr = (uint32_t)(g - gb);
+        const uint32_t gto = (g_to - gb) > 0x40000000ll ? 0x40000000u : (uint32_t)(g_to - gb);
+        const unsigned long long wleft = ((A.M - kb) >> 5) + 100ull;
+        const uint32_t wmax = wleft > 0x02000000ull ? 0x02000000u : (uint32_t)wleft;       // last word index that may be read
+        // the current word of every plane stays in registers; it is reloaded only when a cursor crosses a word boundary
+        uint32_t cwe = 0xffffffffu, cwc = 0xffffffffu, E0w = 0, E1w = 0, EJw = 0, C0w = 0, C1w = 0, CXw = 0;
+        while (gr < gto) {
+            const uint32_t a = kr & 31u, b = gr & 31u;
+            const uint32_t we = min(kr >> 5, wmax), wc = gr >> 5;
+            if (we != cwe) {
+                cwe = we; E0w = E0[we]; E1w = E1[we]; EJw = EJ[we];
+                if (PF && (we & 31u) == 0) { prefetch_l2(E0 + we + 64); prefetch_l2(E1 + we + 64); prefetch_l2(EJ + we + 64); }
+            }
+            if (wc != cwc) {
+                cwc = wc; C0w = C0[wc]; C1w = C1[wc]; CXw = CX[wc];
+                if (PF && (wc & 31u) == 0) { prefetch_l2(C0 + wc + 64); prefetch_l2(C1 + wc + 64); prefetch_l2(CX + wc + 64); }
+            }
+            const uint32_t c0 = C0w >> b, c1 = C1w >> b, cx = CXw >> b;
+            const uint32_t n = min(min(32u - a, 32u - b), gto - gr);
+            const uint32_t term = ((((E0w >> a) ^ c0) | ((E1w >> a) ^ c1) | cx)) & ~(EJw >> a);       // bit i: draw k+i ends locus g+i
+            const uint32_t t = (uint32_t)__ffs(~term) - 1u;                // trailing ones; 0xffffffff when term is all ones
+            if (t >= n) { gr += n; kr += n; continue; }
+            gr += t; kr += t;
+            // draw k repeats the reference base of locus g (or was rejected): keep drawing for this locus
+            const uint32_t m0 = 0u - ((c0 >> t) & 1u), m1 = 0u - ((c1 >> t) & 1u), mx = 0u - ((cx >> t) & 1u);
+            for (;;) {
+                const uint32_t w = min(kr >> 5, wmax);
+                if (w != cwe) { cwe = w; E0w = E0[w]; E1w = E1[w]; EJw = EJ[w]; }
+                const uint32_t ends = (((E0w ^ m0) | (E1w ^ m1) | mx) & ~EJw) >> (kr & 31u);
+                if (ends == 0u) { kr = (kr | 31u) + 1u; continue; }
+                kr += (uint32_t)__ffs(ends);                               // the ending draw is consumed too
+                break;
+            }
+            gr += 1;
+            if (kr > 0x7f000000u) break;                                   // re-base before the 32-bit cursor can wrap
         }
-        const uint32_t e0 = A.e0[we] >> a, e1 = A.e1[we] >> a, ej = A.ej[we] >> a;
-        const uint32_t c0 = A.c0[wc] >> b, c1 = A.c1[wc] >> b, cx = A.cx[wc] >> b;
-        uint32_t n = 32 - a; if (32 - b < n) n = 32 - b; if ((uint64_t)(g_to - g) < n) n = (uint32_t)(g_to - g);
-        const uint32_t term = ((e0 ^ c0) | (e1 ^ c1) | cx) & ~ej;       // bit i: draw k+i ends locus g+i
-        const uint32_t t = (~term) ? (uint32_t)(__ffs(~term) - 1) : 32u;
-        if (t >= n) { g += n; k += n; continue; }
-        g += t; k += t;
-        // draw k repeats the reference base of locus g (or was rejected): keep drawing for this locus
-        const uint32_t m0 = ((c0 >> t) & 1u) ? 0xffffffffu : 0u, m1 = ((c1 >> t) & 1u) ? 0xffffffffu : 0u, mx = ((cx >> t) & 1u) ? 0xffffffffu : 0u;
-        for (;;) {
-            if (k + 64 > A.M) return false;
-            const size_t w = (size_t)(k >> 5);
-            const uint32_t ends = (((A.e0[w] ^ m0) | (A.e1[w] ^ m1) | mx) & ~A.ej[w]) >> (uint32_t)(k & 31);
-            if (ends == 0u) { k = (unsigned long long)(w + 1) << 5; continue; }
-            k += (unsigned long long)__ffs(ends);                       // the ending draw is consumed too
-            break;
-        }
-        g += 1;
+        k = kb + kr; g = gb + gr;
     }
-    return true;
+    return k + 64 <= A.M;
 }
 
 __device__ __forceinline__ bool next_rand(const ChainArgs &A, unsigned long long &k, uint32_t &r)
@@ -351,7 +371,7 @@ constexpr int P1_THREADS = 256;
 // On exit: n_cls[j] survivors, (lo, k_out) pairs in half 0 of the chunk's slots, sorted by lo.
 __global__ void __launch_bounds__(P1_THREADS)
 phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned long long *__restrict__ kbuf, uint32_t *__restrict__ lobuf,
-              unsigned long long stride, uint32_t *__restrict__ n_cls, unsigned int *__restrict__ flags)
+              unsigned long long stride, uint32_t *__restrict__ n_cls, unsigned int *__restrict__ flags, unsigned long long *__restrict__ dbg)
 {
     __shared__ uint32_t s_warp[P1_THREADS / 32];
     __shared__ int s_bad;
@@ -370,6 +390,7 @@ phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned
         int64_t gc = g + step; if (gc > g1 || g1 - gc < step / 2) gc = g1;
         const size_t h0 = first_hit_at_or_after(A.hits, A.H, g);
         int bad = 0;
+        if (dbg && tid == 0) { atomicAdd(&dbg[0], (unsigned long long)alive * (unsigned long long)(gc - g)); atomicAdd(&dbg[3], 1ull); }
         for (uint32_t i = tid; i < alive; i += P1_THREADS) {
             unsigned long long k = kb[cur][i];
             bad |= dry_walk(A, g, gc, h0, k);
@@ -400,7 +421,7 @@ phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned
     if (cur != 0) {                                    // results always in half 0
         for (uint32_t i = tid; i < alive; i += P1_THREADS) { kb[0][i] = kb[1][i]; lb[0][i] = lb[1][i]; }
     }
-    if (tid == 0) n_cls[j] = alive;
+    if (tid == 0) { n_cls[j] = alive; if (dbg) { atomicAdd(&dbg[1], (unsigned long long)alive); atomicMax(&dbg[2], (unsigned long long)alive); } }
 }
 
 // phase 2: one warp walks the chunk maps in order.  entry[j] = exact draw offset at the start of chunk j.
