@@ -189,6 +189,8 @@ def run(args, D):
                      "whole_path": {"algorithmic_bytes_per_step": n + out_bytes, "achieved": (n + out_bytes) * args.steps / (ms / 1e3) / 1e9,
                                     "frac": (n + out_bytes) * args.steps / (ms / 1e3) / 1e9 / peak}},
         "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        "kernel_groups_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+        "chain_chunks": stats["chain_mode"],
         "rng_chain": {"ms_per_step": stage_ms.get("ms_chain", 0.0) / args.steps, "draws": stats["rng_draws"],
                       "note": "serial by construction: one glibc rand() stream consumed at every covered locus (stochasticSpike.c:1197)"},
         "clocks": clk.summary(),

@@ -599,67 +599,82 @@ __device__ __forceinline__ uint32_t exc_word(const uint8_t *seq, const uint8_t *
     return (~samparse::zero_bytes(sq ^ refw) | samparse::zero_bytes(ql ^ 0x21212121u)) & 0x80808080u;
 }
 
+// the rare path of the fast tally: one exceptional base of read o at reference position x, evaluated exactly
+__device__ __noinline__ void tally_exceptional_base(const TallyArgs &A, uint32_t o, int32_t x, int64_t g)
+{
+    const SamRec &r = A.recs[A.k_rec[o]];
+    ReadView mem[3]; int n = 0, self = 0;
+    const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
+    if (p != PRV_NONE && (uint32_t)A.k_end[p] > (uint32_t)r.pos) mem[n++] = view_of(A.sam, A.recs[A.k_rec[p]], p, NULL, 0, 0);
+    self = n; mem[n++] = view_of(A.sam, r, o, NULL, 0, 0);
+    if (q != NO_MATE) mem[n++] = view_of(A.sam, A.recs[A.k_rec[q]], q, NULL, 0, 0);
+    ReadView cov[3]; int nc = 0, sc = 0;
+    for (int m = 0; m < n; m++) if (mem[m].pos <= x && x < mem[m].end) { if (m == self) sc = nc; cov[nc++] = mem[m]; }
+    const uint8_t F = A.contig_seq[r.tid][x];
+    tally_add(A, g, chain_contribution(cov, nc, sc, x, F));
+}
+
+// Compact per-read metadata for the fast tally (one 32-byte load instead of a chain of dependent loads)
+struct __align__(16) KMeta { unsigned long long line_off; uint32_t seq_off, qual_off, l_seq; int32_t pos, end; uint32_t tid_bits; };
+static_assert(sizeof(KMeta) == 32, "KMeta layout");
+
+__global__ void kmeta_kernel(const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec, size_t K, KMeta *__restrict__ km)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= K) return;
+    const SamRec &r = recs[k_rec[o]];
+    KMeta m; m.line_off = r.line_off; m.seq_off = r.seq_off; m.qual_off = r.qual_off; m.l_seq = r.l_seq; m.pos = r.pos; m.end = r.end;
+    m.tid_bits = ((uint32_t)r.tid << 8) | r.bits;
+    km[o] = m;
+}
+
 // One warp per read: SEQ, QUAL and the reference compared four bytes per lane; only bytes that differ from the
 // reference or have BQ 0 -- in this read or in an overlapping mate -- are evaluated one by one.
-__global__ void __launch_bounds__(256)
-tally_fast_kernel(TallyArgs A)
+__global__ void __launch_bounds__(128, 8)
+tally_fast_kernel(TallyArgs A, const KMeta *__restrict__ km)
 {
     const int lane = threadIdx.x & 31;
     const size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (o >= A.K) return;
-    const SamRec &r = A.recs[A.k_rec[o]];
     const unsigned int n_odd = *A.n_odd; const unsigned long long bloom = *A.odd_bloom;
-    if (!tally_is_fast(A, o, r, n_odd, bloom)) return;
-    const int tid = r.tid;
-    const uint8_t *ref = A.contig_seq[tid];
-    if (!ref || (int64_t)r.end > A.contig_len[tid]) { if (lane == 0) set_err(A.err, SSB_E_REF, r.line_off); return; }
-    size_t ri; { size_t lo = 0, hi = A.R; while (hi - lo > 1) { size_t mid = (lo + hi) >> 1;
-                   bool le = A.runs[mid].tid < tid || (A.runs[mid].tid == tid && A.runs[mid].start <= r.pos); if (le) lo = mid; else hi = mid; } ri = lo; }
-    const int64_t gbase = A.runs[ri].base - A.runs[ri].start + r.pos;    // covered ordinal of query offset 0
-    const uint8_t *seq = A.sam + r.line_off + r.seq_off, *qual = A.sam + r.line_off + r.qual_off, *rf = ref + r.pos;
-    const bool qstar = (r.bits & REC_QUALSTAR) != 0;
-    const uint32_t L = r.l_seq;
-    // mate chain neighbours (same QNAME, spans overlap): [p?, me, q?]
-    ReadView mem[3]; int n = 0, self = 0;
+    const KMeta me = km[o];
     const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
-    if (p != PRV_NONE && (uint32_t)A.k_end[p] > (uint32_t)r.pos) mem[n++] = view_of(A.sam, A.recs[A.k_rec[p]], p, NULL, 0, 0);
-    self = n; mem[n++] = view_of(A.sam, r, (uint32_t)o, NULL, 0, 0);
-    if (q != NO_MATE) mem[n++] = view_of(A.sam, A.recs[A.k_rec[q]], q, NULL, 0, 0);
+    auto simple_ok = [&](uint32_t idx, uint32_t tid_bits) {
+        return (tid_bits & REC_SIMPLE) && !A.cplx[idx] && !(n_odd && (bloom & odd_bit(idx)));
+    };
+    if (!simple_ok((uint32_t)o, me.tid_bits)) return;
+    KMeta mp, mq; mp.pos = 0; mp.end = 0; mq.pos = 0; mq.end = 0;
+    bool hp = false, hq = false;
+    if (p != PRV_NONE) { mp = km[p]; if (!simple_ok(p, mp.tid_bits)) return; hp = mp.end > me.pos; }
+    if (q != NO_MATE) { mq = km[q]; if (!simple_ok(q, mq.tid_bits)) return; hq = true; }
+    const int tid = (int)(me.tid_bits >> 8);
+    const uint8_t *ref = A.contig_seq[tid];
+    if (!ref || (int64_t)me.end > A.contig_len[tid]) { if (lane == 0) set_err(A.err, SSB_E_REF, me.line_off); return; }
+    size_t ri; { size_t lo = 0, hi = A.R; while (hi - lo > 1) { size_t mid = (lo + hi) >> 1;
+                   bool le = A.runs[mid].tid < tid || (A.runs[mid].tid == tid && A.runs[mid].start <= me.pos); if (le) lo = mid; else hi = mid; } ri = lo; }
+    const int64_t gbase = A.runs[ri].base - A.runs[ri].start + me.pos;    // covered ordinal of query offset 0
+    const uint8_t *seq = A.sam + me.line_off + me.seq_off, *qual = A.sam + me.line_off + me.qual_off, *rf = ref + me.pos;
+    const bool qstar = (me.tid_bits & REC_QUALSTAR) != 0;
+    const uint32_t L = me.l_seq;
     for (uint32_t w = lane * 4; w < L; w += 128) {
         const uint32_t rw = ldg_u32_unaligned(rf + w);
         uint32_t exc = exc_word(seq, qual, qstar, w, rw);
-        const int32_t x0 = r.pos + (int32_t)w;
-        for (int m = 0; m < n; m++) {
-            if (m == self) continue;
-            const ReadView &v = mem[m];
-            if (x0 + 3 < v.pos || x0 >= v.end) continue;              // no byte of this word under the mate
-            if (x0 >= v.pos && x0 + 4 <= v.end) exc |= exc_word(v.line + v.seq_off, v.line + v.qual_off, v.qual_star, (uint32_t)(x0 - v.pos), rw);
+        const int32_t x0 = me.pos + (int32_t)w;
+        if (hp && !(x0 + 3 < mp.pos || x0 >= mp.end)) {
+            if (x0 >= mp.pos && x0 + 4 <= mp.end)
+                exc |= exc_word(A.sam + mp.line_off + mp.seq_off, A.sam + mp.line_off + mp.qual_off, (mp.tid_bits & REC_QUALSTAR) != 0, (uint32_t)(x0 - mp.pos), rw);
             else exc = 0x80808080u;                                    // the mate starts or ends inside this word: look at every byte
+        }
+        if (hq && !(x0 + 3 < mq.pos || x0 >= mq.end)) {
+            if (x0 >= mq.pos && x0 + 4 <= mq.end)
+                exc |= exc_word(A.sam + mq.line_off + mq.seq_off, A.sam + mq.line_off + mq.qual_off, (mq.tid_bits & REC_QUALSTAR) != 0, (uint32_t)(x0 - mq.pos), rw);
+            else exc = 0x80808080u;
         }
         const uint32_t rem = L - w;
         if (rem < 4) exc &= (1u << (8 * rem)) - 1u;
-        if (!exc) continue;
-        const uint32_t sq = ldg_u32_unaligned(seq + w);
-        const uint32_t ql = qstar ? 0x7e7e7e7eu : ldg_u32_unaligned(qual + w);
         while (exc) {
             const int k = (__ffs(exc) - 1) >> 3; exc &= exc - 1;
-            const int32_t x = x0 + k;
-            const uint8_t F = (uint8_t)(rw >> (8 * k));
-            int contrib;
-            bool overlapped = false;
-            for (int m = 0; m < n; m++) if (m != self && mem[m].pos <= x && x < mem[m].end) overlapped = true;
-            if (overlapped) {
-                ReadView cov[3]; int nc = 0, sc = 0;
-                for (int m = 0; m < n; m++) if (mem[m].pos <= x && x < mem[m].end) { if (m == self) sc = nc; cov[nc++] = mem[m]; }
-                contrib = chain_contribution(cov, nc, sc, x, F);
-            } else {
-                const uint8_t b = (uint8_t)(sq >> (8 * k));
-                const int bq = qstar ? 255 : (int)((ql >> (8 * k)) & 0xff) - 33;
-                if (bq == 0 || b == 'N') contrib = 0;
-                else if (b == F) contrib = 1;
-                else { const int gi = gcat_index(b); contrib = gi < 4 ? 2 + gi : 0; }
-            }
-            tally_add(A, gbase + w + k, contrib);
+            tally_exceptional_base(A, (uint32_t)o, x0 + k, gbase + w + k);
         }
     }
 }
@@ -1298,7 +1313,9 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         TA.nxt = nxt; TA.prv = prv; TA.cplx = cplx; TA.maxspan = h_maxspan; TA.runs = runs; TA.R = R;
         TA.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; TA.contig_len = sp->d_lens; TA.err64 = err64; TA.minus = minus; TA.err = d_err;
         TA.odd = d_odd; TA.n_odd = d_nodd; TA.odd_bloom = d_bloom;
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_fast_kernel, grid_for(K * 32, 256), 256, 0, s, TA);
+        KMeta *kmeta = ar.get<KMeta>(K); SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, kmeta_kernel, grid_for(K, 256), 256, 0, s, recs, k_rec, K, kmeta);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_fast_kernel, grid_for(K * 32, 128), 128, 0, s, TA, kmeta);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_kernel, grid_for(K, 128), 128, 0, s, TA);
         if ((rc = dev_error(ctx, s, d_err, "reference"))) return rc;
         if (H) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_clear_hits_kernel, grid_for(H, 256), 256, 0, s, hits, H, err64);
