@@ -194,10 +194,19 @@ __global__ void cls_kernel(const CovRun *__restrict__ runs, size_t R, int64_t n_
 // ------------------------------------------------------------------------------------------
 __global__ void iota_kernel(uint32_t *p, size_t n) { size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
 
-__global__ void outlen_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ k_len, size_t K, unsigned long long *__restrict__ len)
+// per output line: where it comes from (one 16-byte load in the emit kernel instead of a chain of dependent loads)
+struct __align__(16) EmitDesc { unsigned long long src_off; uint32_t len; uint32_t add_nl; };
+
+__global__ void outlen_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ k_len, const uint32_t *__restrict__ k_rec,
+                              const SamRec *__restrict__ recs, size_t K, unsigned long long *__restrict__ len, EmitDesc *__restrict__ desc)
 {
     size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < K) len[o] = k_len[perm[o]];
+    if (o >= K) return;
+    const uint32_t ord = perm[o];
+    len[o] = k_len[ord];
+    const SamRec &r = recs[k_rec[ord]];
+    EmitDesc d; d.src_off = r.line_off; d.len = r.line_len; d.add_nl = (r.bits & REC_NO_NL) ? 1u : 0u;
+    desc[o] = d;
 }
 
 __global__ void ordoff_kernel(const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ out_off, size_t K, unsigned long long *__restrict__ ord_off)
@@ -208,16 +217,16 @@ __global__ void ordoff_kernel(const uint32_t *__restrict__ perm, const unsigned 
 
 // One warp per output line: dst-aligned 4-byte stores, source words funnel-shifted into place.
 __global__ void __launch_bounds__(256)
-emit_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
-            const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ out_off, size_t K, uint8_t *__restrict__ out)
+emit_kernel(const uint8_t *__restrict__ sam, const EmitDesc *__restrict__ desc, const unsigned long long *__restrict__ out_off, size_t K,
+            uint8_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t o = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); o < K; o += warps) {
-        const SamRec &r = recs[k_rec[perm[o]]];
-        const uint8_t *src = sam + r.line_off;
+        const EmitDesc r = desc[o];
+        const uint8_t *src = sam + r.src_off;
         uint8_t *dst = out + out_off[o];
-        const uint32_t len = r.line_len;
+        const uint32_t len = r.len;
         // head: bytes up to the first 4-byte aligned destination address
         uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
         if (head > len) head = len;
@@ -235,7 +244,7 @@ emit_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, co
         }
         const uint32_t done = head + (words << 2);
         if (done + lane < len) dst[done + lane] = src[done + lane];       // < 4 tail bytes
-        if (lane == 0 && (r.bits & REC_NO_NL)) dst[len] = '\n';
+        if (lane == 0 && r.add_nl) dst[len] = '\n';
     }
 }
 
@@ -1040,7 +1049,8 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         void *tmp = ar.get<uint8_t>(bytes); SPK_CHECK_ARENA(ar);
         SSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, bytes, k_end, s_end, iota, perm, K, 0, 32 + tid_bits, s));   // stable: ties keep input order
         ctx->launches += 8;
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, outlen_kernel, grid_for(K, 256), 256, 0, s, perm, k_len, K, olen);
+        EmitDesc *edesc = ar.get<EmitDesc>(K); SPK_CHECK_ARENA(ar);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, outlen_kernel, grid_for(K, 256), 256, 0, s, perm, k_len, k_rec, recs, K, olen, edesc);
         if ((rc = scan_sum(ar, ctx, olen, out_off, K))) return rc;
         unsigned long long last_off = 0, last_len = 0;
         SSB_CUDA(ctx, cudaMemcpyAsync(&last_off, out_off + K - 1, 8, cudaMemcpyDeviceToHost, s));
@@ -1050,7 +1060,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         if (total_out > out_cap) { snprintf(ctx->err, sizeof ctx->err, "spike: output needs %llu bytes, capacity %zu", total_out, out_cap); return SSB_E_ARG; }
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, ordoff_kernel, grid_for(K, 256), 256, 0, s, perm, out_off, K, ord_off);
         SSB_CUDA(ctx, cudaEventRecord(ev[3], s));
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, emit_kernel, ctx->sm_count * 8, 256, 0, s, d_sam, recs, k_rec, perm, out_off, K, d_out);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, emit_kernel, ctx->sm_count * 8, 256, 0, s, d_sam, edesc, out_off, K, d_out);
     } else SSB_CUDA(ctx, cudaEventRecord(ev[3], s));
     *out_bytes = (size_t)total_out;
     stats->out_bytes = (int64_t)total_out;

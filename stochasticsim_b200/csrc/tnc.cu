@@ -36,6 +36,7 @@ constexpr size_t   TNC_MAX_PIECE = (size_t)1 << 30;
 // A piece this small can never overflow the exception list: at most one record per 2 bytes
 // ("\n>" headers) = 65536 < tnc_exc_cap(131072) = 8192 + 65536.
 constexpr size_t   TNC_SAFE_PIECE = (size_t)1 << 17;
+constexpr int      TNC_SEG_SHIFT = 12;            // 4 KiB segments = 128 chunks of 32 bytes
 
 struct TncDevState {                          // mirrors ssb_tnc_carry
     uint8_t started, prev[3], carry, frag_nonempty, frag_first, frag_has_base;
@@ -101,7 +102,7 @@ __device__ __forceinline__ uint32_t ld_word(const uint8_t *b, size_t n, size_t o
 __global__ void __launch_bounds__(TNC_BLOCK, 2)
 tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__restrict__ st_in,
                 unsigned long long *__restrict__ counts, uint32_t *__restrict__ exc_count,
-                uint32_t *__restrict__ exc, uint32_t exc_cap)
+                uint32_t *__restrict__ exc, uint32_t exc_cap, uint32_t *__restrict__ seg_nobase)
 {
     uint32_t cnt[64];
 #pragma unroll
@@ -145,6 +146,8 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
         const uint32_t keep = first ? 0u : 0xFFFFFFFFu;
 
         const uint32_t V   = P.a | P.c | P.g | P.t;
+        // base-free chunks are counted per 4 KiB segment: the fix-up kernel jumps over base-free stretches (N blocks)
+        if (V == 0u) atomicAdd(&seg_nobase[p0 >> TNC_SEG_SHIFT], 1u);
         const uint32_t hV  = hf.a | hf.c | hf.g | hf.t;
         const uint32_t NL2 = back2(P.nl, halo2(hf.nl));        // newline at p-2
         const uint32_t V1  = back1(V, halo1(hV));
@@ -241,11 +244,29 @@ __device__ long scan_fwd_newline(const uint8_t *b, long n, long q)
 
 // Last byte of the nearest kept, newline-terminated record that ends before line start q
 // (0 when there is none): the reference's 1-byte carry (tncCountsProfile.c:441-443).
-__device__ uint8_t resolve_carry(const uint8_t *b, const TncDevState &st, long q)
+// every 32-byte chunk of segment s is free of upper-case bases
+__device__ __forceinline__ bool seg_free(const uint32_t *seg, long n, long s)
+{
+    const long left = n - (s << TNC_SEG_SHIFT);
+    const uint32_t chunks = left >= (1L << TNC_SEG_SHIFT) ? (1u << (TNC_SEG_SHIFT - 5)) : (uint32_t)((left + 31) >> 5);
+    return seg[s] == chunks;
+}
+
+__device__ uint8_t resolve_carry(const uint8_t *b, long n, const uint32_t *seg, const TncDevState &st, long q)
 {
     long e = q - 1;                               // the newline that terminates the previous record
     for (;;) {
         if (e < 0) return st.carry;               // that newline lies before this piece
+        // records that lie completely inside a base-free stretch cannot be kept: jump to the record that straddles its start
+        if (seg && e >= (2L << TNC_SEG_SHIFT)) {
+            long s = (e - 1) >> TNC_SEG_SHIFT;
+            if (seg_free(seg, n, s) && seg_free(seg, n, s - 1)) {
+                while (s > 0 && seg_free(seg, n, s - 1)) s--;
+                const long z0 = s << TNC_SEG_SHIFT;
+                const long f = scan_fwd_newline(b, n, z0);      // first newline inside the stretch (e itself at the latest)
+                if (f < e) e = f;
+            }
+        }
         long a; bool hb;
         scan_back(b, e, a, hb);
         if (a >= 0) {
@@ -269,7 +290,7 @@ __device__ __forceinline__ void bump(unsigned long long *counts, uint8_t x, uint
 
 // A header record occupies [q, f) (q may be -1: it began before the piece).  Undo what the scan
 // counted optimistically inside and right after it.
-__device__ void fix_header(const uint8_t *b, long n, const TncDevState &st, unsigned long long *counts, long q)
+__device__ void fix_header(const uint8_t *b, long n, const uint32_t *seg, const TncDevState &st, unsigned long long *counts, long q)
 {
     const int lane = threadIdx.x & 31;
     long f = scan_fwd_newline(b, n, q < 0 ? 0 : q);
@@ -283,7 +304,7 @@ __device__ void fix_header(const uint8_t *b, long n, const TncDevState &st, unsi
     }
     // (2) the record after the header: the scan used the header's last byte as the carry
     if (f + 2 < n && f - 1 >= 0 && is_base(b[f - 1]) && is_base(b[f + 1]) && is_base(b[f + 2])) {
-        uint8_t carry = resolve_carry(b, st, f + 1);
+        uint8_t carry = resolve_carry(b, n, seg, st, f + 1);
         if (lane == 0) {
             bump(counts, b[f - 1], b[f + 1], b[f + 2], -1);
             if (is_base(carry)) bump(counts, carry, b[f + 1], b[f + 2], +1);
@@ -295,7 +316,7 @@ __global__ void __launch_bounds__(128)
 tnc_fixup_kernel(const uint8_t *__restrict__ b, size_t n_, const TncDevState *__restrict__ st_in,
                  TncDevState *__restrict__ st_out, unsigned long long *__restrict__ counts,
                  const uint32_t *__restrict__ exc_count, uint32_t *__restrict__ ovf,
-                 const uint32_t *__restrict__ exc, uint32_t exc_cap)
+                 const uint32_t *__restrict__ exc, uint32_t exc_cap, const uint32_t *__restrict__ seg)
 {
     const long n = (long)n_;
     TncDevState st = *st_in;
@@ -312,20 +333,20 @@ tnc_fixup_kernel(const uint8_t *__restrict__ b, size_t n_, const TncDevState *__
         if (task < nexc) {
             uint32_t rec = exc[task];
             long p = (long)(rec & ~EXC_HEADER);
-            if (rec & EXC_HEADER) fix_header(b, n, st, counts, p);
+            if (rec & EXC_HEADER) fix_header(b, n, seg, st, counts, p);
             else {
-                uint8_t carry = resolve_carry(b, st, p - 1);
+                uint8_t carry = resolve_carry(b, n, seg, st, p - 1);
                 if (lane == 0 && is_base(carry)) bump(counts, carry, byte_at(b, st, p - 1), b[p], +1);
             }
         } else if (task == nexc) {
-            if (st.frag_nonempty && st.frag_first == '>') fix_header(b, n, st, counts, -1);
+            if (st.frag_nonempty && st.frag_first == '>') fix_header(b, n, seg, st, counts, -1);
         } else if (st_out) {
             long a; bool hb;
             scan_back(b, n, a, hb);
             TncDevState o;
             o.started = 1;
             if (a >= 0) {
-                o.carry = resolve_carry(b, st, a);
+                o.carry = resolve_carry(b, n, seg, st, a);
                 o.frag_nonempty = n > a;
                 o.frag_first = n > a ? b[a] : 0;
                 o.frag_has_base = hb;
@@ -359,7 +380,9 @@ struct TncScratch {
     unsigned long long *acc;         // 64 per-call accumulators
     uint32_t           *exc;
     uint32_t            exc_cap;
-    uint8_t            *tail;        // first byte after the exception list (256-byte aligned)
+    uint32_t           *seg;         // per 4 KiB segment: number of 32-byte chunks without an upper-case base
+    size_t              seg_words;
+    uint8_t            *tail;        // first byte after the scratch arrays (256-byte aligned)
 };
 
 size_t tnc_exc_cap(size_t piece_bytes) { return piece_bytes / 16 + (1u << 16); }
@@ -367,7 +390,11 @@ size_t tnc_exc_cap(size_t piece_bytes) { return piece_bytes / 16 + (1u << 16); }
 int tnc_scratch(ssb_ctx *ctx, size_t piece_bytes, size_t extra_bytes, TncScratch *s)
 {
     size_t cap = tnc_exc_cap(piece_bytes);
+    size_t seg_words = (piece_bytes >> TNC_SEG_SHIFT) + 2;
     size_t head = 1024 + cap * sizeof(uint32_t);
+    head = (head + 255) & ~(size_t)255;
+    const size_t seg_off = head;
+    head += seg_words * sizeof(uint32_t);
     head = (head + 255) & ~(size_t)255;
     int r = ssb_scratch_reserve(ctx, head + extra_bytes);
     if (r) return r;
@@ -379,6 +406,8 @@ int tnc_scratch(ssb_ctx *ctx, size_t piece_bytes, size_t extra_bytes, TncScratch
     s->acc = (unsigned long long *)(base + 256);
     s->exc = (uint32_t *)(base + 1024);
     s->exc_cap = (uint32_t)cap;
+    s->seg = (uint32_t *)(base + seg_off);
+    s->seg_words = seg_words;
     s->tail = base + head;
     return SSB_OK;
 }
@@ -394,14 +423,15 @@ int tnc_piece(ssb_ctx *ctx, cudaStream_t stream, const uint8_t *d, size_t n, con
               TncDevState *st_in, TncDevState *st_out)
 {
     SSB_CUDA(ctx, cudaMemsetAsync(s.exc_count, 0, sizeof(uint32_t), stream));
+    SSB_CUDA(ctx, cudaMemsetAsync(s.seg, 0, ((n >> TNC_SEG_SHIFT) + 2) * sizeof(uint32_t), stream));
     size_t n_chunks = (n + TNC_BPT - 1) / TNC_BPT;
     int grid = (int)((n_chunks + TNC_BLOCK - 1) / TNC_BLOCK);
     int max_grid = ctx->sm_count * 2 * 4;        // 2 resident blocks per SM, 4 block slots of work each
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
-    SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, s.acc, s.exc_count, s.exc, s.exc_cap);
+    SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, s.acc, s.exc_count, s.exc, s.exc_cap, s.seg);
     int fgrid = ctx->sm_count * 4;
-    SSB_LAUNCH_P(ctx, SSB_K_TNC_FIXUP, tnc_fixup_kernel, fgrid, 128, 0, stream, d, n, st_in, st_out, s.acc, s.exc_count, s.ovf, s.exc, s.exc_cap);
+    SSB_LAUNCH_P(ctx, SSB_K_TNC_FIXUP, tnc_fixup_kernel, fgrid, 128, 0, stream, d, n, st_in, st_out, s.acc, s.exc_count, s.ovf, s.exc, s.exc_cap, s.seg);
     return SSB_OK;
 }
 
