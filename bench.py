@@ -350,6 +350,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # only the JSON line may reach stdout: libraries (NCCL prints its version there) go to stderr meanwhile
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     D = Dist(args.gpus)
     workload = args.workload
     if workload == "auto":
@@ -366,7 +377,7 @@ def main():
         else:
             res = run_tnc_reference(args, D)
         if D.rank == 0:
-            print(json.dumps(res), flush=True)
+            emit(res)
         D.close()
         return
 
@@ -388,7 +399,7 @@ def main():
             assert got.encode() == ref_out, "GPU counts differ from the reference binary on the CPU sample"
             res["cpu_baseline"] = cb
     if D.rank == 0:
-        print(json.dumps(res), flush=True)
+        emit(res)
     D.close()
 
 

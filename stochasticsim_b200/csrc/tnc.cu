@@ -30,13 +30,13 @@
 namespace {
 
 constexpr int      TNC_BLOCK = 256;
-constexpr int      TNC_BPT   = 32;            // bytes per thread per iteration
+constexpr int      TNC_BPT   = 16;            // bytes per thread per iteration
 constexpr uint32_t EXC_HEADER = 0x80000000u;  // exception kind flag (positions stay < 2^31)
 constexpr size_t   TNC_MAX_PIECE = (size_t)1 << 30;
 // A piece this small can never overflow the exception list: at most one record per 2 bytes
 // ("\n>" headers) = 65536 < tnc_exc_cap(131072) = 8192 + 65536.
 constexpr size_t   TNC_SAFE_PIECE = (size_t)1 << 17;
-constexpr int      TNC_SEG_SHIFT = 12;            // 4 KiB segments = 128 chunks of 32 bytes
+constexpr int      TNC_SEG_SHIFT = 12;            // 4 KiB segments = 256 chunks of 16 bytes
 
 struct TncDevState {                          // mirrors ssb_tnc_carry
     uint8_t started, prev[3], carry, frag_nonempty, frag_first, frag_has_base;
@@ -47,155 +47,209 @@ __host__ __device__ inline bool is_base(uint8_t c) { return c == 'A' || c == 'C'
 // reference index order A<C<G<T (tncCountsProfile.c:14-77)
 __host__ __device__ inline int ref_code(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
 
-// ---- per-word classification -------------------------------------------------------------
-// Flags come back in bit 7 of every byte of the word.
-struct WordFlags { uint32_t a, c, g, t, nl, gt; };
+// ---- scan kernel ------------------------------------------------------------------------------
+// Every thread takes 16 bytes per iteration.  Fast path (all bytes of the chunk and of its 2-byte halo are one of
+// A C G T '\n', verified exactly with one PRMT table lookup per word): bytes become 3-bit symbols
+// ((b >> 1) & 3 for the bases, bit 2 set for '\n'), and the 4-mers that start at every second position go into a
+// 4096-bin shared-memory histogram -- one shared atomic per two windows.  When the block is done the histogram is
+// folded: bin (s0,s1,s2,s3) feeds window (s0,s1,s2) and window (s1,s2,s3) when their symbols are bases.
+// Anything else in a chunk (N, lower case, '>', '\r', the ragged end of the piece) takes the generic path, which
+// looks at every position.  Newlines are not handled where they are found (that would make every warp execute the
+// rare code for a few lanes): their positions go into a per-warp queue that is drained 32 at a time, one newline
+// per lane: the straddling window (b[q-1], b[q+1], b[q+2]) is counted if its carry byte is a base, otherwise it
+// becomes an exception for tnc_fixup_kernel; a '>' behind the newline becomes a header exception.
+constexpr int TNC_WARPS = TNC_BLOCK / 32;
+constexpr int TNC_SUB = 4;                        // 16-byte chunks per thread and warp iteration
+constexpr int NLQ_CAP = 128;                      // >= 31 left over + 32 lanes * up to 2 newlines in 16 bytes... drained when >= 32
 
-__device__ __forceinline__ WordFlags classify(uint32_t w)
+__device__ __forceinline__ uint32_t zero_bytes_mask(uint32_t d) { return ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d | 0x7f7f7f7fu); }
+
+// non-zero iff some byte of w is not one of A C G T '\n'   (low three bits 1 3 7 4 2 select the only candidate)
+__device__ __forceinline__ uint32_t not_acgtnl(uint32_t w)
 {
-    // 8-entry byte table indexed by the low 3 bits of the byte: the only byte with those low
-    // bits that we care about.  A=0x41(1) C=0x43(3) G=0x47(7) T=0x54(4) '\n'=0x0A(2) '>'=0x3E(6).
-    // Entries 0 and 5 hold 0x01, which can never equal a byte whose low bits are 0 or 5.
-    const uint32_t TLO = 0x430A4101u, THI = 0x473E0154u;
-    uint32_t s  = w & 0x07070707u;
-    uint32_t e0 = __byte_perm(TLO, THI, s);          // [T[b0], T[0], T[b1], T[0]]
-    uint32_t e1 = __byte_perm(TLO, THI, s >> 16);    // [T[b2], T[0], T[b3], T[0]]
-    uint32_t e  = __byte_perm(e0, e1, 0x6420);       // [T[b0], T[b1], T[b2], T[b3]]
-    uint32_t d  = w ^ e;                             // zero byte <=> byte is one of the six
-    uint32_t t2 = (d & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-    uint32_t z  = ~(t2 | d | 0x7f7f7f7fu);           // 0x80 where the byte of d is zero (exact)
-    uint32_t w1 = w << 1, w5 = w << 5, w6 = w << 6;  // bit6 / bit2 / bit1 of each byte -> bit 7
-    uint32_t base = z & w1;
-    WordFlags f;
-    f.a  = base & ~w5 & ~w6;
-    f.c  = base & ~w5 &  w6;
-    f.g  = base &  w5 &  w6;
-    f.t  = base &  w5 & ~w6;
-    f.nl = z & ~w1 & ~w5;
-    f.gt = z & ~w1 &  w5;
-    return f;
+    const uint32_t TLO = 0x430A4101u, THI = 0x47010154u;      // idx 0->01 1->'A' 2->'\n' 3->'C' | 4->'T' 5->01 6->01 7->'G'
+    const uint32_t sidx = w & 0x07070707u;
+    const uint32_t e0 = __byte_perm(TLO, THI, sidx), e1 = __byte_perm(TLO, THI, sidx >> 16);
+    return w ^ __byte_perm(e0, e1, 0x6420);
 }
-
-// Bit planes over the 32 positions of a thread, in "residue-major" order:
-// bit (8k + j) <-> byte k of word j <-> position 4j + k.
-struct Planes { uint32_t a, c, g, t, nl, gt; };
-
-// plane value at position p-1 / p-2 / p-3, given the flags of the 3 bytes before the thread's chunk
-__device__ __forceinline__ uint32_t back1(uint32_t u, uint32_t h) { return (u << 8)  | ((u >> 23) & 0x000000FEu) | h; }
-__device__ __forceinline__ uint32_t back2(uint32_t u, uint32_t h) { return (u << 16) | ((u >> 15) & 0x0000FEFEu) | h; }
-__device__ __forceinline__ uint32_t back3(uint32_t u, uint32_t h) { return (u << 24) | ((u >> 7)  & 0x00FEFEFEu) | h; }
-
-// halo flags (bit 7 of bytes 1..3 of the word before the chunk = positions -3,-2,-1)
-__device__ __forceinline__ uint32_t halo1(uint32_t f) { return (f >> 31) & 1u; }                                   // pos -1 -> bit 0
-__device__ __forceinline__ uint32_t halo2(uint32_t f) { return ((f >> 23) & 1u) | (((f >> 31) & 1u) << 8); }       // -2 -> bit0, -1 -> bit8
-__device__ __forceinline__ uint32_t halo3(uint32_t f) { return ((f >> 15) & 1u) | (((f >> 23) & 1u) << 8) | (((f >> 31) & 1u) << 16); }
+// 3-bit symbols of four bytes known to be A C G T or '\n':  A0 C1 T2 G3, bit 2 set for '\n'
+__device__ __forceinline__ uint32_t symbols(uint32_t w) { return ((w >> 1) & 0x03030303u) | ((~w >> 4) & 0x04040404u); }
+// symbols [a,b,c,d] (one per byte) -> 12-bit bin a | b<<3 | c<<6 | d<<9
+__device__ __forceinline__ uint32_t pack4(uint32_t z) { const uint32_t t = z | (z >> 5); return (t & 0x3Fu) | ((t >> 10) & 0xFC0u); }
 
 __device__ __forceinline__ uint32_t ld_word(const uint8_t *b, size_t n, size_t off)
 {
-    // aligned 4-byte load with zero fill past the end (0x00 is "other": no flag is set for it)
+    // aligned 4-byte load with zero fill past the end (0x00 is "other")
     if (off + 4 <= n) return *reinterpret_cast<const uint32_t *>(b + off);
     uint32_t w = 0;
     for (int k = 0; k < 4; k++) if (off + k < n) w |= (uint32_t)b[off + k] << (8 * k);
     return w;
 }
 
-__global__ void __launch_bounds__(TNC_BLOCK, 2)
+// one newline per lane: q = its position (q < n), or -1 / -2 for a newline that closes the 3-byte halo of the piece
+__device__ __forceinline__ void handle_newline(const uint8_t *__restrict__ b, long n, const TncDevState &st, long q, uint32_t *hist3,
+                                               uint32_t *__restrict__ exc_count, uint32_t *__restrict__ exc, uint32_t exc_cap)
+{
+    auto at = [&](long i) -> uint8_t { return i >= 0 ? b[i] : st.prev[3 + i]; };
+    auto push = [&](uint32_t rec) { uint32_t slot = atomicAdd(exc_count, 1u); if (slot < exc_cap) exc[slot] = rec; };
+    if (q + 1 >= 0 && q + 1 < n && b[q + 1] == '>') push((uint32_t)(q + 1) | EXC_HEADER);        // a header record starts here
+    const long p = q + 2;
+    if (p >= n) return;
+    const uint8_t c1 = at(q + 1), c2 = b[p];
+    if (!is_base(c1) || !is_base(c2)) return;
+    // the straddling window needs the last byte of the record before the newline; when that byte is not a base, or lies
+    // before this piece, the fix-up kernel finds the real carry
+    if (q >= 1 && is_base(b[q - 1])) atomicAdd(&hist3[16 * ref_code(b[q - 1]) + 4 * ref_code(c1) + ref_code(c2)], 1u);
+    else push((uint32_t)p);
+}
+
+__global__ void __launch_bounds__(TNC_BLOCK)
 tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__restrict__ st_in,
                 unsigned long long *__restrict__ counts, uint32_t *__restrict__ exc_count,
                 uint32_t *__restrict__ exc, uint32_t exc_cap, uint32_t *__restrict__ seg_nobase)
 {
-    uint32_t cnt[64];
-#pragma unroll
-    for (int i = 0; i < 64; i++) cnt[i] = 0;
+    __shared__ uint32_t hist4[4096];
+    __shared__ uint32_t hist3[64];
+    __shared__ uint32_t nlq[TNC_WARPS][NLQ_CAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 4096; i += TNC_BLOCK) hist4[i] = 0;
+    if (threadIdx.x < 64) hist3[threadIdx.x] = 0;
+    __syncthreads();
+    TncDevState st = *st_in;
+    if (!st.started) { st.prev[0] = st.prev[1] = st.prev[2] = '\n'; }                 // start of file behaves like "\n\n\n"
+    uint32_t qn = 0;                                                                   // entries in this warp's newline queue (warp uniform)
+    uint32_t *q = nlq[wid];
 
     const size_t n_chunks = (n + TNC_BPT - 1) / TNC_BPT;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t chunk = (size_t)blockIdx.x * blockDim.x + threadIdx.x; chunk < n_chunks; chunk += stride) {
+    // a warp iteration covers TNC_SUB * 32 consecutive chunks (lane l takes chunks l, l+32, ...): the loop overhead and the
+    // newline queue are paid once per 2 KiB.  All lanes of a warp run the same number of iterations (the queue is warp collective).
+    const size_t stride = ((size_t)gridDim.x * blockDim.x) * TNC_SUB;
+    const size_t warp_first = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) - lane) * TNC_SUB;
+    for (size_t cbase = warp_first; cbase < n_chunks; cbase += stride) {
+      unsigned long long nl64 = 0;                                                     // bit 16*sub + i: byte i of sub-chunk `sub` is '\n'
+#pragma unroll 1
+      for (int sub = 0; sub < TNC_SUB; sub++) {
+        const size_t chunk = cbase + (size_t)sub * 32 + lane;
+        uint32_t nlmask = 0;
         const size_t p0 = chunk * TNC_BPT;
-        uint32_t w[8];
-        if (p0 + TNC_BPT <= n) {
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(b + p0);
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(b + p0 + 16);
-            w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
-        } else {
+        if (chunk < n_chunks) {
+            uint32_t w[4];
+            if (p0 + TNC_BPT <= n) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(b + p0);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; j++) w[j] = ld_word(b, n, p0 + 4 * j);
-        }
-        // the 4 bytes before the chunk; for the very first chunk they come from the carried state
-        uint32_t hw;
-        bool first = (p0 == 0);
-        if (!first) hw = *reinterpret_cast<const uint32_t *>(b + p0 - 4);
-        else {
-            TncDevState s = *st_in;
-            hw = s.started ? ((uint32_t)s.prev[0] << 8 | (uint32_t)s.prev[1] << 16 | (uint32_t)s.prev[2] << 24)
-                           : 0x0A0A0A00u;                      // start of file behaves like "\n\n\n"
-        }
-        Planes P = {0, 0, 0, 0, 0, 0};
+                for (int j = 0; j < 4; j++) w[j] = ld_word(b, n, p0 + 4 * j);
+            }
+            uint32_t hw;                                                               // the 4 bytes before the chunk
+            if (p0) hw = *reinterpret_cast<const uint32_t *>(b + p0 - 4);
+            else hw = (uint32_t)st.prev[0] << 8 | (uint32_t)st.prev[1] << 16 | (uint32_t)st.prev[2] << 24;
+            const uint32_t bad = not_acgtnl(w[0]) | not_acgtnl(w[1]) | not_acgtnl(w[2]) | not_acgtnl(w[3]) | (not_acgtnl(hw) & 0xFFFF0000u);
+            if (bad == 0u && p0 + TNC_BPT <= n) {
+                // ---- fast path ----
+                uint32_t prev = symbols(hw), f0, f1, f2, f3;
+                {
+                    const uint32_t s0 = symbols(w[0]), s1 = symbols(w[1]), s2 = symbols(w[2]), s3 = symbols(w[3]);
+                    atomicAdd(&hist4[pack4(__funnelshift_r(prev, s0, 16))], 1u);     // windows ending at 0, 1
+                    atomicAdd(&hist4[pack4(s0)], 1u);                                // windows ending at 2, 3
+                    atomicAdd(&hist4[pack4(__funnelshift_r(s0, s1, 16))], 1u);
+                    atomicAdd(&hist4[pack4(s1)], 1u);
+                    atomicAdd(&hist4[pack4(__funnelshift_r(s1, s2, 16))], 1u);
+                    atomicAdd(&hist4[pack4(s2)], 1u);
+                    atomicAdd(&hist4[pack4(__funnelshift_r(s2, s3, 16))], 1u);
+                    atomicAdd(&hist4[pack4(s3)], 1u);
+                    f0 = s0 & 0x04040404u; f1 = s1 & 0x04040404u; f2 = s2 & 0x04040404u; f3 = s3 & 0x04040404u;
+                }
+                if (f0 | f1 | f2 | f3) {                                             // a newline in these 16 bytes (one chunk in four)
+                    nlmask = ((((f0 >> 2) * 0x00204081u) >> 21) & 0xFu) | (((((f1 >> 2) * 0x00204081u) >> 21) & 0xFu) << 4) |
+                             (((((f2 >> 2) * 0x00204081u) >> 21) & 0xFu) << 8) | (((((f3 >> 2) * 0x00204081u) >> 21) & 0xFu) << 12);
+                }
+            } else {
+                // ---- generic path: every position on its own ----
+                uint8_t c[19];
+                c[0] = (uint8_t)(hw >> 8); c[1] = (uint8_t)(hw >> 16); c[2] = (uint8_t)(hw >> 24);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            WordFlags f = classify(w[j]);
-            P.a |= f.a >> (7 - j); P.c |= f.c >> (7 - j); P.g |= f.g >> (7 - j);
-            P.t |= f.t >> (7 - j); P.nl |= f.nl >> (7 - j); P.gt |= f.gt >> (7 - j);
-        }
-        // the shifts above drag bit 7 of byte k+1.. into lower bits of neighbours only for j<7:
-        // f >> (7-j) moves bit 7 of byte k to bit j of byte k -- never across a byte. (f has only bit-7 flags.)
-        const WordFlags hf = classify(hw);
-        // Straddle windows need the last byte of the previous record (position p-3).  For the
-        // first chunk of a piece that byte lies in the previous piece: never trust it here, send
-        // the window to the exception path instead (the carried state resolves it).
-        const uint32_t keep = first ? 0u : 0xFFFFFFFFu;
-
-        const uint32_t V   = P.a | P.c | P.g | P.t;
-        // base-free chunks are counted per 4 KiB segment: the fix-up kernel jumps over base-free stretches (N blocks)
-        if (V == 0u) atomicAdd(&seg_nobase[p0 >> TNC_SEG_SHIFT], 1u);
-        const uint32_t hV  = hf.a | hf.c | hf.g | hf.t;
-        const uint32_t NL2 = back2(P.nl, halo2(hf.nl));        // newline at p-2
-        const uint32_t V1  = back1(V, halo1(hV));
-        const uint32_t V3c = back3(V, halo3(hV & keep));       // base at p-3, usable as a carry
-        // exceptions ---------------------------------------------------------------
-        uint32_t x2 = NL2 & V1 & V & ~V3c;                     // straddle window whose carry is not the byte before the newline
-        uint32_t x1 = P.gt & back1(P.nl, halo1(hf.nl));        // header record starts here
-        while (x2 | x1) {
-            uint32_t m = x2 ? x2 : x1;
-            uint32_t kind = x2 ? 0u : EXC_HEADER;
-            int bit = __ffs(m) - 1;
-            if (x2) x2 &= x2 - 1; else x1 &= x1 - 1;
-            size_t p = p0 + 4 * (bit & 7) + (bit >> 3);
-            if (p < n) {
-                uint32_t slot = atomicAdd(exc_count, 1u);
-                if (slot < exc_cap) exc[slot] = (uint32_t)p | kind;
+                for (int j = 0; j < 4; j++) { c[3 + 4 * j] = (uint8_t)w[j]; c[4 + 4 * j] = (uint8_t)(w[j] >> 8); c[5 + 4 * j] = (uint8_t)(w[j] >> 16); c[6 + 4 * j] = (uint8_t)(w[j] >> 24); }
+                // upper-case base flags (bit 7 per byte) and newline flags of the four words, exactly
+                uint32_t bf[4], nf[4], anyb = 0, anyn = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t z = zero_bytes_mask(not_acgtnl(w[j]));           // 0x80 where the byte is A C G T or newline
+                    bf[j] = z & (w[j] << 1);                                        // bit 6 set: a base
+                    nf[j] = z & ~(w[j] << 1);
+                    anyb |= bf[j]; anyn |= nf[j];
+                }
+                if (anyn) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) nlmask |= ((((nf[j] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * j);
+                    if (p0 + TNC_BPT > n) nlmask &= (1u << (n - p0)) - 1u;
+                }
+                if (!anyb) atomicAdd(&seg_nobase[p0 >> TNC_SEG_SHIFT], 1u);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        if (p0 + i >= n) break;
+                        const uint8_t x = c[i + 1], y = c[i + 2], z = c[i + 3];
+                        if (is_base(z) && is_base(x) && is_base(y)) atomicAdd(&hist3[16 * ref_code(x) + 4 * ref_code(y) + ref_code(z)], 1u);
+                    }
+                }
+            }
+            if (chunk == 0) {
+                // newlines that close the halo of the piece (positions -2 and -1) are handled right here
+                if (st.prev[1] == '\n') handle_newline(b, (long)n, st, -2, hist3, exc_count, exc, exc_cap);
+                if (st.prev[2] == '\n') handle_newline(b, (long)n, st, -1, hist3, exc_count, exc, exc_cap);
             }
         }
-        // counting -----------------------------------------------------------------
-        uint32_t X[4], Y[4], Z[4];
-        {
-            const uint32_t pl[4]  = {P.a, P.c, P.g, P.t};      // internal order A,C,G,T
-            const uint32_t hpl[4] = {hf.a, hf.c, hf.g, hf.t};
+        nl64 |= (unsigned long long)nlmask << (16 * sub);
+      }
+        // ---- queue the newline positions of this warp iteration, drain 32 at a time ----
+        const unsigned has_nl = __ballot_sync(0xffffffffu, nl64 != 0ull);
+        if (has_nl) {
+            const uint32_t cnt = __popcll(nl64);
+            auto pos_of = [&](int bit) -> size_t { return (cbase + (size_t)(bit >> 4) * 32 + lane) * TNC_BPT + (bit & 15); };
+            uint32_t incl, total;
+            if (__ballot_sync(0xffffffffu, cnt > 1u) == 0u) {                       // the usual case: at most one newline per lane
+                incl = __popc(has_nl & (0xffffffffu >> (31 - lane))); total = __popc(has_nl);
+            } else {
+                incl = cnt;
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
-                Z[x] = pl[x];
-                Y[x] = back1(pl[x], halo1(hpl[x]));
-                X[x] = back2(pl[x], halo2(hpl[x])) | (NL2 & back3(pl[x], halo3(hpl[x] & keep)));
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                total = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (qn + total <= NLQ_CAP) {
+                uint32_t slot = qn + incl - cnt; unsigned long long m = nl64;
+                while (m) { const int bit = __ffsll((long long)m) - 1; m &= m - 1; q[slot++] = (uint32_t)pos_of(bit); }
+                qn += total;
+            } else {
+                // (pathological: more than two newlines per 16 bytes across the warp) handle them in place
+                unsigned long long m = nl64;
+                while (__ballot_sync(0xffffffffu, m != 0ull)) {
+                    if (m) { const int bit = __ffsll((long long)m) - 1; m &= m - 1; handle_newline(b, (long)n, st, (long)pos_of(bit), hist3, exc_count, exc, exc_cap); }
+                }
+            }
+            __syncwarp();
+            while (qn >= 32) {
+                qn -= 32;
+                handle_newline(b, (long)n, st, (long)q[qn + lane], hist3, exc_count, exc, exc_cap);
+                __syncwarp();
             }
         }
-#pragma unroll
-        for (int x = 0; x < 4; x++)
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-                const uint32_t xy = X[x] & Y[y];
-#pragma unroll
-                for (int z = 0; z < 4; z++) cnt[16 * x + 4 * y + z] += __popc(xy & Z[z]);
-            }
     }
-    // fold: warp shuffle reduce, one 64-bit global atomic per warp and context
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int i = 0; i < 64; i++) {
-        uint32_t v = cnt[i];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicAdd(&counts[i], (unsigned long long)v);
+    __syncwarp();
+    if ((uint32_t)lane < qn) handle_newline(b, (long)n, st, (long)q[lane], hist3, exc_count, exc, exc_cap);
+    __syncthreads();
+    // ---- fold the 4-mer histogram into the 64 contexts (reference index order A<C<G<T) ----
+    for (int bin = threadIdx.x; bin < 4096; bin += TNC_BLOCK) {
+        const uint32_t v = hist4[bin];
+        if (!v) continue;
+        const uint32_t s0 = bin & 7, s1 = (bin >> 3) & 7, s2 = (bin >> 6) & 7, s3 = (bin >> 9) & 7;
+        // symbol -> reference code: A0 C1 T2 G3 -> A0 C1 G2 T3
+        const uint32_t r0 = s0 ^ (s0 >> 1), r1 = s1 ^ (s1 >> 1), r2 = s2 ^ (s2 >> 1), r3 = s3 ^ (s3 >> 1);
+        if ((s0 | s1 | s2) < 4) atomicAdd(&hist3[16 * r0 + 4 * r1 + r2], v);
+        if ((s1 | s2 | s3) < 4) atomicAdd(&hist3[16 * r1 + 4 * r2 + r3], v);
     }
+    __syncthreads();
+    if (threadIdx.x < 64 && hist3[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)hist3[threadIdx.x]);
 }
 
 // ---- exception resolution ----------------------------------------------------------------
@@ -248,7 +302,7 @@ __device__ long scan_fwd_newline(const uint8_t *b, long n, long q)
 __device__ __forceinline__ bool seg_free(const uint32_t *seg, long n, long s)
 {
     const long left = n - (s << TNC_SEG_SHIFT);
-    const uint32_t chunks = left >= (1L << TNC_SEG_SHIFT) ? (1u << (TNC_SEG_SHIFT - 5)) : (uint32_t)((left + 31) >> 5);
+    const uint32_t chunks = left >= (1L << TNC_SEG_SHIFT) ? (1u << (TNC_SEG_SHIFT - 4)) : (uint32_t)((left + 15) >> 4);
     return seg[s] == chunks;
 }
 
@@ -425,8 +479,8 @@ int tnc_piece(ssb_ctx *ctx, cudaStream_t stream, const uint8_t *d, size_t n, con
     SSB_CUDA(ctx, cudaMemsetAsync(s.exc_count, 0, sizeof(uint32_t), stream));
     SSB_CUDA(ctx, cudaMemsetAsync(s.seg, 0, ((n >> TNC_SEG_SHIFT) + 2) * sizeof(uint32_t), stream));
     size_t n_chunks = (n + TNC_BPT - 1) / TNC_BPT;
-    int grid = (int)((n_chunks + TNC_BLOCK - 1) / TNC_BLOCK);
-    int max_grid = ctx->sm_count * 2 * 4;        // 2 resident blocks per SM, 4 block slots of work each
+    int grid = (int)((n_chunks + (size_t)TNC_BLOCK * TNC_SUB - 1) / ((size_t)TNC_BLOCK * TNC_SUB));
+    int max_grid = ctx->sm_count * 8;            // persistent: every block folds its 4096-bin histogram once
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, s.acc, s.exc_count, s.exc, s.exc_cap, s.seg);
