@@ -24,8 +24,8 @@ $(LIBDIR)/obj/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/ssb200.h
 $(LIBDIR)/libssb200.so: $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -ldl
 
-$(LIBDIR)/%: $(HOST)/%.c $(LIBDIR)/libssb200.so include/ssb200.h
-	$(CC) -std=c99 -O2 -Wall -D_GNU_SOURCE -Iinclude -o $@ $< -L$(LIBDIR) -lssb200 -Wl,-rpath,'$$ORIGIN' -lm
+$(LIBDIR)/%: $(HOST)/%.c $(LIBDIR)/libssb200.so include/ssb200.h $(wildcard $(HOST)/*.h)
+	$(CC) -std=c99 -O2 -Wall -D_GNU_SOURCE -Iinclude -o $@ $< -L$(LIBDIR) -lssb200 -Wl,-rpath,'$$ORIGIN' -lm -lz -lpthread
 
 tools: tools/_build/gen_synth tools/_build/libsynth.so
 

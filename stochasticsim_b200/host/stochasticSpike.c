@@ -10,10 +10,10 @@
  * back.  The pileup loop itself (:1129-1623) runs on the GPU; there is no CPU fallback: without a
  * B200 the program fails with exit status 3.
  *
- * Input format: argv[1] is alignment TEXT (SAM, coordinate sorted, "-" = stdin).  htslib would also
- * accept BAM there; BGZF decoding is not part of this build and a BAM input is refused with a message
- * (pipe it through `samtools view -h`).  An index is not needed (the reference loads one at :1035 but
- * never uses it, :1078-1080).
+ * Input format: argv[1] is a coordinate-sorted BAM (BGZF; its .bai/.csi must exist, as at :1035-1039, although the
+ * reference never uses it, :1078-1080) or SAM text ("-" = stdin), auto-detected like htslib's sam_open.  BAM is
+ * decoded on the host (bam_input.h: parallel BGZF inflate + sam_format1-style printing) into the SAM text the
+ * GPU tokeniser consumes.
  *
  * Environment: SSB_DEVICE=i selects the CUDA device (default 0).
  */
@@ -28,6 +28,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include "ssb200.h"
+#include "bam_input.h"
 
 #define VERSION "0.01"                        /* stochasticSpike.c:1 */
 
@@ -183,9 +184,27 @@ int main(int argc, char **argv)
     size_t n_in; int mapped;
     uint8_t *in = slurp(argv[1], &n_in, &mapped);
     if (!in) { fprintf(stderr, "Couldn't open bam...\n"); return 1; }                         /* :962-965 */
-    if (n_in >= 2 && in[0] == 0x1f && in[1] == 0x8b) {
-        fprintf(stderr, "%s: %s is BGZF/BAM; this build reads SAM text only (use: samtools view -h %s | %s - ...)\n", cmd, argv[1], argv[1], cmd);
-        return 1;
+    if (bam_is_bgzf(in, n_in)) {
+        /* BGZF: inflate the blocks in parallel; a BAM inside is printed as SAM text (htslib's sam_open auto-detects the same way) */
+        size_t n_raw = 0, n_txt = 0;
+        uint8_t *raw = bgzf_inflate_all(in, n_in, &n_raw);
+        if (!raw) { fprintf(stderr, "Couldn't read header...\n"); return 1; }                        /* :971-975 */
+        if (mapped) munmap(in, n_in); else free(in);
+        mapped = 0;
+        if (n_raw >= 4 && !memcmp(raw, "BAM\1", 4)) {
+            uint8_t *txt = bam_to_sam_text(raw, n_raw, &n_txt);
+            free(raw);
+            if (!txt) { fprintf(stderr, "Couldn't read header...\n"); return 1; }
+            in = txt; n_in = n_txt;
+        } else { in = raw; n_in = n_raw; }                                                            /* bgzip-compressed SAM text */
+        if (strcmp(argv[1], "-") != 0) {                                                              /* :1035-1039: the index must exist */
+            char ip[4200]; int have = 0;
+            snprintf(ip, sizeof ip, "%s.bai", argv[1]); if (access(ip, R_OK) == 0) have = 1;
+            snprintf(ip, sizeof ip, "%s.csi", argv[1]); if (access(ip, R_OK) == 0) have = 1;
+            size_t al = strlen(argv[1]);
+            if (al > 4 && !strcmp(argv[1] + al - 4, ".bam")) { snprintf(ip, sizeof ip, "%.*s.bai", (int)(al - 4), argv[1]); if (access(ip, R_OK) == 0) have = 1; }
+            if (!have) { fprintf(stderr, "\nCan't load index for %s..\n\n", argv[1]); exit(EXIT_FAILURE); }
+        }
     }
     /* header = leading lines that start with '@' (sam_hdr_read, :971) */
     size_t hdr_end = 0;

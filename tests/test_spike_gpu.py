@@ -101,6 +101,26 @@ def test_parallel_chain_matches_serial(name, chunk, tmp_path, ctx, monkeypatch):
         assert st_p.chain_mode > 1, "expected the chunked chain to be used"
 
 
+@pytest.mark.parametrize("name", ["plain", "overlap_heavy", "two_contigs_window"])
+def test_bam_input(name, tmp_path, ctx):
+    """argv[1] as a real BGZF BAM (what bin/spikeIn.bash passes): same SAM, truth.vcf body and stats as from the SAM text."""
+    import bam_writer
+    prefix = sc.generate(name, str(tmp_path))
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    bam = tmp_path / "in.bam"
+    bam.write_bytes(bam_writer.sam_to_bam(open(prefix + ".sam", "rb").read()))
+    # the reference insists on an index next to the BAM (stochasticSpike.c:1035-1039)
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "noidx"), sam=str(bam))
+    assert got[0] == 1 and b"Can't load index" in got[4]
+    (tmp_path / "in.bam.bai").write_bytes(b"BAI\1")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"), sam=str(bam))
+    assert got[0] == 0, got[4]
+    assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
+    assert got[1] == want[1]
+    strip = lambda v: b"\n".join(l for l in v.split(b"\n") if not l.startswith(b"##stochasticSpikeCommand="))
+    assert strip(got[3]) == strip(want[3]), first_diff(strip(want[3]), strip(got[3]))
+
+
 def test_golden_fixture(tmp_path, ctx):
     """tests/golden/spike_toy was produced by the unmodified reference over the htslib shim."""
     for f in ("in.sam", "in.fa", "in.spike"):
