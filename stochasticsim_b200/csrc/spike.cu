@@ -1179,7 +1179,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         const char *env_serial = getenv("SSB_CHAIN_SERIAL");
         int P = 1; int64_t Lc = n_walk;
         const char *env_chunk = getenv("SSB_CHAIN_CHUNK");                 // loci per chunk (testing / tuning)
-        if (!(env_serial && env_serial[0] == '1') && (n_walk >= (1 << 20) || env_chunk)) {
+        // the chunked formulation pays off when the walk between targets dominates; every phase-1 walker dry-runs the pileups it
+        // passes, so dense deep panels (pileup entries comparable to walked loci) stay on the one-warp serial chain
+        const bool sparse_targets = (unsigned long long)E * 16ull < (unsigned long long)n_walk;
+        if (!(env_serial && env_serial[0] == '1') && ((n_walk >= (1 << 20) && sparse_targets) || env_chunk)) {
             Lc = n_walk / 512; if (Lc < 32768) Lc = 32768;
             if (env_chunk && atoll(env_chunk) >= 64) Lc = atoll(env_chunk);
             Lc = (Lc + 31) & ~(int64_t)31;
