@@ -22,7 +22,8 @@ constexpr int OVERHANG  = 4096;
 constexpr int THREADS   = 128;
 constexpr int MAX_LINES = 1024;                 // a valid SAM line has >= 22 bytes -> <= 745 per tile
 constexpr int CHUNKS    = TILE / 16;            // 16-byte chunks per tile
-constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64;
+constexpr int REFW      = 4096;                 // reference window staged per tile for the base-vs-reference comparison
+constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + REFW + 16;
 
 // tile_state word: bits 63..62 = status (0 none, 1 aggregate, 2 inclusive prefix), low 62 bits = line count
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
@@ -31,6 +32,10 @@ struct ContigNames {          // device: concatenated names + offsets, for RNAME
     const char *text;
     const uint32_t *off;      // n + 1 offsets
     int n;
+    // reference sequences (ASCII, case preserved) for the base-vs-reference comparison of kept simple reads
+    const uint8_t *const *seq; const int64_t *len;
+    // exceptional bases found while tokenising: (global line index << 16) | query offset.  The tally stage resolves them.
+    unsigned long long *exc; unsigned long long *exc_count; unsigned long long exc_cap;
 };
 
 __device__ __forceinline__ uint32_t nl_mask16(uint4 v)
@@ -144,8 +149,9 @@ __device__ int aux_ok(const Cursor &cur, size_t p, size_t q)
 // unaligned 32-bit read from shared memory; reads one aligned word past `off` (always inside the dynamic smem block)
 __device__ __forceinline__ uint32_t lds_u32(const uint8_t *text, uint32_t off)
 {
-    const uint32_t a = off & 3u;
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(text + (off - a));
+    const uint8_t *q = text + off;
+    const uint32_t a = (uint32_t)((uintptr_t)q & 3u);                // alignment of the address, not of the offset
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(q - a);
     return __funnelshift_r(p[0], p[1], a * 8);
 }
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t d)          // 0x80 in every byte of d that is zero (exact)
@@ -511,11 +517,13 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
     uint8_t  *text   = sm;                                            // TILE + OVERHANG
     uint16_t *masks  = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG);          // CHUNKS
     uint32_t *starts = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2);   // MAX_LINES (tile-relative)
+    uint8_t  *refwin = sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64;              // REFW + 16
     __shared__ unsigned int s_tile;
     __shared__ unsigned int s_warp_tot[THREADS / 32];
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_first;
     __shared__ unsigned long long s_last_end;
+    __shared__ int s_tid1, s_minpos, s_maxend;
 
     const size_t n_tiles = (n + TILE - 1) / TILE;
     const int tid_ = threadIdx.x, lane = tid_ & 31, wid = tid_ >> 5;
@@ -638,6 +646,8 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (lane == 0) s_last_end = e > n ? n : e;
         }
         __syncthreads();
+        // the first line a thread parses in this tile may take part in the base-vs-reference comparison below
+        bool elig = false; unsigned long long gi0 = 0; int32_t e_tid = -1, e_pos = 0, e_end = 0; uint32_t e_lseq = 0, e_seq = 0, e_qual = 0, e_lo = 0; bool e_qstar = false;
         for (uint32_t i = tid_; i < n_here; i += THREADS) {
             size_t s = T0 + starts[i];
             size_t e;
@@ -651,6 +661,52 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             unsigned long long gi = gbase + i;
             if (gi < rec_cap) recs[gi] = r;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
+            if (i == (uint32_t)tid_ && !rc && names.exc && gi < rec_cap && (r.bits & REC_KEEP) && (r.bits & REC_SIMPLE) && e <= stage_end &&
+                r.l_seq < 65536u && gi < (1ull << 47) && names.seq[r.tid] && (int64_t)r.end <= names.len[r.tid]) {
+                elig = true; gi0 = gi; e_tid = r.tid; e_pos = r.pos; e_end = r.end; e_lseq = r.l_seq; e_seq = r.seq_off; e_qual = r.qual_off;
+                e_lo = starts[i]; e_qstar = (r.bits & REC_QUALSTAR) != 0;
+            }
+        }
+        // 5. exceptional bases.  A base of a kept read that is not "reference base with BQ > 0" is what the per-locus tallies
+        //    are made of (stochasticSpike.c:1296-1357).  For reads whose query offsets align 1:1 to the reference they are found
+        //    here, while SEQ and QUAL sit in shared memory: the reference window under the tile's reads is staged next to them.
+        if (names.exc) {
+            if (tid_ == 0) { s_tid1 = 0; s_minpos = 0x7fffffff; s_maxend = 0; }
+            __syncthreads();
+            if (elig) atomicMax(&s_tid1, e_tid + 1);
+            __syncthreads();
+            const int wtid = s_tid1 - 1;
+            const bool in_t = elig && e_tid == wtid;
+            if (in_t) { atomicMin(&s_minpos, e_pos); atomicMax(&s_maxend, e_end); }
+            __syncthreads();
+            if (wtid >= 0) {
+                const int32_t w_lo = s_minpos;
+                int32_t w_hi = s_maxend; if (w_hi > w_lo + REFW) w_hi = w_lo + REFW;
+                const uint8_t *ref = names.seq[wtid] + w_lo;
+                const uint32_t ra = (uint32_t)((uintptr_t)ref & 3u);
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(ref - ra);
+                uint32_t *dw = reinterpret_cast<uint32_t *>(refwin);
+                const int nwords = (w_hi - w_lo + 3) >> 2;
+                for (int w = tid_; w < nwords; w += THREADS) dw[w] = __funnelshift_r(__ldg(rw + w), __ldg(rw + w + 1), ra * 8);
+                __syncthreads();
+                if (in_t && e_end <= w_lo + REFW) {
+                    const uint8_t *L = text + e_lo;
+                    const uint32_t roff = (uint32_t)(e_pos - w_lo);
+                    for (uint32_t w = 0; w < e_lseq; w += 4) {
+                        const uint32_t sq = lds_u32(L, e_seq + w), refw = lds_u32(refwin, roff + w);
+                        const uint32_t ql = e_qstar ? 0x7e7e7e7eu : lds_u32(L, e_qual + w);
+                        uint32_t exc = (~zero_bytes(sq ^ refw) | zero_bytes(ql ^ 0x21212121u)) & 0x80808080u;
+                        const uint32_t rem = e_lseq - w;
+                        if (rem < 4) exc &= (1u << (8 * rem)) - 1u;
+                        while (exc) {
+                            const int k = (__ffs(exc) - 1) >> 3; exc &= exc - 1;
+                            const unsigned long long slot = atomicAdd(names.exc_count, 1ull);
+                            if (slot < names.exc_cap) names.exc[slot] = (gi0 << 16) | (w + k);
+                        }
+                    }
+                    recs[gi0].bits |= REC_EXC_DONE;               // this thread wrote the record above
+                }
+            }
         }
     }
 }

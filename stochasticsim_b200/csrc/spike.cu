@@ -25,6 +25,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
+#include <time.h>
 
 namespace {
 
@@ -538,6 +539,7 @@ struct TallyArgs {
     const CovRun *runs; size_t R; const uint8_t *const *contig_seq; const int64_t *contig_len;
     unsigned long long *err64; unsigned int *minus; DevErr *err;
     const OddPatch *odd; const unsigned int *n_odd; const unsigned long long *odd_bloom;
+    int listed_only;          // 1: the tokeniser's exception list is in use; fast reads it did not cover take the generic kernel
 };
 
 // what entry `self` (index into members) adds at locus x, given the same-name reads that cover x in file order:
@@ -590,6 +592,19 @@ __device__ __forceinline__ bool tally_is_fast(const TallyArgs &A, size_t o, cons
     if (p != PRV_NONE && !tally_simple_read(A, p, n_odd, bloom)) return false;
     if (q != NO_MATE && !tally_simple_read(A, q, n_odd, bloom)) return false;
     (void)r;
+    return true;
+}
+
+// List mode: a read is settled from the tokeniser's exception list iff it is fast-eligible, the tokeniser listed its own
+// exceptional bases, and it listed those of its mate-chain neighbours too (a plain base only changes its contribution when a
+// neighbour's base over the same position is exceptional, and that entry is what triggers the re-evaluation).  Every other
+// read is self-contained work of tally_kernel.
+__device__ __forceinline__ bool tally_is_listed(const TallyArgs &A, size_t o, const SamRec &r, unsigned int n_odd, unsigned long long bloom)
+{
+    if (!(r.bits & REC_EXC_DONE) || !tally_is_fast(A, o, r, n_odd, bloom)) return false;
+    const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
+    if (p != PRV_NONE && !(A.recs[A.k_rec[p]].bits & REC_EXC_DONE)) return false;
+    if (q != NO_MATE && !(A.recs[A.k_rec[q]].bits & REC_EXC_DONE)) return false;
     return true;
 }
 
@@ -688,6 +703,45 @@ tally_fast_kernel(TallyArgs A, const KMeta *__restrict__ km)
     }
 }
 
+// One thread per exceptional base listed by the tokeniser: the base itself, and any mate lying over the same position
+// whose own base is plain (so it has no entry of its own) but which this base may have marked handled.
+__global__ void __launch_bounds__(128)
+tally_resolve_kernel(TallyArgs A, const unsigned long long *__restrict__ list, unsigned long long n_list, const uint32_t *__restrict__ keep,
+                     const uint32_t *__restrict__ kord)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    const unsigned long long e = list[i];
+    const size_t line = (size_t)(e >> 16);
+    if (!keep[line]) return;
+    const uint32_t o = kord[line];
+    const SamRec &r = A.recs[A.k_rec[o]];
+    const unsigned int n_odd = *A.n_odd; const unsigned long long bloom = *A.odd_bloom;
+    const bool own = tally_is_listed(A, o, r, n_odd, bloom);           // else the read itself is tally_kernel's work
+    const int32_t x = r.pos + (int32_t)(e & 0xffff);
+    size_t ri; { size_t lo = 0, hi = A.R; while (hi - lo > 1) { size_t mid = (lo + hi) >> 1;
+                   bool le = A.runs[mid].tid < r.tid || (A.runs[mid].tid == r.tid && A.runs[mid].start <= r.pos); if (le) lo = mid; else hi = mid; } ri = lo; }
+    const int64_t g = A.runs[ri].base + (x - A.runs[ri].start);
+    if (A.cplx[o]) return;                                             // three or more same-name reads overlap: all of them are tally_kernel's
+    ReadView mem[3]; uint32_t ords[3]; int n = 0, self = 0;
+    const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
+    if (p != PRV_NONE && (uint32_t)A.k_end[p] > (uint32_t)r.pos) { ords[n] = p; mem[n++] = view_of(A.sam, A.recs[A.k_rec[p]], p, NULL, 0, 0); }
+    self = n; ords[n] = o; mem[n++] = view_of(A.sam, r, o, NULL, 0, 0);
+    if (q != NO_MATE) { ords[n] = q; mem[n++] = view_of(A.sam, A.recs[A.k_rec[q]], q, NULL, 0, 0); }
+    ReadView cov[3]; uint32_t cord[3]; int nc = 0, sc = 0;
+    for (int m = 0; m < n; m++) if (mem[m].pos <= x && x < mem[m].end) { if (m == self) sc = nc; cord[nc] = ords[m]; cov[nc++] = mem[m]; }
+    const uint8_t F = A.contig_seq[r.tid][x];
+    if (own) tally_add(A, g, chain_contribution(cov, nc, sc, x, F));
+    for (int m = 0; m < nc; m++) {
+        if (m == sc) continue;
+        if (!(A.recs[A.k_rec[cord[m]]].bits & REC_SIMPLE)) continue;      // a neighbour with indels is never list-settled
+        uint8_t b; int bq; bool sk;
+        base_at(cov[m], x, b, bq, sk);
+        // a plain base of a list-settled neighbour has no entry of its own: it matters only if it was marked handled here
+        if (b == F && bq != 0 && tally_is_listed(A, cord[m], A.recs[A.k_rec[cord[m]]], n_odd, bloom)) tally_add(A, g, chain_contribution(cov, nc, m, x, F));
+    }
+}
+
 __global__ void __launch_bounds__(128)
 tally_kernel(TallyArgs A)
 {
@@ -695,7 +749,7 @@ tally_kernel(TallyArgs A)
     if (o >= A.K) return;
     const SamRec &r = A.recs[A.k_rec[o]];
     const unsigned int n_odd = *A.n_odd; const unsigned long long bloom = *A.odd_bloom;
-    if (tally_is_fast(A, o, r, n_odd, bloom)) return;                  // done by tally_fast_kernel
+    if (A.listed_only ? tally_is_listed(A, o, r, n_odd, bloom) : tally_is_fast(A, o, r, n_odd, bloom)) return;   // settled by tally_resolve_kernel / tally_fast_kernel
     const ReadView me = view_of(A.sam, r, (uint32_t)o, A.odd, n_odd, bloom);
     const int tid = r.tid;
     const uint8_t *ref = A.contig_seq[tid];
@@ -838,7 +892,7 @@ extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_c
         off.push_back((uint32_t)names.size());
         uint8_t *d = NULL;
         if (contigs[i].seq && contigs[i].len > 0) {
-            SSB_CUDA(ctx, cudaMalloc(&d, (size_t)contigs[i].len));
+            SSB_CUDA(ctx, cudaMalloc(&d, (size_t)contigs[i].len + 64));
             SSB_CUDA(ctx, cudaMemcpy(d, contigs[i].seq, (size_t)contigs[i].len, cudaMemcpyHostToDevice));
         }
         sp->d_seqs.push_back(d); ptrs.push_back(d); lens.push_back(d ? contigs[i].len : 0);
@@ -948,6 +1002,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     cudaStream_t s = ctx->stream;
     memset(stats, 0, sizeof *stats);
     *out_bytes = 0;
+    const bool dbg_t = getenv("SSB_CHAIN_DEBUG") != NULL;
+    const bool dbg_sync = dbg_t && getenv("SSB_CHAIN_DEBUG")[0] == '1';
+    auto dbg_mark = [&](const char *what) { if (dbg_t) { if (dbg_sync) cudaStreamSynchronize(s); struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); fprintf(stderr, "[tally] %-12s %.3f ms\n", what, ts.tv_sec * 1e3 + ts.tv_nsec / 1e6); } };
+
     if (sp->d_se) { cudaFreeAsync(sp->d_se, ctx->stream); sp->d_se = NULL; }
     sp->n_se = 0;
     stats->in_bytes = (int64_t)n;
@@ -969,6 +1027,8 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     // ---------------------------------------------------------------- parse
     size_t N = 0;
     SamRec *recs = NULL;
+    unsigned long long *exc_list = NULL, *d_exc_count = NULL, exc_cap = 0;
+    uint32_t *keep = NULL, *kord = NULL;
     if (n) {
         const size_t n_tiles = (n + samparse::TILE - 1) / samparse::TILE;
         unsigned long long *tile_state = ar.get<unsigned long long>(n_tiles);
@@ -976,6 +1036,8 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         unsigned long long *d_nlines = ar.get<unsigned long long>(1);
         SPK_CHECK_ARENA(ar);
         size_t rec_cap = n / 96 + 4096;
+        exc_cap = n / 96 + 65536;
+        exc_list = ar.get<unsigned long long>(exc_cap); d_exc_count = ar.get<unsigned long long>(1); SPK_CHECK_ARENA(ar);
         SSB_CUDA(ctx, cudaFuncSetAttribute(samparse::parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, samparse::SMEM_BYTES));
         for (int attempt = 0; attempt < 2; attempt++) {
             recs = ar.get<SamRec>(rec_cap); SPK_CHECK_ARENA(ar);
@@ -983,7 +1045,9 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             SSB_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
             SSB_CUDA(ctx, cudaMemsetAsync(d_nlines, 0, sizeof(unsigned long long), s));
             SSB_CUDA(ctx, cudaMemsetAsync(d_err, 0, sizeof(DevErr), s));
-            samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs};
+            SSB_CUDA(ctx, cudaMemsetAsync(d_exc_count, 0, sizeof(unsigned long long), s));
+            samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_lens,
+                                        getenv("SSB_NO_EXC_LIST") ? NULL : exc_list, d_exc_count, exc_cap};
             int grid = (int)(n_tiles < (size_t)ctx->sm_count * 8 ? n_tiles : (size_t)ctx->sm_count * 8);
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_PARSE, samparse::parse_kernel, grid, samparse::THREADS, samparse::SMEM_BYTES, s,
                          d_sam, n, names, recs, rec_cap, tile_state, ticket, d_nlines, reinterpret_cast<SpikeErr *>(d_err));
@@ -1009,7 +1073,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     SSB_CUDA(ctx, cudaMemsetAsync(d_maxspan, 0, sizeof(unsigned int), s));
     SSB_CUDA(ctx, cudaMemsetAsync(d_maxdepth, 0, sizeof(unsigned int), s));
     if (N) {
-        uint32_t *keep = ar.get<uint32_t>(N), *kord = ar.get<uint32_t>(N);
+        keep = ar.get<uint32_t>(N); kord = ar.get<uint32_t>(N);
         unsigned long long *pkey = ar.get<unsigned long long>(N), *pmax = ar.get<unsigned long long>(N);
         SPK_CHECK_ARENA(ar);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, flags_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, pkey);
@@ -1139,6 +1203,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     stats->n_hits = (int64_t)H;
     SSB_CUDA(ctx, cudaEventRecord(ev[6], s));
 
+    dbg_mark("targets");
     // ---------------------------------------------------------------- gather + rng + chain + patch
     if (H) {
         int rc;
@@ -1164,6 +1229,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         if ((rc = dev_error(ctx, s, d_err, "reference"))) return rc;
         SSB_CUDA(ctx, cudaEventRecord(ev[7], s));
 
+        dbg_mark("gathered");
         uint32_t seedw[61];
         glibc_seed_window(seed, seedw);
         uint32_t *d_seedw = ar.get<uint32_t>(61); SPK_CHECK_ARENA(ar);
@@ -1300,6 +1366,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             stats->chain_mode = parallel ? P : 1;
             break;
         }
+        dbg_mark("chain-end");
         stats->ms_rng = ms_rng; stats->ms_chain = ms_chain;
         unsigned long long draws = 0;
         SSB_CUDA(ctx, cudaMemcpyAsync(&draws, d_draws, 8, cudaMemcpyDeviceToHost, s));
@@ -1307,10 +1374,12 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, odd_fix_kernel, 4, 128, 0, s, d_odd, d_nodd, odd_cap, patches, n_patches, recs, k_rec, ord_off, d_out);
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         stats->rng_draws = (int64_t)draws;
+        dbg_mark("patched");
     } else {
         SSB_CUDA(ctx, cudaEventRecord(ev[7], s));
         SSB_CUDA(ctx, cudaEventRecord(ev[10], s));
     }
+    dbg_mark("begin");
     if (n_cov) {
         int rc;
         // per-locus tallies of the non-target loci (SEQ_ERROR lines)
@@ -1318,6 +1387,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SPK_CHECK_ARENA(ar);
         SSB_CUDA(ctx, cudaMemsetAsync(err64, 0, ((size_t)n_cov + 1) * sizeof(unsigned long long), s));
         SSB_CUDA(ctx, cudaMemsetAsync(minus, 0, ((size_t)n_cov + 1) * sizeof(unsigned int), s));
+        dbg_mark("memset");
         unsigned int h_maxspan = 0;
         SSB_CUDA(ctx, cudaMemcpyAsync(&h_maxspan, d_maxspan, 4, cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
@@ -1326,10 +1396,21 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         TA.nxt = nxt; TA.prv = prv; TA.cplx = cplx; TA.maxspan = h_maxspan; TA.runs = runs; TA.R = R;
         TA.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; TA.contig_len = sp->d_lens; TA.err64 = err64; TA.minus = minus; TA.err = d_err;
         TA.odd = d_odd; TA.n_odd = d_nodd; TA.odd_bloom = d_bloom;
-        KMeta *kmeta = ar.get<KMeta>(K); SPK_CHECK_ARENA(ar);
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, kmeta_kernel, grid_for(K, 256), 256, 0, s, recs, k_rec, K, kmeta);
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_fast_kernel, grid_for(K * 32, 128), 128, 0, s, TA, kmeta);
+        // exceptional bases of the simple reads: listed by the tokeniser (unless the list overflowed or is switched off)
+        unsigned long long n_list = 0;
+        if (d_exc_count) { SSB_CUDA(ctx, cudaMemcpyAsync(&n_list, d_exc_count, 8, cudaMemcpyDeviceToHost, s)); SSB_CUDA(ctx, cudaStreamSynchronize(s)); }
+        const bool use_list = d_exc_count && !getenv("SSB_NO_EXC_LIST") && n_list <= exc_cap;
+        TA.listed_only = use_list ? 1 : 0;
+        if (use_list) {
+            if (n_list) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_resolve_kernel, grid_for((size_t)n_list, 128), 128, 0, s, TA, exc_list, n_list, keep, kord);
+        } else {
+            KMeta *kmeta = ar.get<KMeta>(K); SPK_CHECK_ARENA(ar);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, kmeta_kernel, grid_for(K, 256), 256, 0, s, recs, k_rec, K, kmeta);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_fast_kernel, grid_for(K * 32, 128), 128, 0, s, TA, kmeta);
+        }
+        dbg_mark("resolve");
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_kernel, grid_for(K, 128), 128, 0, s, TA);
+        dbg_mark("generic");
         if ((rc = dev_error(ctx, s, d_err, "reference"))) return rc;
         if (H) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_clear_hits_kernel, grid_for(H, 256), 256, 0, s, hits, H, err64);
         uint32_t *sflag = ar.get<uint32_t>((size_t)n_cov), *sidx = ar.get<uint32_t>((size_t)n_cov);
@@ -1340,6 +1421,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaMemcpyAsync(&li, sidx + n_cov - 1, 4, cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaMemcpyAsync(&lf, sflag + n_cov - 1, 4, cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
+        dbg_mark("flag+scan");
         sp->n_se = (size_t)li + lf;
         if (sp->n_se) {
             SSB_CUDA(ctx, cudaMallocAsync((void **)&sp->d_se, sp->n_se * sizeof(ssb_seq_error), s));
@@ -1347,6 +1429,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
                          k_start, s_end, K, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_se);
         }
     }
+    dbg_mark("emit");
     SSB_CUDA(ctx, cudaEventRecord(ev[11], s));
     if (T && n_cov) SSB_CUDA(ctx, cudaMemcpyAsync(results, d_res, T * sizeof(ssb_target_result), cudaMemcpyDeviceToHost, s));
     unsigned long long fold = 0; unsigned int md = 0;
