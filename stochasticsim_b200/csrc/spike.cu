@@ -1249,7 +1249,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         // passes, so dense deep panels (pileup entries comparable to walked loci) stay on the one-warp serial chain
         const bool sparse_targets = (unsigned long long)E * 16ull < (unsigned long long)n_walk;
         if (!(env_serial && env_serial[0] == '1') && ((n_walk >= (1 << 20) && sparse_targets) || env_chunk)) {
-            Lc = n_walk / 512; if (Lc < 32768) Lc = 32768;
+            Lc = n_walk / 1024; if (Lc < 32768) Lc = 32768;
             if (env_chunk && atoll(env_chunk) >= 64) Lc = atoll(env_chunk);
             Lc = (Lc + 31) & ~(int64_t)31;
             P = (int)((n_walk + Lc - 1) / Lc);
@@ -1266,11 +1266,13 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         std::vector<ChunkWin> h_win(P);
         std::vector<ChunkDesc> h_chunks(P);
-        double cm = 0, cv = 0; unsigned long long woff = 0, wmax = 0;
+        double cm = 0, cv = 0; unsigned long long woff = 0, wmax = 0; uint32_t max_ewords = 0;
         for (int j = 0; j < P; j++) {
             const double half = j == 0 ? 0.0 : 5.0 * sqrt(cv) + 48.0;        // +-5 sigma: a miss (3e-7 per chunk) falls back to the serial chain
             double lo = cm - half; if (lo < 0) lo = 0;
-            h_win[j].klo = (unsigned long long)lo; h_win[j].W = j == 0 ? 1u : (uint32_t)(cm + half - (double)h_win[j].klo) + 2u; h_win[j].pad = 0;
+            h_win[j].klo = (unsigned long long)lo; h_win[j].W = j == 0 ? 1u : (uint32_t)(cm + half - (double)h_win[j].klo) + 2u;
+            // draw words staged in shared memory: the window, the chunk's expected draws and 8 sigma of the chunk on top
+            { const double span = (double)h_win[j].W + h_mean[j] + 8.0 * sqrt(h_var[j]) + 2048.0; h_win[j].ewords = (uint32_t)(span / 32.0) + 4u; if (h_win[j].ewords > max_ewords) max_ewords = h_win[j].ewords; }
             h_win[j].off = woff; woff += h_win[j].W; if (h_win[j].W > wmax) wmax = h_win[j].W;
             h_chunks[j].g0 = (int64_t)j * Lc; h_chunks[j].g1 = (int64_t)(j + 1) * Lc < n_walk ? (int64_t)(j + 1) * Lc : n_walk;
             h_chunks[j].k_in = 0; h_chunks[j].k_out = ~0ull;
@@ -1328,7 +1330,11 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             if (parallel) {
                 unsigned long long *d_dbg = NULL;
                 if (getenv("SSB_CHAIN_DEBUG")) { d_dbg = ar.get<unsigned long long>(4); SPK_CHECK_ARENA(ar); SSB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, 32, s)); }
-                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, P, P1_THREADS, 0, s, A, Lc, d_win, kbuf, lobuf, woff, d_ncls, d_flags, d_dbg);
+                const size_t p1_smem = (3 * (size_t)max_ewords + 3 * ((size_t)(Lc >> 5) + 2)) * sizeof(uint32_t);
+                if (p1_smem > 200 * 1024) { parallel = false; if ((rc = reset_apply())) return rc; }     // chunk planes would not fit: serial chain
+                else {
+                SSB_CUDA(ctx, cudaFuncSetAttribute(phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem));
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, P, P1_THREADS, p1_smem, s, A, Lc, d_win, kbuf, lobuf, woff, d_ncls, d_flags, d_dbg);
                 if (d_dbg) {
                     unsigned long long h_dbg[4];
                     SSB_CUDA(ctx, cudaMemcpyAsync(h_dbg, d_dbg, 32, cudaMemcpyDeviceToHost, s));
@@ -1336,6 +1342,9 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
                     fprintf(stderr, "[chain] P=%d L=%lld walkers=%llu walker-loci=%llu rounds=%llu final survivors: sum %llu max %llu\n", P, (long long)Lc, woff, h_dbg[0], h_dbg[3], h_dbg[1], h_dbg[2]);
                 }
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, P, d_win, kbuf, lobuf, d_ncls, d_chunks, d_flags);
+                }
+            }
+            if (parallel) {
                 SSB_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
                 SSB_CUDA(ctx, cudaStreamSynchronize(s));
                 if (!flags) {

@@ -350,20 +350,56 @@ __device__ __forceinline__ size_t first_hit_at_or_after(const HitTarget *hits, s
 }
 
 // walk [g, g_to) including the targets inside, counting draws only
-__device__ int dry_walk(const ChainArgs &A, int64_t g, const int64_t g_to, size_t h, unsigned long long &k)
+// The chunk's bit planes staged in shared memory: draws [kb, kb + 32*we_n), loci [gb, gb + 32*wc_n).
+struct SmemPlanes { const uint32_t *e0, *e1, *ej, *c0, *c1, *cx; unsigned long long kb; int64_t gb; uint32_t we_n; };
+
+// walk_loci on the staged planes: 32-bit cursors relative to the chunk, plain shared-memory loads, no re-basing.
+// Returns 0, or CHAIN_COMPLEX when a walker leaves the staged draw range (the caller falls back to the serial chain).
+__device__ __forceinline__ int walk_smem(const SmemPlanes &P, uint32_t &gr, const uint32_t gto, uint32_t &kr)
 {
-    while (h < A.H && A.hits[h].locus_index < g_to) {
-        const int64_t gt = A.hits[h].locus_index;
-        if (!walk_loci<false>(A, g, gt, k)) return CHAIN_OVERRUN;
-        const int rc = dry_apply(A, h, gt, k);
-        if (rc) return rc;
-        g = gt + 1; h++;
+    while (gr < gto) {
+        const uint32_t a = kr & 31u, b = gr & 31u, we = kr >> 5, wc = gr >> 5;
+        if (we + 1 >= P.we_n) return CHAIN_COMPLEX;
+        const uint32_t e0 = P.e0[we] >> a, e1 = P.e1[we] >> a, ej = P.ej[we] >> a;
+        const uint32_t c0 = P.c0[wc] >> b, c1 = P.c1[wc] >> b, cx = P.cx[wc] >> b;
+        const uint32_t n = min(min(32u - a, 32u - b), gto - gr);
+        const uint32_t term = ((e0 ^ c0) | (e1 ^ c1) | cx) & ~ej;
+        const uint32_t t = (uint32_t)__ffs(~term) - 1u;
+        if (t >= n) { gr += n; kr += n; continue; }
+        gr += t; kr += t;
+        const uint32_t m0 = 0u - ((c0 >> t) & 1u), m1 = 0u - ((c1 >> t) & 1u), mx = 0u - ((cx >> t) & 1u);
+        for (;;) {
+            const uint32_t w = kr >> 5;
+            if (w + 1 >= P.we_n) return CHAIN_COMPLEX;
+            const uint32_t ends = (((P.e0[w] ^ m0) | (P.e1[w] ^ m1) | mx) & ~P.ej[w]) >> (kr & 31u);
+            if (ends == 0u) { kr = (kr | 31u) + 1u; continue; }
+            kr += (uint32_t)__ffs(ends);
+            break;
+        }
+        gr += 1;
     }
-    if (!walk_loci<false>(A, g, g_to, k)) return CHAIN_OVERRUN;
     return 0;
 }
 
-struct ChunkWin { unsigned long long klo; uint32_t W; uint32_t pad; unsigned long long off; };   // start offsets klo .. klo+W-1; off = slot in the walker buffers
+// walk [g, g_to) including the targets inside, counting draws only
+__device__ int dry_walk(const ChainArgs &A, const SmemPlanes &P, int64_t g, const int64_t g_to, size_t h, unsigned long long &k)
+{
+    uint32_t gr = (uint32_t)(g - P.gb), kr = (uint32_t)(k - P.kb);
+    int rc = 0;
+    while (h < A.H && A.hits[h].locus_index < g_to) {
+        const int64_t gt = A.hits[h].locus_index;
+        if ((rc = walk_smem(P, gr, (uint32_t)(gt - P.gb), kr))) return rc;
+        k = P.kb + kr;
+        if ((rc = dry_apply(A, h, gt, k))) return rc;
+        if (k - P.kb >= ((unsigned long long)P.we_n << 5)) return CHAIN_COMPLEX;
+        kr = (uint32_t)(k - P.kb); gr = (uint32_t)(gt + 1 - P.gb); h++;
+    }
+    if ((rc = walk_smem(P, gr, (uint32_t)(g_to - P.gb), kr))) return rc;
+    k = P.kb + kr;
+    return 0;
+}
+
+struct ChunkWin { unsigned long long klo; uint32_t W; uint32_t ewords; unsigned long long off; };   // start offsets klo .. klo+W-1; off = slot in the walker buffers
 
 constexpr int P1_THREADS = 256;
 
@@ -378,6 +414,17 @@ phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned
     const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const ChunkWin cw = win[j];
     const int64_t g0 = (int64_t)j * L, g1 = (g0 + L < A.n_walk) ? g0 + L : A.n_walk;
+    // stage the bit planes this chunk can touch (L is a multiple of 32, so g0 is word aligned)
+    extern __shared__ uint32_t p1_smem[];
+    const uint32_t wc_n = (uint32_t)((g1 - g0 + 31) >> 5) + 1u, we_n = cw.ewords;
+    uint32_t *se0 = p1_smem, *se1 = se0 + we_n, *sej = se1 + we_n, *sc0 = sej + we_n, *sc1 = sc0 + wc_n, *scx = sc1 + wc_n;
+    {
+        const size_t ew0 = (size_t)(cw.klo >> 5), cw0 = (size_t)(g0 >> 5);
+        for (uint32_t i = tid; i < we_n; i += P1_THREADS) { se0[i] = A.e0[ew0 + i]; se1[i] = A.e1[ew0 + i]; sej[i] = A.ej[ew0 + i]; }
+        for (uint32_t i = tid; i < wc_n; i += P1_THREADS) { sc0[i] = A.c0[cw0 + i]; sc1[i] = A.c1[cw0 + i]; scx[i] = A.cx[cw0 + i]; }
+    }
+    SmemPlanes SP; SP.e0 = se0; SP.e1 = se1; SP.ej = sej; SP.c0 = sc0; SP.c1 = sc1; SP.cx = scx;
+    SP.kb = cw.klo & ~31ull; SP.gb = g0; SP.we_n = we_n;
     unsigned long long *kb[2] = {kbuf + cw.off, kbuf + stride + cw.off};
     uint32_t *lb[2] = {lobuf + cw.off, lobuf + stride + cw.off};
     uint32_t alive = cw.W;
@@ -393,7 +440,7 @@ phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned
         if (dbg && tid == 0) { atomicAdd(&dbg[0], (unsigned long long)alive * (unsigned long long)(gc - g)); atomicAdd(&dbg[3], 1ull); }
         for (uint32_t i = tid; i < alive; i += P1_THREADS) {
             unsigned long long k = kb[cur][i];
-            bad |= dry_walk(A, g, gc, h0, k);
+            bad |= dry_walk(A, SP, g, gc, h0, k);
             kb[cur][i] = k;
         }
         if (bad) atomicOr(&s_bad, bad);
@@ -415,7 +462,7 @@ phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned
             __syncthreads();
         }
         alive = total; cur ^= 1;
-        g = gc; step *= 4;
+        g = gc; step *= 2;
         __syncthreads();
     }
     if (cur != 0) {                                    // results always in half 0
