@@ -49,9 +49,9 @@ __host__ __device__ inline int ref_code(uint8_t c) { return c == 'A' ? 0 : c == 
 
 // ---- scan kernel ------------------------------------------------------------------------------
 // Every thread takes 16 bytes per iteration.  Fast path (all bytes of the chunk and of its 2-byte halo are one of
-// A C G T '\n', verified exactly with one PRMT table lookup per word): bytes become 3-bit symbols
-// ((b >> 1) & 3 for the bases, bit 2 set for '\n'), and the 4-mers that start at every second position go into a
-// 4096-bin shared-memory histogram -- one shared atomic per two windows.  When the block is done the histogram is
+// A C G T '\n', verified exactly with one PRMT table lookup per word): bytes become 3-bit symbols ((b >> 1) & 7:
+// A 0, C 1, T 2, G 3, '\n' 5), and the 4-mers that start at every second position are binned base 6 (one integer dot
+// product) into a 1296-bin shared-memory histogram -- one shared atomic per two windows.  When the block is done the histogram is
 // folded: bin (s0,s1,s2,s3) feeds window (s0,s1,s2) and window (s1,s2,s3) when their symbols are bases.
 // Anything else in a chunk (N, lower case, '>', '\r', the ragged end of the piece) takes the generic path, which
 // looks at every position.  Newlines are not handled where they are found (that would make every warp execute the
@@ -64,18 +64,19 @@ constexpr int NLQ_CAP = 128;                      // >= 31 left over + 32 lanes 
 
 __device__ __forceinline__ uint32_t zero_bytes_mask(uint32_t d) { return ~(((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d | 0x7f7f7f7fu); }
 
-// non-zero iff some byte of w is not one of A C G T '\n'   (low three bits 1 3 7 4 2 select the only candidate)
-__device__ __forceinline__ uint32_t not_acgtnl(uint32_t w)
+// Symbols: s = (byte >> 1) & 7 is distinct for the five bytes that matter -- A 0, C 1, T 2, G 3, '\n' 5 -- so it serves both as
+// the 3-bit symbol and as the key of the exactness check: a byte is one of the five iff it equals TABLE[s].
+__device__ __forceinline__ uint32_t symbols(uint32_t w) { return (w >> 1) & 0x07070707u; }
+// non-zero iff some byte of w is not one of A C G T '\n' (sy = symbols(w))
+__device__ __forceinline__ uint32_t not_acgtnl(uint32_t w, uint32_t sy)
 {
-    const uint32_t TLO = 0x430A4101u, THI = 0x47010154u;      // idx 0->01 1->'A' 2->'\n' 3->'C' | 4->'T' 5->01 6->01 7->'G'
-    const uint32_t sidx = w & 0x07070707u;
-    const uint32_t e0 = __byte_perm(TLO, THI, sidx), e1 = __byte_perm(TLO, THI, sidx >> 16);
+    const uint32_t TLO = 0x47544341u, THI = 0x01010A01u;      // key 0->'A' 1->'C' 2->'T' 3->'G' | 4->01 5->'\n' 6->01 7->01
+    const uint32_t e0 = __byte_perm(TLO, THI, sy), e1 = __byte_perm(TLO, THI, sy >> 16);
     return w ^ __byte_perm(e0, e1, 0x6420);
 }
-// 3-bit symbols of four bytes known to be A C G T or '\n':  A0 C1 T2 G3, bit 2 set for '\n'
-__device__ __forceinline__ uint32_t symbols(uint32_t w) { return ((w >> 1) & 0x03030303u) | ((~w >> 4) & 0x04040404u); }
-// symbols [a,b,c,d] (one per byte) -> 12-bit bin a | b<<3 | c<<6 | d<<9
-__device__ __forceinline__ uint32_t pack4(uint32_t z) { const uint32_t t = z | (z >> 5); return (t & 0x3Fu) | ((t >> 10) & 0xFC0u); }
+// four symbols [a,b,c,d] (one per byte, each 0..5) -> base-6 bin a + 6b + 36c + 216d: one integer dot product
+__device__ __forceinline__ uint32_t pack4(uint32_t z) { return __dp4a(z, 0xD8240601u, 0u); }
+constexpr int TNC_BINS = 1296;
 
 __device__ __forceinline__ uint32_t ld_word(const uint8_t *b, size_t n, size_t off)
 {
@@ -108,11 +109,11 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
                 unsigned long long *__restrict__ counts, uint32_t *__restrict__ exc_count,
                 uint32_t *__restrict__ exc, uint32_t exc_cap, uint32_t *__restrict__ seg_nobase)
 {
-    __shared__ uint32_t hist4[4096];
+    __shared__ uint32_t hist4[TNC_BINS];
     __shared__ uint32_t hist3[64];
     __shared__ uint32_t nlq[TNC_WARPS][NLQ_CAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 4096; i += TNC_BLOCK) hist4[i] = 0;
+    for (int i = threadIdx.x; i < TNC_BINS; i += TNC_BLOCK) hist4[i] = 0;
     if (threadIdx.x < 64) hist3[threadIdx.x] = 0;
     __syncthreads();
     TncDevState st = *st_in;
@@ -144,22 +145,19 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
             uint32_t hw;                                                               // the 4 bytes before the chunk
             if (p0) hw = *reinterpret_cast<const uint32_t *>(b + p0 - 4);
             else hw = (uint32_t)st.prev[0] << 8 | (uint32_t)st.prev[1] << 16 | (uint32_t)st.prev[2] << 24;
-            const uint32_t bad = not_acgtnl(w[0]) | not_acgtnl(w[1]) | not_acgtnl(w[2]) | not_acgtnl(w[3]) | (not_acgtnl(hw) & 0xFFFF0000u);
+            const uint32_t s0 = symbols(w[0]), s1 = symbols(w[1]), s2 = symbols(w[2]), s3 = symbols(w[3]), sh = symbols(hw);
+            const uint32_t bad = not_acgtnl(w[0], s0) | not_acgtnl(w[1], s1) | not_acgtnl(w[2], s2) | not_acgtnl(w[3], s3) | (not_acgtnl(hw, sh) & 0xFFFF0000u);
             if (bad == 0u && p0 + TNC_BPT <= n) {
                 // ---- fast path ----
-                uint32_t prev = symbols(hw), f0, f1, f2, f3;
-                {
-                    const uint32_t s0 = symbols(w[0]), s1 = symbols(w[1]), s2 = symbols(w[2]), s3 = symbols(w[3]);
-                    atomicAdd(&hist4[pack4(__funnelshift_r(prev, s0, 16))], 1u);     // windows ending at 0, 1
-                    atomicAdd(&hist4[pack4(s0)], 1u);                                // windows ending at 2, 3
-                    atomicAdd(&hist4[pack4(__funnelshift_r(s0, s1, 16))], 1u);
-                    atomicAdd(&hist4[pack4(s1)], 1u);
-                    atomicAdd(&hist4[pack4(__funnelshift_r(s1, s2, 16))], 1u);
-                    atomicAdd(&hist4[pack4(s2)], 1u);
-                    atomicAdd(&hist4[pack4(__funnelshift_r(s2, s3, 16))], 1u);
-                    atomicAdd(&hist4[pack4(s3)], 1u);
-                    f0 = s0 & 0x04040404u; f1 = s1 & 0x04040404u; f2 = s2 & 0x04040404u; f3 = s3 & 0x04040404u;
-                }
+                atomicAdd(&hist4[pack4(__funnelshift_r(sh, s0, 16))], 1u);       // windows ending at 0, 1
+                atomicAdd(&hist4[pack4(s0)], 1u);                                // windows ending at 2, 3
+                atomicAdd(&hist4[pack4(__funnelshift_r(s0, s1, 16))], 1u);
+                atomicAdd(&hist4[pack4(s1)], 1u);
+                atomicAdd(&hist4[pack4(__funnelshift_r(s1, s2, 16))], 1u);
+                atomicAdd(&hist4[pack4(s2)], 1u);
+                atomicAdd(&hist4[pack4(__funnelshift_r(s2, s3, 16))], 1u);
+                atomicAdd(&hist4[pack4(s3)], 1u);
+                const uint32_t f0 = s0 & 0x04040404u, f1 = s1 & 0x04040404u, f2 = s2 & 0x04040404u, f3 = s3 & 0x04040404u;   // symbol 5 = newline
                 if (f0 | f1 | f2 | f3) {                                             // a newline in these 16 bytes (one chunk in four)
                     nlmask = ((((f0 >> 2) * 0x00204081u) >> 21) & 0xFu) | (((((f1 >> 2) * 0x00204081u) >> 21) & 0xFu) << 4) |
                              (((((f2 >> 2) * 0x00204081u) >> 21) & 0xFu) << 8) | (((((f3 >> 2) * 0x00204081u) >> 21) & 0xFu) << 12);
@@ -174,7 +172,7 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
                 uint32_t bf[4], nf[4], anyb = 0, anyn = 0;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint32_t z = zero_bytes_mask(not_acgtnl(w[j]));           // 0x80 where the byte is A C G T or newline
+                    const uint32_t z = zero_bytes_mask(not_acgtnl(w[j], symbols(w[j])));   // 0x80 where the byte is A C G T or newline
                     bf[j] = z & (w[j] << 1);                                        // bit 6 set: a base
                     nf[j] = z & ~(w[j] << 1);
                     anyb |= bf[j]; anyn |= nf[j];
@@ -239,14 +237,14 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
     if ((uint32_t)lane < qn) handle_newline(b, (long)n, st, (long)q[lane], hist3, exc_count, exc, exc_cap);
     __syncthreads();
     // ---- fold the 4-mer histogram into the 64 contexts (reference index order A<C<G<T) ----
-    for (int bin = threadIdx.x; bin < 4096; bin += TNC_BLOCK) {
+    for (int bin = threadIdx.x; bin < TNC_BINS; bin += TNC_BLOCK) {
         const uint32_t v = hist4[bin];
         if (!v) continue;
-        const uint32_t s0 = bin & 7, s1 = (bin >> 3) & 7, s2 = (bin >> 6) & 7, s3 = (bin >> 9) & 7;
+        const uint32_t s0 = bin % 6, s1 = (bin / 6) % 6, s2 = (bin / 36) % 6, s3 = bin / 216;
         // symbol -> reference code: A0 C1 T2 G3 -> A0 C1 G2 T3
         const uint32_t r0 = s0 ^ (s0 >> 1), r1 = s1 ^ (s1 >> 1), r2 = s2 ^ (s2 >> 1), r3 = s3 ^ (s3 >> 1);
-        if ((s0 | s1 | s2) < 4) atomicAdd(&hist3[16 * r0 + 4 * r1 + r2], v);
-        if ((s1 | s2 | s3) < 4) atomicAdd(&hist3[16 * r1 + 4 * r2 + r3], v);
+        if (s0 < 4 && s1 < 4 && s2 < 4) atomicAdd(&hist3[16 * r0 + 4 * r1 + r2], v);
+        if (s1 < 4 && s2 < 4 && s3 < 4) atomicAdd(&hist3[16 * r1 + 4 * r2 + r3], v);
     }
     __syncthreads();
     if (threadIdx.x < 64 && hist3[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)hist3[threadIdx.x]);
@@ -480,7 +478,7 @@ int tnc_piece(ssb_ctx *ctx, cudaStream_t stream, const uint8_t *d, size_t n, con
     SSB_CUDA(ctx, cudaMemsetAsync(s.seg, 0, ((n >> TNC_SEG_SHIFT) + 2) * sizeof(uint32_t), stream));
     size_t n_chunks = (n + TNC_BPT - 1) / TNC_BPT;
     int grid = (int)((n_chunks + (size_t)TNC_BLOCK * TNC_SUB - 1) / ((size_t)TNC_BLOCK * TNC_SUB));
-    int max_grid = ctx->sm_count * 8;            // persistent: every block folds its 4096-bin histogram once
+    int max_grid = ctx->sm_count * 8;            // persistent: every block folds its 1296-bin histogram once
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
     SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, s.acc, s.exc_count, s.exc, s.exc_cap, s.seg);
