@@ -184,11 +184,16 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
                 }
                 if (!anyb) atomicAdd(&seg_nobase[p0 >> TNC_SEG_SHIFT], 1u);
                 else {
+                    // base flags of positions -2 .. 15 as a bit mask (bit i+2 <-> position i); a window ends where three in a row are set
+                    const uint32_t hz = zero_bytes_mask(not_acgtnl(hw, symbols(hw))) & (hw << 1);
+                    uint32_t bm = ((((hz >> 7) * 0x00204081u) >> 21) & 0xFu) >> 2;                   // positions -2, -1 -> bits 0, 1
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        if (p0 + i >= n) break;
-                        const uint8_t x = c[i + 1], y = c[i + 2], z = c[i + 3];
-                        if (is_base(z) && is_base(x) && is_base(y)) atomicAdd(&hist3[16 * ref_code(x) + 4 * ref_code(y) + ref_code(z)], 1u);
+                    for (int j = 0; j < 4; j++) bm |= ((((bf[j] >> 7) * 0x00204081u) >> 21) & 0xFu) << (2 + 4 * j);
+                    uint32_t win = bm & (bm >> 1) & (bm >> 2);                                        // bit i: window ending at position i
+                    if (p0 + TNC_BPT > n) win &= (1u << (n - p0)) - 1u;
+                    while (win) {
+                        const int i = __ffs(win) - 1; win &= win - 1;
+                        atomicAdd(&hist3[16 * ref_code(c[i + 1]) + 4 * ref_code(c[i + 2]) + ref_code(c[i + 3])], 1u);
                     }
                 }
             }
