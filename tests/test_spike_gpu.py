@@ -121,6 +121,31 @@ def test_bam_input(name, tmp_path, ctx):
     assert strip(got[3]) == strip(want[3]), first_diff(strip(want[3]), strip(got[3]))
 
 
+@pytest.mark.parametrize("k", range(8))
+def test_fuzz_configs(k, tmp_path, ctx, monkeypatch):
+    """Seeded random generator settings (depth, read/fragment geometry, error mix, contigs, spike density), alternating
+    the chain mode: SAM, truth.vcf and stats must match the oracle byte for byte."""
+    import random
+    rng = random.Random(1000 + k)
+    rl = rng.choice([36, 50, 76, 100, 151])
+    args = dict(seed=2000 + k, contigs=rng.choice(["c1:9000", "chrA:6000,chrB:5000", "chr1:4000,chr2:4000,chr3:3000"]),
+                coverage=rng.choice([3, 12, 40, 150]), read_len=rl, frag_mean=int(rl * rng.choice([1.05, 1.4, 2.2, 3.0])), frag_sd=rng.choice([3, 15, 40]),
+                sub=rng.choice([0.0, 0.002, 0.03]), indel=rng.choice([0.0, 0.01, 0.08]), nrate=rng.choice([0.0, 0.005]), q0=rng.choice([0.0, 0.02]),
+                softclip=rng.choice([0.0, 0.1]), refskip=rng.choice([0.0, 0.04]), filt=rng.choice([0.0, 0.1]), lower=rng.choice([0.0, 0.2]),
+                spikes=rng.choice([5, 60, 400]), alt_mode=rng.choice([0, 1]), aux=rng.choice([0, 1]), af=rng.choice(["0.01:0.5", "0.3:1.0", "0.001:0.02"]))
+    prefix = sc.generate("plain", str(tmp_path), **args)
+    if k % 2:
+        monkeypatch.setenv("SSB_CHAIN_CHUNK", str(rng.choice([96, 320, 1024])))
+    if k % 3 == 0:
+        monkeypatch.setenv("SSB_NO_EXC_LIST", "1")
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), seed=434 + k, cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"), seed=434 + k)
+    assert want[0] == 0 and got[0] == 0, got[4]
+    assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
+    assert got[1] == want[1]
+    assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
+
+
 def test_golden_fixture(tmp_path, ctx):
     """tests/golden/spike_toy was produced by the unmodified reference over the htslib shim."""
     for f in ("in.sam", "in.fa", "in.spike"):
