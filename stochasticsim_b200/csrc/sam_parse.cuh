@@ -23,7 +23,8 @@ constexpr int THREADS   = 128;
 constexpr int MAX_LINES = 1024;                 // a valid SAM line has >= 22 bytes -> <= 745 per tile
 constexpr int CHUNKS    = TILE / 16;            // 16-byte chunks per tile
 constexpr int REFW      = 4096;                 // reference window staged per tile for the base-vs-reference comparison
-constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + REFW + 16;
+constexpr int EXC_BUF   = 1024;                 // exceptional bases of one tile, kept in shared memory until the tile is done
+constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + 16 + REFW + 32 + EXC_BUF * 4;
 
 // tile_state word: bits 63..62 = status (0 none, 1 aggregate, 2 inclusive prefix), low 62 bits = line count
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
@@ -508,6 +509,178 @@ __device__ int parse_line_smem(const Cursor &cur, const uint8_t *L, uint32_t len
     return 0;
 }
 
+// ---- the common shape of a line, parsed so that the lanes of a warp stay together ----
+//
+// parse_line_smem() leaves a loop the moment it meets a byte it does not like; with those exits inside the loops the
+// lanes of a warp no longer reconverge after a field whose length differs from lane to lane, and everything behind it --
+// SEQ, QUAL, the comparison with the reference -- runs a few lanes at a time.  The functions below accept exactly the
+// lines of the common shape (mapped RNAME, a CIGAR, RNEXT '=' or '*', SEQ of the CIGAR's query length) and collect
+// every objection in one flag instead of leaving; a line that raises the flag is handed to parse_line_smem(), which
+// decides.  Every loop has one exit, and the lanes meet again (__syncwarp) after each field.
+
+__device__ __forceinline__ uint32_t udec_conv(const uint8_t *L, uint32_t &p, uint32_t len, uint32_t maxv, uint32_t &out)
+{
+    const uint32_t p0 = p; uint32_t v = 0, bad = 0;
+    while (p < len) {
+        const uint32_t c = L[p];
+        if (c == '\t') break;
+        const uint32_t d = c - '0';
+        bad |= (uint32_t)(d > 9u) | (uint32_t)(v > 214748364u) | (uint32_t)(v == 214748364u && d > 7u);
+        v = v * 10u + d;
+        p++;
+    }
+    bad |= (uint32_t)(p >= len) | (uint32_t)(p == p0) | (uint32_t)(p - p0 > 10u) | (uint32_t)(v > maxv);
+    bad |= (uint32_t)(p - p0 > 1u && L[p0] == '0');
+    out = v;
+    return bad;
+}
+
+// QNAME .. QUAL bounds of the line [L, L+len).  Returns 0 when the line has the common shape and its head is valid; then
+// r holds everything but the verdict on the SEQ / QUAL / optional-field bytes, and qend is the end of QUAL.
+__device__ __forceinline__ uint32_t parse_head_conv(const Cursor &cur, const uint8_t *L, uint32_t len, size_t s, bool has_nl,
+                                                    const ContigNames &names, int tid_cache, SamRec &r, uint32_t &qend, unsigned mask)
+{
+    uint32_t p = 0, v = 0, bad = 0;
+    r.line_off = s;
+    r.line_len = len + (has_nl ? 1u : 0u);
+    r.bits = has_nl ? 0 : REC_NO_NL;
+    for (int k = 0; k < 6; k++) r.pad[k] = 0;
+    uint32_t h1 = 2166136261u, h2 = 0x9747b28cu;
+    while (p < len) { const uint32_t c = L[p]; if (c == '\t') break; bad |= (uint32_t)(c - '!' > (uint32_t)('~' - '!')); h1 = (h1 ^ c) * 16777619u; h2 = (h2 + c) * 0x85ebca6bu; p++; }
+    bad |= (uint32_t)(p >= len) | (uint32_t)(p == 0) | (uint32_t)(p > 254u);
+    r.qhash = ((uint64_t)h1 << 32) | (h2 ^ (h2 >> 15)); r.qname_len = (uint16_t)p;
+    p++;
+    __syncwarp(mask);
+    bad |= udec_conv(L, p, len, 65535u, v);
+    r.flag = (uint16_t)v; p++;
+    __syncwarp(mask);
+    uint32_t p0 = p;
+    while (p < len && L[p] != '\t') p++;
+    bad |= (uint32_t)(p >= len) | (uint32_t)(p == p0);
+    __syncwarp(mask);
+    r.tid = -1;
+    if (!bad && !(p - p0 == 1 && L[p0] == '*')) r.tid = name_lookup(cur, s + p0, p - p0, names, tid_cache);
+    bad |= (uint32_t)(r.tid < 0);
+    p++;
+    __syncwarp(mask);
+    bad |= udec_conv(L, p, len, 0x7fffffffu, v);
+    r.pos = (int32_t)v - 1; p++;
+    bad |= udec_conv(L, p, len, 255u, v);
+    r.mapq = (uint8_t)v; p++;
+    __syncwarp(mask);
+    p0 = p;
+    uint32_t rlen = 0, qlen = 0, num = 0, nd = 0, first = 0; bool simple = true;
+    while (p < len) {
+        const uint32_t c = L[p];
+        if (c == '\t') break;
+        const uint32_t d = c - '0';
+        if (d <= 9u) { if (!nd) first = c; num = num * 10u + d; nd++; bad |= (uint32_t)(nd > 9u) | (uint32_t)(num > 0x0fffffffu); }
+        else {
+            bad |= (uint32_t)(!nd) | (uint32_t)(nd > 1u && first == '0');
+            const bool m = c == 'M' || c == '=' || c == 'X', dn = c == 'D' || c == 'N', is = c == 'I' || c == 'S', hp = c == 'H' || c == 'P';
+            if (m || dn) rlen += num;
+            if (m || is) qlen += num;
+            if (!m) simple = false;
+            bad |= (uint32_t)(!(m || dn || is || hp)) | (uint32_t)(rlen > 0x7ffffff0u) | (uint32_t)(qlen > 0x7ffffff0u);
+            num = 0; nd = 0;
+        }
+        p++;
+    }
+    bad |= (uint32_t)(nd != 0) | (uint32_t)(p >= len) | (uint32_t)(p == p0) | (uint32_t)(p - p0 > 65535u) | (uint32_t)(p0 > 65535u);
+    if (simple) r.bits |= REC_SIMPLE;
+    r.cigar_off = (uint16_t)p0; r.cigar_len = (uint16_t)(p - p0);
+    bad |= (uint32_t)(r.pos < 0 && rlen) | (uint32_t)((uint64_t)(r.pos < 0 ? 0 : r.pos) + rlen > 0x7ffffff0ull);
+    r.end = r.pos + (int32_t)rlen;
+    p++;
+    __syncwarp(mask);
+    p0 = p;
+    while (p < len && L[p] != '\t') p++;
+    bad |= (uint32_t)(p >= len) | (uint32_t)(p - p0 != 1u);
+    if (!bad) bad |= (uint32_t)(L[p0] != '=' && L[p0] != '*');
+    p++;
+    __syncwarp(mask);
+    bad |= udec_conv(L, p, len, 0x7fffffffu, v);
+    p++;
+    if (p < len && L[p] == '-') { p++; bad |= (uint32_t)(p < len && L[p] == '0'); }
+    bad |= udec_conv(L, p, len, 0x7fffffffu, v);
+    p++;
+    __syncwarp(mask);
+    r.seq_off = p; r.l_seq = qlen;
+    bad |= (uint32_t)(qlen == 0) | (uint32_t)(p >= len) | (uint32_t)((uint64_t)p + qlen >= len);
+    if (!bad) bad |= (uint32_t)(L[p + qlen] != '\t');
+    p += qlen + 1;
+    r.qual_off = p;
+    bad |= (uint32_t)(p >= len);
+    qend = p;
+    if (!bad) {
+        if (L[p] == '*' && (p + 1 == len || L[p + 1] == '\t')) { r.bits |= REC_QUALSTAR; qend = p + 1; }
+        else { qend = p + qlen; bad |= (uint32_t)(qend > len); if (!bad && qend < len) bad |= (uint32_t)(L[qend] != '\t'); }
+    }
+    const bool pass = !(r.flag & (4 | 256 | 512 | 1024)) && r.mapq >= 30 && !((r.flag & 1) && !(r.flag & 2));
+    if (pass && r.end > r.pos) r.bits |= REC_PUSHED | REC_KEEP; else if (pass) r.bits |= REC_PUSHED;
+    return bad;
+}
+
+// SEQ and QUAL of one line in a single pass over aligned SEQ words (QUAL, and the reference under the read, are shifted
+// into place).  CMP: the read aligns 1:1 to the staged reference window `ref` (bytes that are not A/C/G/T/N replaced by
+// 0xff there, so "equal to the reference" implies "valid SEQ byte"); every base that differs from the reference or has
+// BQ 0 goes to the tile's exception buffer.  Returns nonzero if a byte is outside what htslib prints back unchanged.
+template <bool CMP>
+__device__ __forceinline__ uint32_t long_fields(const uint8_t *L, uint32_t seq_off, uint32_t l_seq, uint32_t qual_off, bool qstar,
+                                                const uint8_t *ref, const uint8_t *ref_raw, uint32_t line_in_tile, unsigned long long gi,
+                                                uint32_t *excbuf, unsigned int *s_nexc, const ContigNames &names)
+{
+    const uint8_t *As = L + seq_off;
+    const uint32_t sh = (uint32_t)((uintptr_t)As & 3u);
+    const uint32_t *Ws = reinterpret_cast<const uint32_t *>(As - sh);
+    const uint32_t nw = (sh + l_seq + 3u) >> 2;
+    const uint8_t *Aq = L + qual_off - sh;
+    const uint32_t shq = (uint32_t)((uintptr_t)Aq & 3u);
+    const uint32_t *Wq = reinterpret_cast<const uint32_t *>(Aq - shq);
+    uint32_t qprev = qstar ? 0u : Wq[0];
+    const uint8_t *Ar = CMP ? ref - sh : L;
+    const uint32_t shr = (uint32_t)((uintptr_t)Ar & 3u);
+    const uint32_t *Wr = reinterpret_cast<const uint32_t *>(Ar - shr);
+    uint32_t rprev = CMP ? Wr[0] : 0u;
+    const uint32_t m_first = 0x80808080u << (8 * sh);
+    const uint32_t tail = (sh + l_seq) & 3u;
+    const uint32_t m_last = tail ? (0x80808080u >> (8 * (4 - tail))) : 0x80808080u;
+    uint32_t bad = 0;
+    for (uint32_t j = 0; j < nw; j++) {
+        const uint32_t sq = Ws[j];
+        uint32_t ql = 0x7e7e7e7eu, rf = 0;
+        if (!qstar) { const uint32_t nx = Wq[j + 1]; ql = __funnelshift_r(qprev, nx, shq * 8); qprev = nx; }
+        uint32_t fl;
+        if (CMP) {
+            const uint32_t nx = Wr[j + 1]; rf = __funnelshift_r(rprev, nx, shr * 8); rprev = nx;
+            const uint32_t d = sq ^ rf;
+            fl = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d | sq) | (ql | ~(ql + 0x5e5e5e5eu) | (ql + 0x01010101u));   // differs | >= 0x80 | BQ outside '"'..'~'
+        } else fl = non_acgtn_bytes(sq) | nonprint_bytes(ql);
+        fl &= 0x80808080u;
+        if (j == 0) fl &= m_first;
+        if (j == nw - 1) fl &= m_last;
+        while (fl) {
+            const uint32_t k = (uint32_t)(__ffs(fl) - 1) >> 3; fl &= fl - 1;
+            const uint32_t sb = (sq >> (8 * k)) & 0xffu, qb = (ql >> (8 * k)) & 0xffu;
+            if (!seq_char_ok((uint8_t)sb) || qb < '!' || qb > '~') { bad = 1; continue; }
+            if (CMP) {
+                const uint32_t q = 4 * j + k - sh;
+                uint32_t rb = (rf >> (8 * k)) & 0xffu;
+                if (rb == 0xffu) rb = ref_raw[q];                          // not A/C/G/T/N: the tally compares with the byte as it is
+                if (sb != rb || qb == '!') {
+                    const unsigned int slot = atomicAdd(s_nexc, 1u);
+                    if (slot < (unsigned int)EXC_BUF) excbuf[slot] = (line_in_tile << 16) | q;
+                    else {
+                        const unsigned long long gs = atomicAdd(names.exc_count, 1ull);
+                        if (gs < names.exc_cap) names.exc[gs] = (gi << 16) | q;
+                    }
+                }
+            }
+        }
+    }
+    return bad;
+}
+
 __global__ void __launch_bounds__(THREADS)
 parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamRec *__restrict__ recs, size_t rec_cap,
              unsigned long long *__restrict__ tile_state, unsigned int *__restrict__ ticket,
@@ -517,17 +690,20 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
     uint8_t  *text   = sm;                                            // TILE + OVERHANG
     uint16_t *masks  = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG);          // CHUNKS
     uint32_t *starts = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2);   // MAX_LINES (tile-relative)
-    uint8_t  *refwin = sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64;              // REFW + 16
+    uint8_t  *refwin = sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + 16;         // REFW + 32 (16 bytes in front: words are read from 3 bytes before a read's first base)
+    uint32_t *excbuf = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + 16 + REFW + 32);   // EXC_BUF
     __shared__ unsigned int s_tile;
     __shared__ unsigned int s_warp_tot[THREADS / 32];
     __shared__ unsigned long long s_base;
     __shared__ unsigned int s_first;
     __shared__ unsigned long long s_last_end;
-    __shared__ int s_tid1, s_minpos, s_maxend;
+    __shared__ int4 s_wkey[THREADS / 32];
+    __shared__ unsigned int s_nexc;
 
     const size_t n_tiles = (n + TILE - 1) / TILE;
     const int tid_ = threadIdx.x, lane = tid_ & 31, wid = tid_ >> 5;
     int tid_cache = -1;
+    if (tid_ == 0) s_nexc = 0;
 
     for (;;) {
         __syncthreads();
@@ -646,66 +822,106 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (lane == 0) s_last_end = e > n ? n : e;
         }
         __syncthreads();
-        // the first line a thread parses in this tile may take part in the base-vs-reference comparison below
-        bool elig = false; unsigned long long gi0 = 0; int32_t e_tid = -1, e_pos = 0, e_end = 0; uint32_t e_lseq = 0, e_seq = 0, e_qual = 0, e_lo = 0; bool e_qstar = false;
-        for (uint32_t i = tid_; i < n_here; i += THREADS) {
-            size_t s = T0 + starts[i];
-            size_t e;
-            if (i + 1 < n_here) e = T0 + starts[i + 1] - 1;
-            else e = s_last_end;
-            SamRec r;
-            int rc;
-            if (e <= stage_end && e - s < 0x40000000ull) rc = parse_line_smem(cur, text + (s - T0), (uint32_t)(e - s), s, e < n, names, tid_cache, r);
-            else rc = parse_line(cur, s, e, names, tid_cache, r);
-            if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = s; memset(&r, 0, sizeof r); r.line_off = s; r.tid = -1; }
-            unsigned long long gi = gbase + i;
-            if (gi < rec_cap) recs[gi] = r;
-            else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
-            if (i == (uint32_t)tid_ && !rc && names.exc && gi < rec_cap && (r.bits & REC_KEEP) && (r.bits & REC_SIMPLE) && e <= stage_end &&
-                r.l_seq < 65536u && gi < (1ull << 47) && names.seq[r.tid] && (int64_t)r.end <= names.len[r.tid]) {
-                elig = true; gi0 = gi; e_tid = r.tid; e_pos = r.pos; e_end = r.end; e_lseq = r.l_seq; e_seq = r.seq_off; e_qual = r.qual_off;
-                e_lo = starts[i]; e_qstar = (r.bits & REC_QUALSTAR) != 0;
-            }
+        // 4a. heads.  Thread t takes line t of the tile; the lanes of a warp stay together (parse_head_conv).  A line that is
+        //     not of the common shape, or does not end inside the staged window, is parsed by the careful functions at once.
+        const uint32_t li = (uint32_t)tid_;
+        const bool have = li < n_here;
+        const unsigned wmask = __ballot_sync(0xffffffffu, have);
+        SamRec r; int rc = 0; bool fast = false; uint32_t qend = 0, lo = 0, len = 0; size_t ls = 0;
+        if (have) {
+            lo = starts[li]; ls = T0 + lo;
+            const size_t e = (li + 1 < n_here) ? T0 + starts[li + 1] - 1 : (size_t)s_last_end;
+            const bool insm = e <= stage_end && e - ls < 0x40000000ull;
+            const unsigned fmask = __ballot_sync(wmask, insm);
+            if (insm) {
+                len = (uint32_t)(e - ls);
+                fast = parse_head_conv(cur, text + lo, len, ls, e < n, names, tid_cache, r, qend, fmask) == 0;
+                if (!fast) rc = parse_line_smem(cur, text + lo, len, ls, e < n, names, tid_cache, r);
+            } else rc = parse_line(cur, ls, e, names, tid_cache, r);
+            if (!rc && r.tid >= 0) tid_cache = r.tid;
         }
-        // 5. exceptional bases.  A base of a kept read that is not "reference base with BQ > 0" is what the per-locus tallies
-        //    are made of (stochasticSpike.c:1296-1357).  For reads whose query offsets align 1:1 to the reference they are found
-        //    here, while SEQ and QUAL sit in shared memory: the reference window under the tile's reads is staged next to them.
+        const unsigned long long gi = gbase + li;
+        // the reference window under the tile's reads: lowest (tid, pos) among the reads that align 1:1
+        const bool elig = fast && names.exc && (r.bits & REC_KEEP) && (r.bits & REC_SIMPLE) && r.l_seq < 65536u && gi < rec_cap && gi < (1ull << 47) &&
+                          names.seq[r.tid] && (int64_t)r.end <= names.len[r.tid];
         if (names.exc) {
-            if (tid_ == 0) { s_tid1 = 0; s_minpos = 0x7fffffff; s_maxend = 0; }
-            __syncthreads();
-            if (elig) atomicMax(&s_tid1, e_tid + 1);
-            __syncthreads();
-            const int wtid = s_tid1 - 1;
-            const bool in_t = elig && e_tid == wtid;
-            if (in_t) { atomicMin(&s_minpos, e_pos); atomicMax(&s_maxend, e_end); }
-            __syncthreads();
-            if (wtid >= 0) {
-                const int32_t w_lo = s_minpos;
-                int32_t w_hi = s_maxend; if (w_hi > w_lo + REFW) w_hi = w_lo + REFW;
+            const int tmin = __reduce_min_sync(0xffffffffu, elig ? r.tid : 0x7fffffff);
+            const int pmin = __reduce_min_sync(0xffffffffu, (elig && r.tid == tmin) ? r.pos : 0x7fffffff);
+            const int emax = __reduce_max_sync(0xffffffffu, (elig && r.tid == tmin) ? r.end : 0);
+            if (lane == 0) s_wkey[wid] = make_int4(tmin, pmin, emax, 0);
+        }
+        __syncthreads();
+        bool in_win = false; int32_t w_lo = 0; int wtid = -1;
+        if (names.exc) {
+            int emax = 0; int pmin = 0x7fffffff; wtid = 0x7fffffff;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; w++) { const int4 k = s_wkey[w]; if (k.x < wtid) wtid = k.x; }
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; w++) { const int4 k = s_wkey[w]; if (k.x == wtid) { if (k.y < pmin) pmin = k.y; if (k.z > emax) emax = k.z; } }
+            if (wtid != 0x7fffffff) {
+                w_lo = pmin;
+                int32_t w_hi = emax; if (w_hi > w_lo + REFW) w_hi = w_lo + REFW;
                 const uint8_t *ref = names.seq[wtid] + w_lo;
                 const uint32_t ra = (uint32_t)((uintptr_t)ref & 3u);
                 const uint32_t *rw = reinterpret_cast<const uint32_t *>(ref - ra);
                 uint32_t *dw = reinterpret_cast<uint32_t *>(refwin);
-                const int nwords = (w_hi - w_lo + 3) >> 2;
-                for (int w = tid_; w < nwords; w += THREADS) dw[w] = __funnelshift_r(__ldg(rw + w), __ldg(rw + w + 1), ra * 8);
-                __syncthreads();
-                if (in_t && e_end <= w_lo + REFW) {
-                    const uint8_t *L = text + e_lo;
-                    const uint32_t roff = (uint32_t)(e_pos - w_lo);
-                    for (uint32_t w = 0; w < e_lseq; w += 4) {
-                        const uint32_t sq = lds_u32(L, e_seq + w), refw = lds_u32(refwin, roff + w);
-                        const uint32_t ql = e_qstar ? 0x7e7e7e7eu : lds_u32(L, e_qual + w);
-                        uint32_t exc = (~zero_bytes(sq ^ refw) | zero_bytes(ql ^ 0x21212121u)) & 0x80808080u;
-                        const uint32_t rem = e_lseq - w;
-                        if (rem < 4) exc &= (1u << (8 * rem)) - 1u;
-                        while (exc) {
-                            const int k = (__ffs(exc) - 1) >> 3; exc &= exc - 1;
-                            const unsigned long long slot = atomicAdd(names.exc_count, 1ull);
-                            if (slot < names.exc_cap) names.exc[slot] = (gi0 << 16) | (w + k);
-                        }
-                    }
-                    recs[gi0].bits |= REC_EXC_DONE;               // this thread wrote the record above
+                const int nwords = ((w_hi - w_lo + 3) >> 2) + 1;
+                for (int w = tid_; w < nwords; w += THREADS) {
+                    const uint32_t x = __funnelshift_r(__ldg(rw + w), __ldg(rw + w + 1), ra * 8);
+                    dw[w] = x | ((non_acgtn_bytes(x) >> 7) * 0xffu);           // anything but A C G T N can never equal a valid SEQ byte
                 }
+                in_win = elig && r.tid == wtid && r.pos >= w_lo && r.end <= w_lo + REFW;
+            } else wtid = -1;
+        }
+        __syncthreads();
+        // 4b. SEQ, QUAL (and the reference under the read) in one pass; optional fields; the record
+        if (have) {
+            if (fast) {
+                const uint8_t *L = text + lo;
+                const bool qstar = (r.bits & REC_QUALSTAR) != 0;
+                uint32_t bad;
+                if (in_win) {
+                    bad = long_fields<true>(L, r.seq_off, r.l_seq, r.qual_off, qstar, refwin + (r.pos - w_lo), names.seq[wtid] + r.pos, li, gi, excbuf, &s_nexc, names);
+                    r.bits |= REC_EXC_DONE;
+                } else bad = long_fields<false>(L, r.seq_off, r.l_seq, r.qual_off, qstar, NULL, NULL, li, gi, excbuf, &s_nexc, names);
+                for (size_t q = ls + qend; q < ls + len;) {
+                    size_t a = q + 1, b = a;
+                    while (b < ls + len && cur.at(b) != '\t') b++;
+                    if (aux_ok(cur, a, b)) bad = 1;
+                    q = b;
+                }
+                if (bad) rc = SSB_E_FORMAT;
+            }
+            if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = ls; memset(&r, 0, sizeof r); r.line_off = ls; r.tid = -1; }
+            if (gi < rec_cap) recs[gi] = r;
+            else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = ls;
+        }
+        // tiles of very short lines: the lines beyond the first THREADS take the careful path, one per thread
+        for (uint32_t i = tid_ + THREADS; i < n_here; i += THREADS) {
+            const size_t s = T0 + starts[i];
+            const size_t e = (i + 1 < n_here) ? T0 + starts[i + 1] - 1 : (size_t)s_last_end;
+            SamRec r2; int rc2;
+            if (e <= stage_end && e - s < 0x40000000ull) rc2 = parse_line_smem(cur, text + (s - T0), (uint32_t)(e - s), s, e < n, names, tid_cache, r2);
+            else rc2 = parse_line(cur, s, e, names, tid_cache, r2);
+            if (rc2) { if (atomicCAS(&err->code, 0, rc2) == 0) err->where = s; memset(&r2, 0, sizeof r2); r2.line_off = s; r2.tid = -1; }
+            const unsigned long long g2 = gbase + i;
+            if (g2 < rec_cap) recs[g2] = r2;
+            else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
+        }
+        // 5. hand the tile's exceptional bases over: one reservation per tile, coalesced stores
+        if (names.exc) {
+            __syncthreads();
+            if (wid == 0) {
+                unsigned int cnt = s_nexc; if (cnt > (unsigned int)EXC_BUF) cnt = EXC_BUF;
+                unsigned long long slot = 0;
+                if (lane == 0 && cnt) slot = atomicAdd(names.exc_count, (unsigned long long)cnt);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                for (unsigned int k = lane; k < cnt; k += 32) {
+                    const uint32_t v = excbuf[k];
+                    if (slot + k < names.exc_cap) names.exc[slot + k] = ((gbase + (v >> 16)) << 16) | (v & 0xffffu);
+                }
+                __syncwarp();
+                if (lane == 0) s_nexc = 0;
             }
         }
     }
