@@ -1264,35 +1264,54 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaMemcpyAsync(h_mean.data(), d_mean, P * sizeof(double), cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaMemcpyAsync(h_var.data(), d_var, P * sizeof(double), cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
-        std::vector<ChunkWin> h_win(P);
+        // groups of Rg consecutive chunks share one start-offset window; the window is cut into slices of ~wt offsets
+        int Rg = 2; uint32_t wt = 16384;
+        if (const char *e = getenv("SSB_CHAIN_GROUP")) { if (atoi(e) >= 1) Rg = atoi(e); }
+        if (const char *e = getenv("SSB_CHAIN_SLICE")) { if (atoi(e) >= 1) wt = (uint32_t)atoi(e); }
+        const int G = (P + Rg - 1) / Rg;
+        std::vector<GroupDesc> h_groups(G);
+        std::vector<SliceDesc> h_slices;
         std::vector<ChunkDesc> h_chunks(P);
-        double cm = 0, cv = 0; unsigned long long woff = 0, wmax = 0; uint32_t max_ewords = 0;
-        for (int j = 0; j < P; j++) {
-            const double half = j == 0 ? 0.0 : 5.0 * sqrt(cv) + 48.0;        // +-5 sigma: a miss (3e-7 per chunk) falls back to the serial chain
+        double cm = 0, cv = 0; unsigned long long woff = 0;
+        for (int q = 0; q < G; q++) {
+            GroupDesc &gd = h_groups[q];
+            gd.f0 = q * Rg; gd.nf = (gd.f0 + Rg <= P) ? Rg : P - gd.f0;
+            const double half = q == 0 ? 0.0 : 5.0 * sqrt(cv) + 48.0;        // +-5 sigma: a miss (3e-7 per group) falls back to the serial chain
             double lo = cm - half; if (lo < 0) lo = 0;
-            h_win[j].klo = (unsigned long long)lo; h_win[j].W = j == 0 ? 1u : (uint32_t)(cm + half - (double)h_win[j].klo) + 2u;
-            // draw words staged in shared memory: the window, the chunk's expected draws and 8 sigma of the chunk on top
-            { const double span = (double)h_win[j].W + h_mean[j] + 8.0 * sqrt(h_var[j]) + 2048.0; h_win[j].ewords = (uint32_t)(span / 32.0) + 4u; if (h_win[j].ewords > max_ewords) max_ewords = h_win[j].ewords; }
-            h_win[j].off = woff; woff += h_win[j].W; if (h_win[j].W > wmax) wmax = h_win[j].W;
-            h_chunks[j].g0 = (int64_t)j * Lc; h_chunks[j].g1 = (int64_t)(j + 1) * Lc < n_walk ? (int64_t)(j + 1) * Lc : n_walk;
-            h_chunks[j].k_in = 0; h_chunks[j].k_out = ~0ull;
-            cm += h_mean[j]; cv += h_var[j];
+            gd.klo = (unsigned long long)lo; gd.W = q == 0 ? 1u : (uint32_t)(cm + half - (double)gd.klo) + 2u;
+            uint32_t S = (gd.W + wt - 1) / wt; gd.w = (gd.W + S - 1) / S; S = (gd.W + gd.w - 1) / gd.w;
+            gd.S = S; gd.b0 = (uint32_t)h_slices.size();
+            for (uint32_t sl = 0; sl < S; sl++) {
+                SliceDesc sd; sd.q = q; sd.i0 = sl * gd.w; sd.n = (sd.i0 + gd.w <= gd.W) ? gd.w : gd.W - sd.i0; sd.off = woff; woff += sd.n;
+                h_slices.push_back(sd);
+            }
+            for (int f = gd.f0; f < gd.f0 + gd.nf; f++) {
+                h_chunks[f].g0 = (int64_t)f * Lc; h_chunks[f].g1 = (int64_t)(f + 1) * Lc < n_walk ? (int64_t)(f + 1) * Lc : n_walk;
+                h_chunks[f].k_in = 0; h_chunks[f].k_out = ~0ull;
+                cm += h_mean[f]; cv += h_var[f];
+            }
         }
+        const size_t n_slices = h_slices.size();
+        const unsigned long long pool_cap = woff + (1ull << 20);
         // the stream must cover the top of the last window (and everything a lone walker can reach)
         unsigned long long M = (unsigned long long)(cm + 8.0 * sqrt(cv)) + 3 * E + (1u << 17);
         float ms_rng = 0, ms_chain = 0;
         unsigned int *d_flags = ar.get<unsigned int>(1);
-        ChunkWin *d_win = ar.get<ChunkWin>((size_t)P); ChunkDesc *d_chunks = ar.get<ChunkDesc>((size_t)P), *d_serial = ar.get<ChunkDesc>(1);
-        uint32_t *d_ncls = ar.get<uint32_t>((size_t)P);
-        unsigned long long *kbuf = NULL; uint32_t *lobuf = NULL;
-        if (P > 1) { kbuf = ar.get<unsigned long long>(2 * woff); lobuf = ar.get<uint32_t>(2 * woff); }
+        ChunkDesc *d_chunks = ar.get<ChunkDesc>((size_t)P), *d_serial = ar.get<ChunkDesc>(1);
+        GroupDesc *d_groups = ar.get<GroupDesc>((size_t)G); SliceDesc *d_slices = ar.get<SliceDesc>(n_slices);
+        BoundaryList *d_lists = ar.get<BoundaryList>(n_slices * (size_t)Rg);
+        unsigned long long *d_gk = ar.get<unsigned long long>((size_t)G), *d_pool_used = ar.get<unsigned long long>(1);
+        unsigned long long *kbuf = NULL, *pool_k = NULL; uint32_t *lobuf = NULL, *pool_lo = NULL;
+        if (P > 1) { kbuf = ar.get<unsigned long long>(2 * woff); lobuf = ar.get<uint32_t>(2 * woff); pool_k = ar.get<unsigned long long>(pool_cap); pool_lo = ar.get<uint32_t>(pool_cap); }
         SPK_CHECK_ARENA(ar);
-        SSB_CUDA(ctx, cudaMemcpyAsync(d_win, h_win.data(), P * sizeof(ChunkWin), cudaMemcpyHostToDevice, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_groups, h_groups.data(), G * sizeof(GroupDesc), cudaMemcpyHostToDevice, s));
+        SSB_CUDA(ctx, cudaMemcpyAsync(d_slices, h_slices.data(), n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, s));
         SSB_CUDA(ctx, cudaMemcpyAsync(d_chunks, h_chunks.data(), P * sizeof(ChunkDesc), cudaMemcpyHostToDevice, s));
         ChunkDesc serial_cd; serial_cd.g0 = 0; serial_cd.g1 = n_walk; serial_cd.k_in = 0; serial_cd.k_out = ~0ull;
         SSB_CUDA(ctx, cudaMemcpyAsync(d_serial, &serial_cd, sizeof serial_cd, cudaMemcpyHostToDevice, s));
         bool parallel = P > 1;
         stats->n_runs = (int64_t)R;
+        bool chain_done = false;
         for (int attempt = 0; attempt < 8; attempt++) {
             M = (M + RNG_BLOCK - 1) / RNG_BLOCK * RNG_BLOCK;
             const size_t nblocks = (size_t)(M / RNG_BLOCK);
@@ -1330,29 +1349,32 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             if (parallel) {
                 unsigned long long *d_dbg = NULL;
                 if (getenv("SSB_CHAIN_DEBUG")) { d_dbg = ar.get<unsigned long long>(4); SPK_CHECK_ARENA(ar); SSB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, 32, s)); }
-                const size_t p1_smem = (3 * (size_t)max_ewords + 3 * ((size_t)(Lc >> 5) + 2)) * sizeof(uint32_t);
-                if (p1_smem > 200 * 1024) { parallel = false; if ((rc = reset_apply())) return rc; }     // chunk planes would not fit: serial chain
-                else {
-                SSB_CUDA(ctx, cudaFuncSetAttribute(phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p1_smem));
-                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, P, P1_THREADS, p1_smem, s, A, Lc, d_win, kbuf, lobuf, woff, d_ncls, d_flags, d_dbg);
+                SSB_CUDA(ctx, cudaMemsetAsync(d_pool_used, 0, 8, s));
+                SSB_CUDA(ctx, cudaMemsetAsync(d_lists, 0, n_slices * (size_t)Rg * sizeof(BoundaryList), s));
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, (int)n_slices, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, woff,
+                             d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, d_dbg);
                 if (d_dbg) {
-                    unsigned long long h_dbg[4];
+                    unsigned long long h_dbg[4], used = 0;
                     SSB_CUDA(ctx, cudaMemcpyAsync(h_dbg, d_dbg, 32, cudaMemcpyDeviceToHost, s));
+                    SSB_CUDA(ctx, cudaMemcpyAsync(&used, d_pool_used, 8, cudaMemcpyDeviceToHost, s));
                     SSB_CUDA(ctx, cudaStreamSynchronize(s));
-                    fprintf(stderr, "[chain] P=%d L=%lld walkers=%llu walker-loci=%llu rounds=%llu final survivors: sum %llu max %llu\n", P, (long long)Lc, woff, h_dbg[0], h_dbg[3], h_dbg[1], h_dbg[2]);
+                    fprintf(stderr, "[chain] chunks=%d L=%lld groups=%d slices=%zu walkers=%llu walker-loci=%llu rounds=%llu final survivors: sum %llu max %llu, recorded %llu\n",
+                            P, (long long)Lc, G, n_slices, woff, h_dbg[0], h_dbg[3], h_dbg[1], h_dbg[2], used);
                 }
-                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, P, d_win, kbuf, lobuf, d_ncls, d_chunks, d_flags);
-                }
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, G, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_flags);
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, boundary_kernel, (P + 127) / 128, 128, 0, s, P, Rg, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_chunks, d_flags);
             }
             if (parallel) {
                 SSB_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
                 SSB_CUDA(ctx, cudaStreamSynchronize(s));
+                if (getenv("SSB_CHAIN_DEBUG")) fprintf(stderr, "[chain] flags after phase 1/2: %u\n", flags);
                 if (!flags) {
                     SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, grid_for((size_t)P * 32, 128), 128, 0, s, A, d_chunks, P, d_draws, d_flags);
                     SSB_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, s));
                     SSB_CUDA(ctx, cudaMemcpyAsync(&n_odd_h, d_nodd, 4, cudaMemcpyDeviceToHost, s));
                     SSB_CUDA(ctx, cudaStreamSynchronize(s));
                 }
+                if (getenv("SSB_CHAIN_DEBUG")) fprintf(stderr, "[chain] flags after phase 3: %u, odd patches %u\n", flags, n_odd_h);
                 if (flags & CHAIN_OVERRUN) { M *= 2; continue; }
                 if (flags || n_odd_h) {               // window miss / too complex / odd patches: the plain serial chain decides
                     parallel = false;
@@ -1371,10 +1393,11 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             SSB_CUDA(ctx, cudaStreamSynchronize(s));
             ms_rng += ev_ms(ev[8], ev[9]); ms_chain += ev_ms(ev[9], ev[10]);
             if (e.code) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: %s", ssb_strerror(e.code)); return e.code; }
-            if (attempt == 7 && (flags & CHAIN_OVERRUN)) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: rand() stream exhausted"); return SSB_E_STATE; }
             stats->chain_mode = parallel ? P : 1;
+            chain_done = true;
             break;
         }
+        if (!chain_done) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: rand() stream exhausted"); return SSB_E_STATE; }
         dbg_mark("chain-end");
         stats->ms_rng = ms_rng; stats->ms_chain = ms_chain;
         unsigned long long draws = 0;

@@ -13,13 +13,15 @@
 //   walk_loci     lock step of draw k+i against locus g+i on 32-bit words: term = ((e0^c0)|(e1^c1)|cx) & ~ej says
 //                 which draws end their locus; the run of trailing ones advances both cursors, a zero starts
 //                 the "repeat draw" loop of that locus.  ~4 loci per iteration.
-//   phase 1       the walk is a monotone map k_in -> k_out per chunk of loci, and walkers that meet stay
-//                 together.  Each chunk (one block) simulates EVERY start offset of a +-6 sigma window around
-//                 the expected offset (mean 4/3 draw per GCAT locus, variance 4/9) and drops duplicates at
-//                 geometrically spaced checkpoints: W walkers shrink like W/sqrt(loci), so a chunk costs
-//                 ~1.7 W sqrt(L) walker-steps instead of W L.  Targets inside a chunk are dry-run per walker.
-//   phase 2       one warp composes the chunk maps in order (a table lookup per chunk): exact start offset of
-//                 every chunk.
+//   phase 1       the walk is a monotone map k_in -> k_out per stretch of loci, and walkers that meet stay
+//                 together.  Chunks are taken in groups; for a group EVERY start offset of a +-5 sigma window
+//                 around the expected offset (mean 4/3 draw per GCAT locus, variance 4/9) is simulated, and
+//                 duplicates are dropped at geometrically spaced checkpoints: W walkers shrink like W/sqrt(loci),
+//                 so a group of length L costs ~2 W sqrt(L) walker-loci instead of W L -- the longer the group the
+//                 less work per locus.  The window is cut into slices (one block each) to keep the GPU full, and
+//                 the survivors at every chunk end inside the group are recorded.  Targets are dry-run per walker.
+//   phase 2       one warp composes the group maps in order (a table lookup per group); then every chunk looks up
+//                 its exact start offset in its group's recorded survivors.
 //   phase 3       one warp per chunk repeats the walk from its exact offset and applies the targets for real
 //                 (speculative 32-entry batches).  Exit offsets must equal the next chunk's start (checked).
 //   fallback      a window miss, an inconsistent exit, a dry-run that was too complex, or any "odd patch"
@@ -349,102 +351,143 @@ __device__ __forceinline__ size_t first_hit_at_or_after(const HitTarget *hits, s
     return lo;
 }
 
-// walk [g, g_to) including the targets inside, counting draws only
-// The chunk's bit planes staged in shared memory: draws [kb, kb + 32*we_n), loci [gb, gb + 32*wc_n).
-struct SmemPlanes { const uint32_t *e0, *e1, *ej, *c0, *c1, *cx; unsigned long long kb; int64_t gb; uint32_t we_n; };
+// ---- phase 1 on staged planes ------------------------------------------------------------------------------------
+// A block owns one SLICE of the start-offset window of one GROUP of consecutive chunks.  All its walkers stand at the
+// same locus between rounds, so a round needs only the loci [g, gc) and the draws from the lowest walker up to what the
+// highest one can reach: those are staged in shared memory, the three planes of a 32-position word side by side
+// (one 16-byte load fetches a word of each plane).
+struct SegPlanes { const uint4 *e, *c; unsigned long long kb; int64_t gb; uint32_t we_n; unsigned long long M; };
 
-// walk_loci on the staged planes: 32-bit cursors relative to the chunk, plain shared-memory loads, no re-basing.
-// Returns 0, or CHAIN_COMPLEX when a walker leaves the staged draw range (the caller falls back to the serial chain).
-__device__ __forceinline__ int walk_smem(const SmemPlanes &P, uint32_t &gr, const uint32_t gto, uint32_t &kr)
+constexpr int P1_THREADS = 128;
+constexpr int P1_SEG     = 4096;               // loci per round at most
+constexpr int P1_EW_CAP  = 1024;               // staged draw words (32768 draws)
+constexpr int P1_CW_CAP  = P1_SEG / 32 + 2;
+constexpr size_t P1_SMEM = (size_t)(P1_EW_CAP + P1_CW_CAP) * sizeof(uint4);
+
+// One step = one window of 32 draws from kr against 32 loci from gr, both shifted into place: the lock step runs to the
+// first draw that does not end its locus (z: that position, one-hot); that locus then takes the next draw of the window
+// that does (y, one-hot).  No branch and no inner loop: a lone walker is one dependency chain, so the step is kept short;
+// a locus that finds no such draw in the window simply stays the current locus of the next step.
+__device__ __forceinline__ int walk_seg(const SegPlanes &P, uint32_t &gr, const uint32_t gto, uint32_t &kr)
 {
     while (gr < gto) {
         const uint32_t a = kr & 31u, b = gr & 31u, we = kr >> 5, wc = gr >> 5;
-        if (we + 1 >= P.we_n) return CHAIN_COMPLEX;
-        const uint32_t e0 = P.e0[we] >> a, e1 = P.e1[we] >> a, ej = P.ej[we] >> a;
-        const uint32_t c0 = P.c0[wc] >> b, c1 = P.c1[wc] >> b, cx = P.cx[wc] >> b;
-        const uint32_t n = min(min(32u - a, 32u - b), gto - gr);
-        const uint32_t term = ((e0 ^ c0) | (e1 ^ c1) | cx) & ~ej;
-        const uint32_t t = (uint32_t)__ffs(~term) - 1u;
-        if (t >= n) { gr += n; kr += n; continue; }
-        gr += t; kr += t;
-        const uint32_t m0 = 0u - ((c0 >> t) & 1u), m1 = 0u - ((c1 >> t) & 1u), mx = 0u - ((cx >> t) & 1u);
-        for (;;) {
-            const uint32_t w = kr >> 5;
-            if (w + 1 >= P.we_n) return CHAIN_COMPLEX;
-            const uint32_t ends = (((P.e0[w] ^ m0) | (P.e1[w] ^ m1) | mx) & ~P.ej[w]) >> (kr & 31u);
-            if (ends == 0u) { kr = (kr | 31u) + 1u; continue; }
-            kr += (uint32_t)__ffs(ends);
-            break;
-        }
-        gr += 1;
+        if (we + 2u > P.we_n) return (P.kb + kr + 96ull > P.M) ? CHAIN_OVERRUN : CHAIN_COMPLEX;
+        const uint4 ea = P.e[we], eb = P.e[we + 1], ca = P.c[wc], cb = P.c[wc + 1];
+        const uint32_t e0 = __funnelshift_r(ea.x, eb.x, a), e1 = __funnelshift_r(ea.y, eb.y, a), ej = __funnelshift_r(ea.z, eb.z, a);
+        const uint32_t c0 = __funnelshift_r(ca.x, cb.x, b), c1 = __funnelshift_r(ca.y, cb.y, b), cx = __funnelshift_r(ca.z, cb.z, b);
+        const uint32_t n = min(32u, gto - gr);
+        const uint32_t beyond = n >= 32u ? 0u : 0xffffffffu << n;         // pairs past the end of the stretch never stop the lock step
+        const uint32_t term = (((e0 ^ c0) | (e1 ^ c1) | cx) & ~ej) | beyond;   // bit i: draw kr+i ends locus gr+i
+        const uint32_t z = ~term & (term + 1u);                            // lowest pair that does not (0: none)
+        const uint32_t m0 = (c0 & z) ? 0xffffffffu : 0u, m1 = (c1 & z) ? 0xffffffffu : 0u, mx = (cx & z) ? 0xffffffffu : 0u;
+        const uint32_t ends = ((e0 ^ m0) | (e1 ^ m1) | mx) & ~ej;           // draws of the window that would end that locus
+        const uint32_t above = ends & ~(z | (z - 1u));                     // ... after the failed one
+        const uint32_t y = above & (0u - above);                           // the first of them (0: none in this window)
+        const uint32_t t = min((uint32_t)__popc(z - 1u), n);               // loci passed in lock step
+        gr += t + (y ? 1u : 0u);
+        kr += y ? (uint32_t)__popc(y - 1u) + 1u : (z ? 32u : n);
     }
     return 0;
 }
 
 // walk [g, g_to) including the targets inside, counting draws only
-__device__ int dry_walk(const ChainArgs &A, const SmemPlanes &P, int64_t g, const int64_t g_to, size_t h, unsigned long long &k)
+__device__ int dry_walk(const ChainArgs &A, const SegPlanes &P, int64_t g, const int64_t g_to, size_t h, unsigned long long &k)
 {
+    if (k < P.kb) return CHAIN_COMPLEX;
     uint32_t gr = (uint32_t)(g - P.gb), kr = (uint32_t)(k - P.kb);
     int rc = 0;
     while (h < A.H && A.hits[h].locus_index < g_to) {
         const int64_t gt = A.hits[h].locus_index;
-        if ((rc = walk_smem(P, gr, (uint32_t)(gt - P.gb), kr))) return rc;
+        if ((rc = walk_seg(P, gr, (uint32_t)(gt - P.gb), kr))) return rc;
         k = P.kb + kr;
         if ((rc = dry_apply(A, h, gt, k))) return rc;
-        if (k - P.kb >= ((unsigned long long)P.we_n << 5)) return CHAIN_COMPLEX;
+        if (k - P.kb >= ((unsigned long long)P.we_n << 5)) return (k + 96ull > P.M) ? CHAIN_OVERRUN : CHAIN_COMPLEX;
         kr = (uint32_t)(k - P.kb); gr = (uint32_t)(gt + 1 - P.gb); h++;
     }
-    if ((rc = walk_smem(P, gr, (uint32_t)(g_to - P.gb), kr))) return rc;
+    if ((rc = walk_seg(P, gr, (uint32_t)(g_to - P.gb), kr))) return rc;
     k = P.kb + kr;
     return 0;
 }
 
-struct ChunkWin { unsigned long long klo; uint32_t W; uint32_t ewords; unsigned long long off; };   // start offsets klo .. klo+W-1; off = slot in the walker buffers
+// group q = chunks [f0, f0 + nf): one start-offset window [klo, klo + W), cut into S slices of w offsets (blocks b0 ..)
+struct GroupDesc { unsigned long long klo; uint32_t W, w, S, b0; int32_t f0, nf; };
+struct SliceDesc { int32_t q; uint32_t i0, n; unsigned long long off; };        // window indices [i0, i0 + n); walker slots at off
+// survivors of one slice at the end of one chunk: (lowest window index of the class, draw offset) pairs in `pool`
+struct BoundaryList { unsigned long long off; uint32_t cnt; uint32_t pad; };
 
-constexpr int P1_THREADS = 256;
+__device__ __forceinline__ uint32_t isqrt_up(uint32_t x) { uint32_t r = (uint32_t)sqrtf((float)x) + 1u; return r; }
 
-// One block per chunk.  kbuf/lobuf: two ping-pong halves of `stride` slots each.
-// On exit: n_cls[j] survivors, (lo, k_out) pairs in half 0 of the chunk's slots, sorted by lo.
+// One block per slice.  kbuf/lobuf: two ping-pong halves of `stride` slots each.
 __global__ void __launch_bounds__(P1_THREADS)
-phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned long long *__restrict__ kbuf, uint32_t *__restrict__ lobuf,
-              unsigned long long stride, uint32_t *__restrict__ n_cls, unsigned int *__restrict__ flags, unsigned long long *__restrict__ dbg)
+phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, const SliceDesc *__restrict__ slices,
+              unsigned long long *__restrict__ kbuf, uint32_t *__restrict__ lobuf, unsigned long long stride,
+              BoundaryList *__restrict__ lists /* [block][max_nf] */, int max_nf, unsigned long long *__restrict__ pool_k, uint32_t *__restrict__ pool_lo,
+              unsigned long long *__restrict__ pool_used, unsigned long long pool_cap, unsigned int *__restrict__ flags, unsigned long long *__restrict__ dbg)
 {
+    extern __shared__ uint4 p1_smem[];
+    uint4 *se = p1_smem, *sc = p1_smem + P1_EW_CAP;
     __shared__ uint32_t s_warp[P1_THREADS / 32];
     __shared__ int s_bad;
-    const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const ChunkWin cw = win[j];
-    const int64_t g0 = (int64_t)j * L, g1 = (g0 + L < A.n_walk) ? g0 + L : A.n_walk;
-    // stage the bit planes this chunk can touch (L is a multiple of 32, so g0 is word aligned)
-    extern __shared__ uint32_t p1_smem[];
-    const uint32_t wc_n = (uint32_t)((g1 - g0 + 31) >> 5) + 1u, we_n = cw.ewords;
-    uint32_t *se0 = p1_smem, *se1 = se0 + we_n, *sej = se1 + we_n, *sc0 = sej + we_n, *sc1 = sc0 + wc_n, *scx = sc1 + wc_n;
-    {
-        const size_t ew0 = (size_t)(cw.klo >> 5), cw0 = (size_t)(g0 >> 5);
-        for (uint32_t i = tid; i < we_n; i += P1_THREADS) { se0[i] = A.e0[ew0 + i]; se1[i] = A.e1[ew0 + i]; sej[i] = A.ej[ew0 + i]; }
-        for (uint32_t i = tid; i < wc_n; i += P1_THREADS) { sc0[i] = A.c0[cw0 + i]; sc1[i] = A.c1[cw0 + i]; scx[i] = A.cx[cw0 + i]; }
-    }
-    SmemPlanes SP; SP.e0 = se0; SP.e1 = se1; SP.ej = sej; SP.c0 = sc0; SP.c1 = sc1; SP.cx = scx;
-    SP.kb = cw.klo & ~31ull; SP.gb = g0; SP.we_n = we_n;
-    unsigned long long *kb[2] = {kbuf + cw.off, kbuf + stride + cw.off};
-    uint32_t *lb[2] = {lobuf + cw.off, lobuf + stride + cw.off};
-    uint32_t alive = cw.W;
-    for (uint32_t i = tid; i < alive; i += P1_THREADS) { kb[0][i] = cw.klo + i; lb[0][i] = i; }
-    if (tid == 0) s_bad = 0;
+    __shared__ unsigned long long s_off, s_kmin, s_kmax;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const SliceDesc sd = slices[blockIdx.x];
+    const GroupDesc gd = groups[sd.q];
+    const int64_t g0 = (int64_t)gd.f0 * L, gend = ((int64_t)(gd.f0 + gd.nf) * L < A.n_walk) ? (int64_t)(gd.f0 + gd.nf) * L : A.n_walk;
+    unsigned long long *kb[2] = {kbuf + sd.off, kbuf + stride + sd.off};
+    uint32_t *lb[2] = {lobuf + sd.off, lobuf + stride + sd.off};
+    uint32_t alive = sd.n;
+    for (uint32_t i = tid; i < alive; i += P1_THREADS) { kb[0][i] = gd.klo + sd.i0 + i; lb[0][i] = sd.i0 + i; }
+    if (tid == 0) { s_bad = 0; s_kmin = gd.klo + sd.i0; s_kmax = gd.klo + sd.i0 + sd.n - 1; }
     __syncthreads();
-    int cur = 0;
+    int cur = 0, r = 0;
     int64_t g = g0, step = 64;
-    while (g < g1) {
-        int64_t gc = g + step; if (gc > g1 || g1 - gc < step / 2) gc = g1;
+    const unsigned long long plane_words = (A.M >> 5) + 160ull;              // words the draw planes hold (padding included)
+    while (g < gend) {
+        const int64_t fine_end = (g0 + (int64_t)(r + 1) * L < gend) ? g0 + (int64_t)(r + 1) * L : gend;
+        int64_t gc = g + step; if (gc > fine_end || fine_end - gc < step / 2) gc = fine_end;
+        if (gc - g > P1_SEG) gc = g + P1_SEG;
+        const unsigned long long kmin = s_kmin, kmax = s_kmax;               // lowest / highest walker (targets can reorder walkers)
+        const unsigned long long kbase = kmin & ~31ull;
         const size_t h0 = first_hit_at_or_after(A.hits, A.H, g);
+        // draws the highest walker can reach in this round: 4/3 per locus and 8 sigma, plus the pileups of the targets inside
+        uint32_t we_n;
+        for (;;) {
+            const size_t h1 = first_hit_at_or_after(A.hits, A.H, gc);
+            const uint32_t len = (uint32_t)(gc - g);
+            const unsigned long long need = (kmax - kbase) + (unsigned long long)len + len / 3u + 8ull * isqrt_up(len) + 3ull * (A.eoff[h1] - A.eoff[h0]) + 64ull * (h1 - h0) + 192ull;
+            const unsigned long long w = (need >> 5) + 3ull;
+            if (w <= (unsigned long long)P1_EW_CAP) { we_n = (uint32_t)w; break; }
+            if (gc - g <= 64) { if (tid == 0) atomicOr(flags, (unsigned int)CHAIN_COMPLEX); return; }     // the slice itself does not fit
+            gc = g + (((gc - g) / 2 + 31) & ~(int64_t)31);
+        }
+        {
+            const unsigned long long ew0 = kbase >> 5; const size_t cw0 = (size_t)(g >> 5);
+            const uint32_t wc_n = (uint32_t)((gc - g + 31) >> 5) + 2u;
+            for (uint32_t i = tid; i < we_n; i += P1_THREADS) {
+                uint4 v;
+                if (ew0 + i < plane_words) { v.x = A.e0[ew0 + i]; v.y = A.e1[ew0 + i]; v.z = A.ej[ew0 + i]; }
+                else { v.x = 0xAAAAAAAAu; v.y = 0xCCCCCCCCu; v.z = 0u; }
+                v.w = 0; se[i] = v;
+            }
+            for (uint32_t i = tid; i < wc_n; i += P1_THREADS) { uint4 v; v.x = A.c0[cw0 + i]; v.y = A.c1[cw0 + i]; v.z = A.cx[cw0 + i]; v.w = 0; sc[i] = v; }
+        }
+        __syncthreads();
+        SegPlanes SP; SP.e = se; SP.c = sc; SP.kb = kbase; SP.gb = g & ~(int64_t)31; SP.we_n = we_n; SP.M = A.M;
         int bad = 0;
         if (dbg && tid == 0) { atomicAdd(&dbg[0], (unsigned long long)alive * (unsigned long long)(gc - g)); atomicAdd(&dbg[3], 1ull); }
+        if (tid == 0) { s_kmin = ~0ull; s_kmax = 0ull; }                    // every thread has read them; the barrier above orders this
+        unsigned long long tmin = ~0ull, tmax = 0ull;
         for (uint32_t i = tid; i < alive; i += P1_THREADS) {
             unsigned long long k = kb[cur][i];
             bad |= dry_walk(A, SP, g, gc, h0, k);
             kb[cur][i] = k;
+            if (k < tmin) tmin = k;
+            if (k > tmax) tmax = k;
         }
         if (bad) atomicOr(&s_bad, bad);
         __syncthreads();
+        if (tmin != ~0ull) { atomicMin(&s_kmin, tmin); atomicMax(&s_kmax, tmax); }
         if (s_bad) { if (tid == 0) atomicOr(flags, (unsigned int)s_bad); return; }
         // drop walkers that met their left neighbour (they stay together from here on); order is kept
         uint32_t total = 0;
@@ -462,40 +505,81 @@ phase1_kernel(ChainArgs A, int64_t L, const ChunkWin *__restrict__ win, unsigned
             __syncthreads();
         }
         alive = total; cur ^= 1;
-        g = gc; step *= 2;
+        g = gc; if (step < P1_SEG) step *= 2;
+        if (g == fine_end) {                              // end of chunk f0 + r: the survivors are that boundary's map
+            if (tid == 0) s_off = atomicAdd(pool_used, (unsigned long long)alive);
+            __syncthreads();
+            const unsigned long long off = s_off;
+            if (off + alive > pool_cap) { if (tid == 0) atomicOr(flags, (unsigned int)CHAIN_COMPLEX); return; }
+            for (uint32_t i = tid; i < alive; i += P1_THREADS) { pool_k[off + i] = kb[cur][i]; pool_lo[off + i] = lb[cur][i]; }
+            if (tid == 0) { BoundaryList bl; bl.off = off; bl.cnt = alive; bl.pad = 0; lists[(size_t)blockIdx.x * max_nf + r] = bl; }
+            r++;
+        }
         __syncthreads();
     }
-    if (cur != 0) {                                    // results always in half 0
-        for (uint32_t i = tid; i < alive; i += P1_THREADS) { kb[0][i] = kb[1][i]; lb[0][i] = lb[1][i]; }
-    }
-    if (tid == 0) { n_cls[j] = alive; if (dbg) { atomicAdd(&dbg[1], (unsigned long long)alive); atomicMax(&dbg[2], (unsigned long long)alive); } }
+    if (tid == 0 && dbg) { atomicAdd(&dbg[1], (unsigned long long)alive); atomicMax(&dbg[2], (unsigned long long)alive); }
 }
 
-// phase 2: one warp walks the chunk maps in order.  entry[j] = exact draw offset at the start of chunk j.
+// draw offset at the end of chunk r of group gd, for the walker that entered the group at offset k: the class of its
+// slice with the largest lowest-index <= its own window index
+__device__ __forceinline__ bool boundary_lookup(const GroupDesc &gd, int r, unsigned long long k, const BoundaryList *__restrict__ lists, int max_nf,
+                                                const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo, unsigned long long &k_out)
+{
+    if (k < gd.klo || k - gd.klo >= gd.W) return false;
+    const uint32_t idx = (uint32_t)(k - gd.klo);
+    uint32_t sl = idx / gd.w; if (sl >= gd.S) sl = gd.S - 1;
+    const BoundaryList bl = lists[(size_t)(gd.b0 + sl) * max_nf + r];
+    const uint32_t *lo = pool_lo + bl.off;
+    uint32_t a = 0, b = bl.cnt;                         // last i with lo[i] <= idx (lo[0] = first index of the slice <= idx)
+    while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (lo[mid] <= idx) a = mid; else b = mid; }
+    k_out = pool_k[bl.off + a];
+    return true;
+}
+
+// phase 2a: one warp walks the group maps in order.  gk[q] = exact draw offset at the start of group q.
 __global__ void __launch_bounds__(32)
-compose_kernel(int P, const ChunkWin *__restrict__ win, const unsigned long long *__restrict__ kbuf, const uint32_t *__restrict__ lobuf,
-               const uint32_t *__restrict__ n_cls, ChunkDesc *__restrict__ chunks, unsigned int *__restrict__ flags)
+compose_kernel(int G, const GroupDesc *__restrict__ groups, const BoundaryList *__restrict__ lists, int max_nf,
+               const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo,
+               unsigned long long *__restrict__ gk, unsigned int *__restrict__ flags)
 {
     const int lane = threadIdx.x;
     unsigned long long k = 0;
-    for (int j = 0; j < P; j++) {
-        const ChunkWin cw = win[j];
-        if (lane == 0) chunks[j].k_in = k;
-        if (k < cw.klo || k - cw.klo >= cw.W) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_MISS); return; }
-        const uint32_t idx = (uint32_t)(k - cw.klo), n = n_cls[j];
-        const uint32_t *lo = lobuf + cw.off; const unsigned long long *ko = kbuf + cw.off;
-        // last survivor with lo <= idx
-        uint32_t best = 0;
-        for (uint32_t base = 0; base < n; base += 32) {
+    for (int q = 0; q < G; q++) {
+        const GroupDesc gd = groups[q];
+        if (lane == 0) gk[q] = k;
+        if (k < gd.klo || k - gd.klo >= gd.W) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_MISS); return; }
+        const uint32_t idx = (uint32_t)(k - gd.klo);
+        uint32_t sl = idx / gd.w; if (sl >= gd.S) sl = gd.S - 1;
+        const BoundaryList bl = lists[(size_t)(gd.b0 + sl) * max_nf + (gd.nf - 1)];
+        const uint32_t *lo = pool_lo + bl.off;
+        uint32_t best = 0;                               // last survivor with lo <= idx
+        for (uint32_t base = 0; base < bl.cnt; base += 32) {
             const uint32_t i = base + lane;
-            const bool le = i < n && lo[i] <= idx;
+            const bool le = i < bl.cnt && lo[i] <= idx;
             const unsigned m = __ballot_sync(0xffffffffu, le);
             if (m) best = base + 31 - __clz(m);
             if (m != 0xffffffffu) break;
         }
-        k = ko[best];
-        if (lane == 0) chunks[j].k_out = k;
+        k = pool_k[bl.off + best];
     }
+}
+
+// phase 2b: every chunk learns its exact entry and exit offsets from its group's boundary lists
+__global__ void boundary_kernel(int P, int nf_per_group, const GroupDesc *__restrict__ groups, const BoundaryList *__restrict__ lists, int max_nf,
+                                const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo,
+                                const unsigned long long *__restrict__ gk, ChunkDesc *__restrict__ chunks, unsigned int *__restrict__ flags)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= P) return;
+    const int q = f / nf_per_group, r = f - q * nf_per_group;
+    const GroupDesc gd = groups[q];
+    const unsigned long long k = gk[q];
+    unsigned long long kin = k, kout = 0;
+    bool ok = true;
+    if (r > 0) ok = boundary_lookup(gd, r - 1, k, lists, max_nf, pool_k, pool_lo, kin);
+    ok = ok && boundary_lookup(gd, r, k, lists, max_nf, pool_k, pool_lo, kout);
+    if (!ok) { atomicOr(flags, (unsigned int)CHAIN_MISS); return; }
+    chunks[f].k_in = kin; chunks[f].k_out = kout;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -76,10 +76,11 @@ def test_seeds(seed, tmp_path, ctx):
     assert vcf_cmp(want[3], got[3]), first_diff(want[3], got[3])
 
 
-@pytest.mark.parametrize("name,chunk", [("plain", 512), ("deep_lowvaf", 256), ("mask_n_ref", 1024), ("overlap_heavy", 512), ("two_contigs_window", 640)])
-def test_parallel_chain_matches_serial(name, chunk, tmp_path, ctx, monkeypatch):
-    """The chunked chain (windows of candidate offsets, merging walkers, composed maps) against the oracle, and
-    against the one-warp serial chain: same SAM, same per-target results, same draw count."""
+@pytest.mark.parametrize("name,chunk,group,slice_", [("plain", 512, 4, 4096), ("deep_lowvaf", 256, 1, 16), ("mask_n_ref", 1024, 3, 5), ("overlap_heavy", 512, 4, 4096),
+                                                     ("two_contigs_window", 640, 2, 9), ("plain", 96, 8, 3), ("deep_lowvaf", 64, 5, 1)])
+def test_parallel_chain_matches_serial(name, chunk, group, slice_, tmp_path, ctx, monkeypatch):
+    """The chunked chain (windows of candidate offsets cut into slices, merging walkers, recorded chunk boundaries, composed
+    group maps) against the oracle, and against the one-warp serial chain: same SAM, same per-target results, same draw count."""
     prefix = sc.generate(name, str(tmp_path))
     want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     sam = open(prefix + ".sam", "rb").read()
@@ -91,6 +92,8 @@ def test_parallel_chain_matches_serial(name, chunk, tmp_path, ctx, monkeypatch):
         out_s, res_s, st_s = s.run_host(body, targets, 434)
         monkeypatch.delenv("SSB_CHAIN_SERIAL")
         monkeypatch.setenv("SSB_CHAIN_CHUNK", str(chunk))
+        monkeypatch.setenv("SSB_CHAIN_GROUP", str(group))
+        monkeypatch.setenv("SSB_CHAIN_SLICE", str(slice_))
         out_p, res_p, st_p = s.run_host(body, targets, 434)
     assert st_s.chain_mode == 1
     assert hdr + out_s == want[2] and hdr + out_p == want[2]
@@ -136,6 +139,8 @@ def test_fuzz_configs(k, tmp_path, ctx, monkeypatch):
     prefix = sc.generate("plain", str(tmp_path), **args)
     if k % 2:
         monkeypatch.setenv("SSB_CHAIN_CHUNK", str(rng.choice([96, 320, 1024])))
+        monkeypatch.setenv("SSB_CHAIN_GROUP", str(rng.choice([1, 2, 4, 7])))
+        monkeypatch.setenv("SSB_CHAIN_SLICE", str(rng.choice([2, 33, 4096])))
     if k % 3 == 0:
         monkeypatch.setenv("SSB_NO_EXC_LIST", "1")
     want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), seed=434 + k, cmdname="stochasticSpike")
