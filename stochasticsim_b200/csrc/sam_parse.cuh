@@ -17,14 +17,15 @@
 
 namespace samparse {
 
-constexpr int TILE      = 16384;
+constexpr int TILE      = 32768;
 constexpr int OVERHANG  = 4096;
 constexpr int THREADS   = 128;
-constexpr int MAX_LINES = 1024;                 // a valid SAM line has >= 22 bytes -> <= 745 per tile
+constexpr int MAX_LINES = 2048;                 // a valid SAM line has >= 22 bytes -> <= 1490 per tile
 constexpr int CHUNKS    = TILE / 16;            // 16-byte chunks per tile
+constexpr int CPT       = CHUNKS / THREADS;     // chunks per thread (a multiple of 8)
 constexpr int REFW      = 4096;                 // reference window staged per tile for the base-vs-reference comparison
 constexpr int EXC_BUF   = 1024;                 // exceptional bases of one tile, kept in shared memory until the tile is done
-constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + 16 + REFW + 32 + EXC_BUF * 4;
+constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 2 + 64 + 16 + REFW + 32 + EXC_BUF * 4;
 
 // tile_state word: bits 63..62 = status (0 none, 1 aggregate, 2 inclusive prefix), low 62 bits = line count
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
@@ -689,9 +690,9 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
     extern __shared__ __align__(16) uint8_t sm[];
     uint8_t  *text   = sm;                                            // TILE + OVERHANG
     uint16_t *masks  = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG);          // CHUNKS
-    uint32_t *starts = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2);   // MAX_LINES (tile-relative)
-    uint8_t  *refwin = sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + 16;         // REFW + 32 (16 bytes in front: words are read from 3 bytes before a read's first base)
-    uint32_t *excbuf = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 4 + 64 + 16 + REFW + 32);   // EXC_BUF
+    uint16_t *starts = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG + CHUNKS * 2);   // MAX_LINES (tile-relative, <= TILE)
+    uint8_t  *refwin = sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 2 + 64 + 16;         // REFW + 32 (16 bytes in front: words are read from 3 bytes before a read's first base)
+    uint32_t *excbuf = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 2 + 64 + 16 + REFW + 32);   // EXC_BUF
     __shared__ unsigned int s_tile;
     __shared__ unsigned int s_warp_tot[THREADS / 32];
     __shared__ unsigned long long s_base;
@@ -713,6 +714,15 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         if (tile >= n_tiles) break;
         const size_t T0 = tile * TILE;
         const size_t stage_end = (T0 + TILE + OVERHANG < n) ? T0 + TILE + OVERHANG : n;
+        // the tile this block is likely to draw next (one round of the resident blocks ahead) is asked into L2 now
+        {
+            const size_t P0 = T0 + (size_t)gridDim.x * TILE;
+#pragma unroll
+            for (int q = 0; q < TILE / 128 / THREADS; q++) {
+                const size_t a = P0 + ((size_t)q * THREADS + tid_) * 128;
+                if (a < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + a));
+            }
+        }
         // 1. stage
         for (size_t o = (size_t)tid_ * 16; T0 + o < stage_end; o += THREADS * 16) {
             if (T0 + o + 16 <= n) *reinterpret_cast<uint4 *>(text + o) = *reinterpret_cast<const uint4 *>(body + T0 + o);
@@ -733,21 +743,27 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         }
         __syncthreads();
         // a line starts after every newline except one sitting on the last byte of the tile (or of the body)
-        // thread t owns chunks [8t, 8t+8)
-        uint32_t mym[8]; uint32_t cnt = 0;
+        // thread t owns chunks [CPT t, CPT t + CPT)
+        uint32_t mym[CPT]; uint32_t cnt = 0;
         {
-            const uint4 mm = *reinterpret_cast<const uint4 *>(masks + 8 * tid_);
-            const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
-            for (int k = 0; k < 4; k++) { mym[2 * k] = w4[k] & 0xFFFFu; mym[2 * k + 1] = w4[k] >> 16; }
-            if (tid_ == THREADS - 1) mym[7] &= 0x7FFFu;              // newline on the last byte of a full tile: next tile's line
+            for (int q = 0; q < CPT / 8; q++) {
+                const uint4 mm = *reinterpret_cast<const uint4 *>(masks + CPT * tid_ + 8 * q);
+                const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                // drop a newline that is the very last byte of the body: nothing starts after it
-                size_t cb = T0 + (size_t)(8 * tid_ + k) * 16;
-                if (n > cb && n - cb <= 16) mym[k] &= ~(1u << (n - cb - 1));
-                cnt += __popc(mym[k]);
+                for (int k = 0; k < 4; k++) { mym[8 * q + 2 * k] = w4[k] & 0xFFFFu; mym[8 * q + 2 * k + 1] = w4[k] >> 16; }
             }
+            if (tid_ == THREADS - 1) mym[CPT - 1] &= 0x7FFFu;        // newline on the last byte of a full tile: next tile's line
+            // drop a newline that is the very last byte of the body: nothing starts after it
+            if (n - T0 <= (size_t)TILE) {
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    const size_t cb = T0 + (size_t)(CPT * tid_ + k) * 16;
+                    if (n > cb && n - cb <= 16) mym[k] &= ~(1u << (n - cb - 1));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; k++) cnt += __popc(mym[k]);
         }
         // block exclusive scan of cnt
         uint32_t incl = cnt;
@@ -799,12 +815,14 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             continue;
         }
         if (tid_ == 0 && first) starts[0] = 0;
+        if (cnt) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            uint32_t m = mym[k];
-            while (m) {
-                int b = __ffs(m) - 1; m &= m - 1;
-                starts[my_base++] = (uint32_t)((8 * tid_ + k) * 16 + b + 1);
+            for (int k = 0; k < CPT; k++) {
+                uint32_t m = mym[k];
+                while (m) {
+                    int b = __ffs(m) - 1; m &= m - 1;
+                    starts[my_base++] = (uint16_t)((CPT * tid_ + k) * 16 + b + 1);
+                }
             }
         }
         __syncthreads();
@@ -824,7 +842,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         __syncthreads();
         // 4a. heads.  Thread t takes line t of the tile; the lanes of a warp stay together (parse_head_conv).  A line that is
         //     not of the common shape, or does not end inside the staged window, is parsed by the careful functions at once.
-        const uint32_t li = (uint32_t)tid_;
+        const uint32_t li = (uint32_t)(lane * (THREADS / 32) + wid);      // consecutive lines go to different warps: all warps share the parsing
         const bool have = li < n_here;
         const unsigned wmask = __ballot_sync(0xffffffffu, have);
         SamRec r; int rc = 0; bool fast = false; uint32_t qend = 0, lo = 0, len = 0; size_t ls = 0;
@@ -897,7 +915,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = ls;
         }
         // tiles of very short lines: the lines beyond the first THREADS take the careful path, one per thread
-        for (uint32_t i = tid_ + THREADS; i < n_here; i += THREADS) {
+        for (uint32_t i = li + THREADS; i < n_here; i += THREADS) {
             const size_t s = T0 + starts[i];
             const size_t e = (i + 1 < n_here) ? T0 + starts[i + 1] - 1 : (size_t)s_last_end;
             SamRec r2; int rc2;

@@ -216,36 +216,88 @@ __global__ void ordoff_kernel(const uint32_t *__restrict__ perm, const unsigned 
     if (o < K) ord_off[perm[o]] = out_off[o];
 }
 
-// One warp per output line: dst-aligned 4-byte stores, source words funnel-shifted into place.
-__global__ void __launch_bounds__(256)
-emit_kernel(const uint8_t *__restrict__ sam, const EmitDesc *__restrict__ desc, const unsigned long long *__restrict__ out_off, size_t K,
+// One warp per output line, 16 bytes per lane: destination-aligned 16-byte stores; the source bytes of a chunk lie in two
+// aligned 16-byte source words, shifted into place.  The shift is the same for the whole line (= for the whole warp), so the
+// word part of it is a four-way switch over statically indexed registers.  Two lines are in flight per warp.
+struct EmitJob { const uint8_t *src; uint8_t *dst; uint32_t len, head, nvec, mis, add_nl;
+                 __device__ __forceinline__ const uint4 *S() const { return reinterpret_cast<const uint4 *>(src + head - mis); }
+                 __device__ __forceinline__ uint4 *D() const { return reinterpret_cast<uint4 *>(dst + head); } };
+
+__device__ __forceinline__ EmitJob emit_job(const uint8_t *__restrict__ sam, const EmitDesc r, unsigned long long off, uint8_t *__restrict__ out)
+{
+    EmitJob j;
+    j.src = sam + r.src_off; j.dst = out + off; j.len = r.len; j.add_nl = r.add_nl;
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)j.dst & 15)) & 15);
+    if (head > j.len) head = j.len;
+    j.head = head;
+    j.nvec = (j.len - head) >> 4;
+    const uint8_t *s0 = j.src + head;
+    j.mis = (uint32_t)((uintptr_t)s0 & 15);
+    return j;
+}
+template <int WQ>
+__device__ __forceinline__ uint4 emit_shift(const uint4 A, const uint4 B, uint32_t sh)
+{
+    const uint32_t W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    uint4 o;
+    o.x = __funnelshift_r(W[WQ], W[WQ + 1], sh); o.y = __funnelshift_r(W[WQ + 1], W[WQ + 2], sh);
+    o.z = __funnelshift_r(W[WQ + 2], W[WQ + 3], sh); o.w = __funnelshift_r(W[WQ + 3], W[WQ + 4], sh);
+    return o;
+}
+__device__ __forceinline__ void emit_load(const EmitJob &j, uint32_t i, const uint8_t *sam_end, uint4 &A, uint4 &B)
+{
+    const uint4 *S = j.S();
+    A = __ldg(S + i);
+    B = make_uint4(0, 0, 0, 0);
+    if (j.mis && reinterpret_cast<const uint8_t *>(S + i + 1) < sam_end) B = __ldg(S + i + 1);
+}
+__device__ __forceinline__ void emit_store(const EmitJob &j, uint32_t i, const uint4 A, const uint4 B)
+{
+    const uint32_t sh = (j.mis & 3u) * 8u;
+    uint4 o;
+    switch (j.mis >> 2) {
+    case 0: o = emit_shift<0>(A, B, sh); break;
+    case 1: o = emit_shift<1>(A, B, sh); break;
+    case 2: o = emit_shift<2>(A, B, sh); break;
+    default: o = emit_shift<3>(A, B, sh); break;
+    }
+    j.D()[i] = o;
+}
+__device__ __forceinline__ void emit_edges(const EmitJob &j, int lane)
+{
+    if ((uint32_t)lane < j.head) j.dst[lane] = j.src[lane];                 // < 16 bytes up to the first aligned destination address
+    const uint32_t done = j.head + (j.nvec << 4);
+    if (done + lane < j.len) j.dst[done + lane] = j.src[done + lane];       // < 16 tail bytes
+    if (lane == 0 && j.add_nl) j.dst[j.len] = '\n';
+}
+
+template <int NL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+emit_kernel(const uint8_t *__restrict__ sam, size_t n_sam, const EmitDesc *__restrict__ desc, const unsigned long long *__restrict__ out_off, size_t K,
             uint8_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t o = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); o < K; o += warps) {
-        const EmitDesc r = desc[o];
-        const uint8_t *src = sam + r.src_off;
-        uint8_t *dst = out + out_off[o];
-        const uint32_t len = r.len;
-        // head: bytes up to the first 4-byte aligned destination address
-        uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
-        if (head > len) head = len;
-        if ((uint32_t)lane < head) dst[lane] = src[lane];
-        const uint32_t words = (len - head) >> 2;
-        const uint8_t *s0 = src + head;
-        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
-        const uint32_t mis = (uint32_t)((uintptr_t)s0 & 3);
-        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s0 - mis);
-        if (mis == 0) {
-            for (uint32_t w = lane; w < words; w += 32) d4[w] = s4[w];
-        } else {
-            const uint32_t sh = mis * 8;
-            for (uint32_t w = lane; w < words; w += 32) d4[w] = __funnelshift_r(s4[w], s4[w + 1], sh);
+    const uint8_t *sam_end = sam + n_sam;
+    for (size_t o = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); o < K; o += NL * warps) {
+        EmitJob j[NL]; bool have[NL], in[NL]; uint4 A[NL], B[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            const size_t ol = o + (size_t)l * warps;
+            have[l] = ol < K;
+            j[l] = emit_job(sam, desc[have[l] ? ol : o], out_off[have[l] ? ol : o], out);
+            in[l] = have[l] && (uint32_t)lane < j[l].nvec;
         }
-        const uint32_t done = head + (words << 2);
-        if (done + lane < len) dst[done + lane] = src[done + lane];       // < 4 tail bytes
-        if (lane == 0 && r.add_nl) dst[len] = '\n';
+#pragma unroll
+        for (int l = 0; l < NL; l++) if (in[l]) emit_load(j[l], lane, sam_end, A[l], B[l]);
+#pragma unroll
+        for (int l = 0; l < NL; l++) if (in[l]) emit_store(j[l], lane, A[l], B[l]);
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            if (!have[l]) continue;
+            for (uint32_t i = lane + 32; i < j[l].nvec; i += 32) { emit_load(j[l], i, sam_end, A[l], B[l]); emit_store(j[l], i, A[l], B[l]); }
+            emit_edges(j[l], lane);
+        }
     }
 }
 
@@ -1048,7 +1100,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             SSB_CUDA(ctx, cudaMemsetAsync(d_exc_count, 0, sizeof(unsigned long long), s));
             samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_lens,
                                         getenv("SSB_NO_EXC_LIST") ? NULL : exc_list, d_exc_count, exc_cap};
-            int grid = (int)(n_tiles < (size_t)ctx->sm_count * 8 ? n_tiles : (size_t)ctx->sm_count * 8);
+            int occ = 1;
+            SSB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, samparse::parse_kernel, samparse::THREADS, samparse::SMEM_BYTES));
+            if (occ < 1) occ = 1;
+            int grid = (int)(n_tiles < (size_t)ctx->sm_count * occ ? n_tiles : (size_t)ctx->sm_count * occ);     // persistent: exactly the resident blocks
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_PARSE, samparse::parse_kernel, grid, samparse::THREADS, samparse::SMEM_BYTES, s,
                          d_sam, n, names, recs, rec_cap, tile_state, ticket, d_nlines, reinterpret_cast<SpikeErr *>(d_err));
             unsigned long long nl = 0; DevErr e;
@@ -1124,7 +1179,11 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         if (total_out > out_cap) { snprintf(ctx->err, sizeof ctx->err, "spike: output needs %llu bytes, capacity %zu", total_out, out_cap); return SSB_E_ARG; }
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, ordoff_kernel, grid_for(K, 256), 256, 0, s, perm, out_off, K, ord_off);
         SSB_CUDA(ctx, cudaEventRecord(ev[3], s));
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, emit_kernel, ctx->sm_count * 8, 256, 0, s, d_sam, edesc, out_off, K, d_out);
+        {
+            const char *ev_ = getenv("SSB_EMIT_VARIANT"); const int v = ev_ ? atoi(ev_) : 0;
+            if (v == 1) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, (emit_kernel<2, 4>), ctx->sm_count * 4, 256, 0, s, d_sam, n, edesc, out_off, K, d_out);
+            else SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, (emit_kernel<1, 8>), ctx->sm_count * 8, 256, 0, s, d_sam, n, edesc, out_off, K, d_out);
+        }
     } else SSB_CUDA(ctx, cudaEventRecord(ev[3], s));
     *out_bytes = (size_t)total_out;
     stats->out_bytes = (int64_t)total_out;
