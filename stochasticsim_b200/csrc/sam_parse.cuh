@@ -18,14 +18,18 @@
 namespace samparse {
 
 constexpr int TILE      = 32768;
-constexpr int OVERHANG  = 4096;
+constexpr int OVERHANG  = 3072;
 constexpr int THREADS   = 128;
 constexpr int MAX_LINES = 2048;                 // a valid SAM line has >= 22 bytes -> <= 1490 per tile
 constexpr int CHUNKS    = TILE / 16;            // 16-byte chunks per tile
 constexpr int CPT       = CHUNKS / THREADS;     // chunks per thread (a multiple of 8)
 constexpr int REFW      = 4096;                 // reference window staged per tile for the base-vs-reference comparison
 constexpr int EXC_BUF   = 1024;                 // exceptional bases of one tile, kept in shared memory until the tile is done
-constexpr int SMEM_BYTES = TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 2 + 64 + 16 + REFW + 32 + EXC_BUF * 4;
+// shared memory of a block: the staged text, then two regions that change hands inside a tile:
+//   A: newline masks (steps 2-3)  ->  reference window (steps 4-5);   B: line starts (steps 3-4a)  ->  exception buffer (steps 4b-5)
+constexpr int REGION_A  = (CHUNKS * 2 > REFW + 64 ? CHUNKS * 2 : REFW + 64);
+constexpr int REGION_B  = (MAX_LINES * 2 > EXC_BUF * 4 ? MAX_LINES * 2 : EXC_BUF * 4);
+constexpr int SMEM_BYTES = TILE + OVERHANG + REGION_A + REGION_B + 64;
 
 // tile_state word: bits 63..62 = status (0 none, 1 aggregate, 2 inclusive prefix), low 62 bits = line count
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
@@ -628,42 +632,41 @@ __device__ __forceinline__ uint32_t parse_head_conv(const Cursor &cur, const uin
 // BQ 0 goes to the tile's exception buffer.  Returns nonzero if a byte is outside what htslib prints back unchanged.
 template <bool CMP>
 __device__ __forceinline__ uint32_t long_fields(const uint8_t *L, uint32_t seq_off, uint32_t l_seq, uint32_t qual_off, bool qstar,
-                                                const uint8_t *ref, const uint8_t *ref_raw, uint32_t line_in_tile, unsigned long long gi,
-                                                uint32_t *excbuf, unsigned int *s_nexc, const ContigNames &names)
+                                                const uint8_t *ref, const uint8_t *ref_raw, uint32_t line_in_tile,
+                                                uint32_t *excbuf, unsigned int *s_nexc)
 {
     const uint8_t *As = L + seq_off;
     const uint32_t sh = (uint32_t)((uintptr_t)As & 3u);
     const uint32_t *Ws = reinterpret_cast<const uint32_t *>(As - sh);
     const uint32_t nw = (sh + l_seq + 3u) >> 2;
     const uint8_t *Aq = L + qual_off - sh;
-    const uint32_t shq = (uint32_t)((uintptr_t)Aq & 3u);
-    const uint32_t *Wq = reinterpret_cast<const uint32_t *>(Aq - shq);
+    const uint32_t shq = (uint32_t)((uintptr_t)Aq & 3u) * 8u;
+    const uint32_t *Wq = reinterpret_cast<const uint32_t *>(Aq - (shq >> 3));
     uint32_t qprev = qstar ? 0u : Wq[0];
     const uint8_t *Ar = CMP ? ref - sh : L;
-    const uint32_t shr = (uint32_t)((uintptr_t)Ar & 3u);
-    const uint32_t *Wr = reinterpret_cast<const uint32_t *>(Ar - shr);
+    const uint32_t shr = (uint32_t)((uintptr_t)Ar & 3u) * 8u;
+    const uint32_t *Wr = reinterpret_cast<const uint32_t *>(Ar - (shr >> 3));
     uint32_t rprev = CMP ? Wr[0] : 0u;
     const uint32_t m_first = 0x80808080u << (8 * sh);
     const uint32_t tail = (sh + l_seq) & 3u;
     const uint32_t m_last = tail ? (0x80808080u >> (8 * (4 - tail))) : 0x80808080u;
-    uint32_t bad = 0;
-    for (uint32_t j = 0; j < nw; j++) {
-        const uint32_t sq = Ws[j];
-        uint32_t ql = 0x7e7e7e7eu, rf = 0;
-        if (!qstar) { const uint32_t nx = Wq[j + 1]; ql = __funnelshift_r(qprev, nx, shq * 8); qprev = nx; }
-        uint32_t fl;
+    uint32_t bad = 0;                                   // bit 0: a byte outside the envelope, bit 1: the exception buffer is full
+    // flags of word j (0x80 per byte that needs a closer look); sq/ql/rf = the word's SEQ, QUAL and reference bytes
+    auto flags = [&](uint32_t j, uint32_t &sq, uint32_t &ql, uint32_t &rf) -> uint32_t {
+        sq = Ws[j]; ql = 0x7e7e7e7eu; rf = 0;
+        if (!qstar) { const uint32_t nx = Wq[j + 1]; ql = __funnelshift_r(qprev, nx, shq); qprev = nx; }
         if (CMP) {
-            const uint32_t nx = Wr[j + 1]; rf = __funnelshift_r(rprev, nx, shr * 8); rprev = nx;
+            const uint32_t nx = Wr[j + 1]; rf = __funnelshift_r(rprev, nx, shr); rprev = nx;
             const uint32_t d = sq ^ rf;
-            fl = (((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d | sq) | (ql | ~(ql + 0x5e5e5e5eu) | (ql + 0x01010101u));   // differs | >= 0x80 | BQ outside '"'..'~'
-        } else fl = non_acgtn_bytes(sq) | nonprint_bytes(ql);
-        fl &= 0x80808080u;
-        if (j == 0) fl &= m_first;
-        if (j == nw - 1) fl &= m_last;
+            return ((((d & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d | sq) | (ql | ~(ql + 0x5e5e5e5eu) | (ql + 0x01010101u))) & 0x80808080u;   // differs | >= 0x80 | BQ outside '"'..'~'
+        }
+        return (non_acgtn_bytes(sq) | nonprint_bytes(ql)) & 0x80808080u;
+    };
+    auto look = [&](uint32_t j, uint32_t fl, uint32_t sq, uint32_t ql, uint32_t rf) {
         while (fl) {
             const uint32_t k = (uint32_t)(__ffs(fl) - 1) >> 3; fl &= fl - 1;
             const uint32_t sb = (sq >> (8 * k)) & 0xffu, qb = (ql >> (8 * k)) & 0xffu;
-            if (!seq_char_ok((uint8_t)sb) || qb < '!' || qb > '~') { bad = 1; continue; }
+            if (!seq_char_ok((uint8_t)sb) || qb < '!' || qb > '~') { bad |= 1u; continue; }
             if (CMP) {
                 const uint32_t q = 4 * j + k - sh;
                 uint32_t rb = (rf >> (8 * k)) & 0xffu;
@@ -671,13 +674,27 @@ __device__ __forceinline__ uint32_t long_fields(const uint8_t *L, uint32_t seq_o
                 if (sb != rb || qb == '!') {
                     const unsigned int slot = atomicAdd(s_nexc, 1u);
                     if (slot < (unsigned int)EXC_BUF) excbuf[slot] = (line_in_tile << 16) | q;
-                    else {
-                        const unsigned long long gs = atomicAdd(names.exc_count, 1ull);
-                        if (gs < names.exc_cap) names.exc[gs] = (gi << 16) | q;
-                    }
+                    else bad |= 2u;
                 }
             }
         }
+    };
+    uint32_t sq, ql, rf;
+    {   // first word (its low bytes may belong to the field before)
+        uint32_t fl = flags(0, sq, ql, rf) & m_first;
+        if (nw == 1) fl &= m_last;
+        if (fl) look(0, fl, sq, ql, rf);
+    }
+    uint32_t j = 1;
+    for (; j + 2 < nw; j += 2) {                        // whole words, two at a time
+        uint32_t sq2, ql2, rf2;
+        const uint32_t f1 = flags(j, sq, ql, rf), f2 = flags(j + 1, sq2, ql2, rf2);
+        if (f1 | f2) { look(j, f1, sq, ql, rf); look(j + 1, f2, sq2, ql2, rf2); }
+    }
+    for (; j < nw; j++) {                               // the rest; the last word's high bytes may belong to the next field
+        uint32_t fl = flags(j, sq, ql, rf);
+        if (j == nw - 1) fl &= m_last;
+        if (fl) look(j, fl, sq, ql, rf);
     }
     return bad;
 }
@@ -689,10 +706,10 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
 {
     extern __shared__ __align__(16) uint8_t sm[];
     uint8_t  *text   = sm;                                            // TILE + OVERHANG
-    uint16_t *masks  = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG);          // CHUNKS
-    uint16_t *starts = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG + CHUNKS * 2);   // MAX_LINES (tile-relative, <= TILE)
-    uint8_t  *refwin = sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 2 + 64 + 16;         // REFW + 32 (16 bytes in front: words are read from 3 bytes before a read's first base)
-    uint32_t *excbuf = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + CHUNKS * 2 + MAX_LINES * 2 + 64 + 16 + REFW + 32);   // EXC_BUF
+    uint16_t *masks  = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG);                  // region A
+    uint8_t  *refwin = sm + TILE + OVERHANG + 16;                                           // region A (16 bytes in front: words are read from 3 bytes before a read's first base)
+    uint16_t *starts = reinterpret_cast<uint16_t *>(sm + TILE + OVERHANG + REGION_A);       // region B: MAX_LINES, tile-relative (<= TILE)
+    uint32_t *excbuf = reinterpret_cast<uint32_t *>(sm + TILE + OVERHANG + REGION_A);       // region B: EXC_BUF
     __shared__ unsigned int s_tile;
     __shared__ unsigned int s_warp_tot[THREADS / 32];
     __shared__ unsigned long long s_base;
@@ -723,10 +740,19 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 if (a < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + a));
             }
         }
-        // 1. stage
-        for (size_t o = (size_t)tid_ * 16; T0 + o < stage_end; o += THREADS * 16) {
-            if (T0 + o + 16 <= n) *reinterpret_cast<uint4 *>(text + o) = *reinterpret_cast<const uint4 *>(body + T0 + o);
-            else for (int k = 0; k < 16; k++) text[o + k] = (T0 + o + k < n) ? body[T0 + o + k] : (uint8_t)'\n';
+        // 1. stage: asynchronous 16-byte copies, all in flight at once (no registers in between)
+        if (T0 + TILE + OVERHANG <= n && ((uintptr_t)body & 15u) == 0) {
+            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(text);
+#pragma unroll 6
+            for (uint32_t o = (uint32_t)tid_ * 16; o < (uint32_t)(TILE + OVERHANG); o += THREADS * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + o), "l"(body + T0 + o) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            for (size_t o = (size_t)tid_ * 16; T0 + o < stage_end; o += THREADS * 16) {
+                if (T0 + o + 16 <= n && ((uintptr_t)body & 15u) == 0) *reinterpret_cast<uint4 *>(text + o) = *reinterpret_cast<const uint4 *>(body + T0 + o);
+                else for (int k = 0; k < 16; k++) text[o + k] = (T0 + o + k < n) ? body[T0 + o + k] : (uint8_t)'\n';
+            }
         }
         if (tid_ == 0) s_first = (T0 == 0) ? 1u : (body[T0 - 1] == '\n');
         __syncthreads();
@@ -788,13 +814,16 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 long long j = (long long)tile - 1;
                 for (;;) {
                     const long long hi = j - 8 * lane;                     // this lane looks at tiles hi, hi-1, .. hi-7
+                    unsigned long long v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) { v[k] = 2ull << 62; if (hi - k >= 0) v[k] = ts[hi - k]; }     // before tile 0: inclusive prefix 0
                     unsigned long long sum = 0; bool has_inc = false;
-                    for (int k = 0; k < 8 && !has_inc; k++) {
-                        const long long idx = hi - k;
-                        unsigned long long v = ST_INC;                     // before tile 0: inclusive prefix 0
-                        if (idx >= 0) { do { v = ts[idx]; } while ((v & ST_MASK) == 0); }
-                        sum += v & ~ST_MASK;
-                        has_inc = (v & ST_MASK) == ST_INC;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (has_inc) continue;
+                        while ((v[k] & ST_MASK) == 0) v[k] = ts[hi - k];                      // not published yet
+                        sum += v[k] & ~ST_MASK;
+                        has_inc = (v[k] & ST_MASK) == ST_INC;
                     }
                     const unsigned inc = __ballot_sync(0xffffffffu, has_inc);
                     const int first = inc ? __ffs(inc) - 1 : 31;           // nearest lane that met an inclusive prefix
@@ -858,6 +887,18 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             } else rc = parse_line(cur, ls, e, names, tid_cache, r);
             if (!rc && r.tid >= 0) tid_cache = r.tid;
         }
+        // tiles of very short lines: the lines beyond the first THREADS take the careful path, one per thread (before the line starts give way to the exception buffer)
+        for (uint32_t i = li + THREADS; i < n_here; i += THREADS) {
+            const size_t s = T0 + starts[i];
+            const size_t e = (i + 1 < n_here) ? T0 + starts[i + 1] - 1 : (size_t)s_last_end;
+            SamRec r2; int rc2;
+            if (e <= stage_end && e - s < 0x40000000ull) rc2 = parse_line_smem(cur, text + (s - T0), (uint32_t)(e - s), s, e < n, names, tid_cache, r2);
+            else rc2 = parse_line(cur, s, e, names, tid_cache, r2);
+            if (rc2) { if (atomicCAS(&err->code, 0, rc2) == 0) err->where = s; memset(&r2, 0, sizeof r2); r2.line_off = s; r2.tid = -1; }
+            const unsigned long long g2 = gbase + i;
+            if (g2 < rec_cap) recs[g2] = r2;
+            else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
+        }
         const unsigned long long gi = gbase + li;
         // the reference window under the tile's reads: lowest (tid, pos) among the reads that align 1:1
         const bool elig = fast && names.exc && (r.bits & REC_KEEP) && (r.bits & REC_SIMPLE) && r.l_seq < 65536u && gi < rec_cap && gi < (1ull << 47) &&
@@ -899,9 +940,10 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 const bool qstar = (r.bits & REC_QUALSTAR) != 0;
                 uint32_t bad;
                 if (in_win) {
-                    bad = long_fields<true>(L, r.seq_off, r.l_seq, r.qual_off, qstar, refwin + (r.pos - w_lo), names.seq[wtid] + r.pos, li, gi, excbuf, &s_nexc, names);
-                    r.bits |= REC_EXC_DONE;
-                } else bad = long_fields<false>(L, r.seq_off, r.l_seq, r.qual_off, qstar, NULL, NULL, li, gi, excbuf, &s_nexc, names);
+                    bad = long_fields<true>(L, r.seq_off, r.l_seq, r.qual_off, qstar, refwin + (r.pos - w_lo), names.seq[wtid] + r.pos, li, excbuf, &s_nexc);
+                    if (!(bad & 2u)) r.bits |= REC_EXC_DONE;               // buffer full: the generic tally takes this read
+                    bad &= 1u;
+                } else bad = long_fields<false>(L, r.seq_off, r.l_seq, r.qual_off, qstar, NULL, NULL, li, excbuf, &s_nexc);
                 for (size_t q = ls + qend; q < ls + len;) {
                     size_t a = q + 1, b = a;
                     while (b < ls + len && cur.at(b) != '\t') b++;
@@ -913,18 +955,6 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = ls; memset(&r, 0, sizeof r); r.line_off = ls; r.tid = -1; }
             if (gi < rec_cap) recs[gi] = r;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = ls;
-        }
-        // tiles of very short lines: the lines beyond the first THREADS take the careful path, one per thread
-        for (uint32_t i = li + THREADS; i < n_here; i += THREADS) {
-            const size_t s = T0 + starts[i];
-            const size_t e = (i + 1 < n_here) ? T0 + starts[i + 1] - 1 : (size_t)s_last_end;
-            SamRec r2; int rc2;
-            if (e <= stage_end && e - s < 0x40000000ull) rc2 = parse_line_smem(cur, text + (s - T0), (uint32_t)(e - s), s, e < n, names, tid_cache, r2);
-            else rc2 = parse_line(cur, s, e, names, tid_cache, r2);
-            if (rc2) { if (atomicCAS(&err->code, 0, rc2) == 0) err->where = s; memset(&r2, 0, sizeof r2); r2.line_off = s; r2.tid = -1; }
-            const unsigned long long g2 = gbase + i;
-            if (g2 < rec_cap) recs[g2] = r2;
-            else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
         }
         // 5. hand the tile's exceptional bases over: one reservation per tile, coalesced stores
         if (names.exc) {
