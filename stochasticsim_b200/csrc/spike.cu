@@ -75,12 +75,21 @@ __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const 
             span = (unsigned long long)(r.end - r.pos);
         }
     }
-    // totalFoldCoverage = sum of reference spans of kept reads (stochasticSpike.c:1259)
+    // totalFoldCoverage = sum of reference spans of kept reads (stochasticSpike.c:1259): one atomic per block
+    __shared__ unsigned long long s_sum[8]; __shared__ unsigned int s_max[8];
     unsigned long long s = span;
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     unsigned int m = (unsigned int)span;
     for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) { if (s) atomicAdd(fold, s); if (m) atomicMax(maxspan, m); }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_sum[w] = s; s_max[w] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int k = 1; k < nw; k++) { s += s_sum[k]; m = max(m, s_max[k]); }
+        if (s) atomicAdd(fold, s);
+        if (m) atomicMax(maxspan, m);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -107,7 +116,17 @@ __global__ void mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__re
     const unsigned long long lim = k_end[o];       // same tid, pos < end  <=>  start key < end key
     const unsigned long long h = k_hash[o];
     uint32_t first = NO_MATE; bool more = false;
-    for (size_t b = o + 1; b < K && k_start[b] < lim; b++) {
+    // reads that start inside this read's span: [o + 1, hi).  The bound is found once (galloping, then bisection), so the
+    // scan itself only touches the hashes.
+    size_t hi;
+    {
+        size_t step = 64, lo = o + 1;
+        hi = lo;
+        while (hi < K && k_start[hi] < lim) { lo = hi + 1; hi += step; step <<= 1; }
+        if (hi > K) hi = K;
+        while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (k_start[mid] < lim) lo = mid + 1; else hi = mid; }
+    }
+    for (size_t b = o + 1; b < hi; b++) {
         if (k_hash[b] != h) continue;
         if (!same_qname(sam, recs[k_rec[o]], recs[k_rec[b]])) continue;
         if (first == NO_MATE) { first = (uint32_t)b; prv[b] = (uint32_t)o; }    // injective: see DESIGN.md (mate links)
@@ -1308,7 +1327,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         // passes, so dense deep panels (pileup entries comparable to walked loci) stay on the one-warp serial chain
         const bool sparse_targets = (unsigned long long)E * 16ull < (unsigned long long)n_walk;
         if (!(env_serial && env_serial[0] == '1') && ((n_walk >= (1 << 20) && sparse_targets) || env_chunk)) {
-            Lc = n_walk / 1024; if (Lc < 32768) Lc = 32768;
+            Lc = n_walk / 4096; if (Lc < 8192) Lc = 8192;              // phase 3 walks one chunk per warp: short chunks keep its chain short
             if (env_chunk && atoll(env_chunk) >= 64) Lc = atoll(env_chunk);
             Lc = (Lc + 31) & ~(int64_t)31;
             P = (int)((n_walk + Lc - 1) / Lc);
@@ -1324,7 +1343,8 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaMemcpyAsync(h_var.data(), d_var, P * sizeof(double), cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         // groups of Rg consecutive chunks share one start-offset window; the window is cut into slices of ~wt offsets
-        int Rg = 2; uint32_t wt = 16384;
+        int Rg = (int)(114688 / Lc); if (Rg < 1) Rg = 1;                    // phase 1 works on groups of ~112 k loci (see spike_chain.cuh)
+        uint32_t wt = 16384;
         if (const char *e = getenv("SSB_CHAIN_GROUP")) { if (atoi(e) >= 1) Rg = atoi(e); }
         if (const char *e = getenv("SSB_CHAIN_SLICE")) { if (atoi(e) >= 1) wt = (uint32_t)atoi(e); }
         const int G = (P + Rg - 1) / Rg;
