@@ -1427,18 +1427,26 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
             if ((rc = reset_apply())) return rc;
             if (parallel) {
                 unsigned long long *d_dbg = NULL;
-                if (getenv("SSB_CHAIN_DEBUG")) { d_dbg = ar.get<unsigned long long>(4); SPK_CHECK_ARENA(ar); SSB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, 32, s)); }
+                if (getenv("SSB_CHAIN_DEBUG")) { d_dbg = ar.get<unsigned long long>(8 + 2 * n_slices); SPK_CHECK_ARENA(ar); SSB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (8 + 2 * n_slices) * 8, s)); }
                 SSB_CUDA(ctx, cudaMemsetAsync(d_pool_used, 0, 8, s));
                 SSB_CUDA(ctx, cudaMemsetAsync(d_lists, 0, n_slices * (size_t)Rg * sizeof(BoundaryList), s));
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, (int)n_slices, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, woff,
                              d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, d_dbg);
                 if (d_dbg) {
-                    unsigned long long h_dbg[4], used = 0;
-                    SSB_CUDA(ctx, cudaMemcpyAsync(h_dbg, d_dbg, 32, cudaMemcpyDeviceToHost, s));
+                    unsigned long long h_dbg[8], used = 0;
+                    SSB_CUDA(ctx, cudaMemcpyAsync(h_dbg, d_dbg, 64, cudaMemcpyDeviceToHost, s));
                     SSB_CUDA(ctx, cudaMemcpyAsync(&used, d_pool_used, 8, cudaMemcpyDeviceToHost, s));
                     SSB_CUDA(ctx, cudaStreamSynchronize(s));
                     fprintf(stderr, "[chain] chunks=%d L=%lld groups=%d slices=%zu walkers=%llu walker-loci=%llu rounds=%llu final survivors: sum %llu max %llu, recorded %llu\n",
                             P, (long long)Lc, G, n_slices, woff, h_dbg[0], h_dbg[3], h_dbg[1], h_dbg[2], used);
+                    fprintf(stderr, "[chain] phase 1 block cycles: rounds with > %d walkers %.3g (avg per block), later rounds %.3g, slowest block %.3g\n", P1_THREADS,
+                            (double)h_dbg[4] / (double)n_slices, (double)h_dbg[5] / (double)n_slices, (double)h_dbg[6]);
+                    if (getenv("SSB_CHAIN_DEBUG")[0] == '3') {
+                        std::vector<unsigned long long> pb(2 * n_slices);
+                        SSB_CUDA(ctx, cudaMemcpy(pb.data(), d_dbg + 8, 2 * n_slices * 8, cudaMemcpyDeviceToHost));
+                        for (size_t b = 0; b < n_slices; b += (n_slices / 60 ? n_slices / 60 : 1))
+                            fprintf(stderr, "[chain]   block %zu group %d i0 %u n %u: total %.3g early %.3g\n", b, h_slices[b].q, h_slices[b].i0, h_slices[b].n, (double)pb[2 * b], (double)pb[2 * b + 1]);
+                    }
                 }
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, G, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_flags);
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, boundary_kernel, (P + 127) / 128, 128, 0, s, P, Rg, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_chunks, d_flags);

@@ -443,7 +443,9 @@ phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, cons
     int cur = 0, r = 0;
     int64_t g = g0, step = 64;
     const unsigned long long plane_words = (A.M >> 5) + 160ull;              // words the draw planes hold (padding included)
+    long long t_prev = dbg ? clock64() : 0, t_start = t_prev; unsigned long long t_early = 0;
     while (g < gend) {
+        if (dbg && tid == 0) { const long long t = clock64(); if (alive > (uint32_t)P1_THREADS) t_early += (unsigned long long)(t - t_prev); atomicAdd(&dbg[alive > (uint32_t)P1_THREADS ? 4 : 5], (unsigned long long)(t - t_prev)); t_prev = t; }
         const int64_t fine_end = (g0 + (int64_t)(r + 1) * L < gend) ? g0 + (int64_t)(r + 1) * L : gend;
         int64_t gc = g + step; if (gc > fine_end || fine_end - gc < step / 2) gc = fine_end;
         if (gc - g > P1_SEG) gc = g + P1_SEG;
@@ -517,7 +519,12 @@ phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, cons
         }
         __syncthreads();
     }
-    if (tid == 0 && dbg) { atomicAdd(&dbg[1], (unsigned long long)alive); atomicMax(&dbg[2], (unsigned long long)alive); }
+    if (tid == 0 && dbg) {
+        atomicAdd(&dbg[1], (unsigned long long)alive); atomicMax(&dbg[2], (unsigned long long)alive);
+        const unsigned long long tot = (unsigned long long)(clock64() - t_start);
+        atomicMax(&dbg[6], tot);
+        dbg[8 + 2 * (size_t)blockIdx.x] = tot; dbg[9 + 2 * (size_t)blockIdx.x] = t_early;       // per block: total, early rounds
+    }
 }
 
 // draw offset at the end of chunk r of group gd, for the walker that entered the group at offset k: the class of its
