@@ -183,8 +183,8 @@ def run(args, D):
         "roofline": {"bound": "hbm", "kernel": "emit_kernel", "achieved": emit_bytes / (emit_ms / 1e3) / 1e9 if emit_ms else None,
                      "peak": peak, "unit": "GB/s", "frac": emit_bytes / (emit_ms / 1e3) / 1e9 / peak if emit_ms else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one emit_kernel launch of this exact workload, from the
-                     # ncu --set full capture summarised in profiles/r01_emit_kernel_ncu.txt (15.225 GB + 14.192 GB)
-                     "traffic": 29.416676e9 if args.scale == 1.0 else None,
+                     # ncu --set full capture summarised in profiles/r01_emit_kernel_ncu.txt (15.294 GB + 14.206 GB)
+                     "traffic": 29.499585e9 if args.scale == 1.0 else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * out_bytes, "kernel_ms_avg": emit_ms / max(1, emit_n),
                      "kernel_share_of_step": emit_ms / ms if ms else None,
                      "parse_kernel": {"achieved": n * args.steps / (parse_ms / 1e3) / 1e9 if parse_ms else None, "kernel_ms_avg": parse_ms / max(1, parse_n),
