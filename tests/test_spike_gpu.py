@@ -3,6 +3,7 @@ oracle restatement -- SAM bytes, truth.vcf and the stats block must be identical
 import os
 import shutil
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -215,3 +216,46 @@ def test_cli_usage_and_errors(tmp_path, ctx):
     assert r.returncode == 1 and b"Couldn't open bam" in r.stderr
     r = subprocess.run([sc.PRODUCT, prefix + ".sam", prefix + ".fa", "/nonexistent.spike", "1", "o.sam"], cwd=tmp_path, capture_output=True)
     assert r.returncode == 255
+
+
+def test_large_properties(ctx, monkeypatch):
+    """Size-independent properties on a chr19-length input (C2's generator at 5x: ~1.95 M reads, ~0.7 GB, 58.6 M covered loci),
+    too large for the CPU oracle: (a) without targets the output is the input's lines in another order (same bytes, same
+    line lengths); (b) with the 10,000 targets the lines stay where they are and only A/C/G/T bytes change, no more than
+    two per pileup entry; (c) the chunked chain (grouped, sliced phase 1 at its production geometry) gives byte for byte
+    what the one-warp serial chain gives, with the same draw count and per-target results; (d) a second run repeats it."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import bench_spike as bs
+    L = bs.synth_lib()
+    ref, parts, n_reads, spike_text = bs.make_workload(L, 2, bs.CHR19, 5.0, 10_000)
+    body = np.concatenate(parts).tobytes()
+    del parts
+    names = ["chr19"]
+    targets = sp.parse_spike(spike_text, names)
+    key = lambda r: (r.status, r.at_pos, r.filter, r.ref_cnt, r.mut_cnt, tuple(r.err_cnt), r.rng_offset, r.mutant_allele)
+    with sp.Spike(ctx, names, {"chr19": ref.tobytes()}) as s:
+        out0, _, st0 = s.run_host(body, [], 434)
+        out_p, res_p, st_p = s.run_host(body, targets, 434)
+        out_p2, res_p2, st_p2 = s.run_host(body, targets, 434)
+        monkeypatch.setenv("SSB_CHAIN_SERIAL", "1")
+        out_s, res_s, st_s = s.run_host(body, targets, 434)
+    a, b0 = np.frombuffer(body, dtype=np.uint8), np.frombuffer(out0, dtype=np.uint8)
+    # (a)
+    assert st0.as_dict()["n_kept"] == n_reads and len(out0) == len(body)
+    assert np.array_equal(np.bincount(a, minlength=256), np.bincount(b0, minlength=256))
+    la = np.sort(np.diff(np.flatnonzero(a == 10), prepend=-1)); lb = np.sort(np.diff(np.flatnonzero(b0 == 10), prepend=-1))
+    assert np.array_equal(la, lb)
+    # (b)
+    bp = np.frombuffer(out_p, dtype=np.uint8)
+    assert len(out_p) == len(out0)
+    d = np.flatnonzero(bp != b0)
+    n_entries = sum(r.ref_cnt + r.mut_cnt + sum(r.err_cnt) for r in res_p)
+    assert 0 < d.size <= 2 * max(1, n_entries)
+    assert set(np.unique(bp[d]).tolist()) <= set(b"ACGT")
+    assert np.array_equal(np.flatnonzero(bp == 10), np.flatnonzero(b0 == 10))
+    # (c), (d)
+    assert st_p.chain_mode > 1 and st_s.chain_mode == 1
+    assert out_p == out_s and out_p == out_p2
+    assert st_p.rng_draws == st_s.rng_draws == st_p2.rng_draws
+    assert [key(r) for r in res_p] == [key(r) for r in res_s] == [key(r) for r in res_p2]
