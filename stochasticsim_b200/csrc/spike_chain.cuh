@@ -191,8 +191,9 @@ struct EntryOut {
     bool ok;
 };
 
+// have_first: the caller already holds rand() #k (first_r), fetched together with its neighbours' draws
 __device__ EntryOut entry_eval(const ChainArgs &A, const PlpEntry &e, uint8_t mate_base, uint8_t mate_bq, bool mate_handled, bool self_handled,
-                               unsigned long long k, uint32_t thresh, uint8_t F, uint8_t Aallele)
+                               unsigned long long k, uint32_t thresh, uint8_t F, uint8_t Aallele, bool have_first = false, uint32_t first_r = 0)
 {
     EntryOut o; o.draws = 0; o.mark_self = o.mark_mate = o.filt = o.tally = o.npatch = 0; o.ok = true;
     o.pbase[0] = o.pbase[1] = o.pmate[0] = o.pmate[1] = 0;
@@ -206,7 +207,8 @@ __device__ EntryOut entry_eval(const ChainArgs &A, const PlpEntry &e, uint8_t ma
     if (base == 'N') { o.mark_self = 1; o.mark_mate = M ? 1 : 0; return o; }         // :584-592
     const unsigned long long k0 = k;
     uint32_t r;
-    if (!next_rand(A, k, r)) { o.ok = false; return o; }
+    if (have_first) { if (k + 64 > A.M) { o.ok = false; return o; } r = first_r; k++; }
+    else if (!next_rand(A, k, r)) { o.ok = false; return o; }
     const bool heads = r < thresh;                                                    // coinToss :332-335
     auto tally_base = [&](uint8_t b) { int gi = gcat_index(b); o.tally = gi < 4 ? (uint8_t)(3 + gi) : 0; };
     auto other = [&](uint8_t &d) -> bool {                                            // selectMutantAllele(A)
@@ -622,11 +624,23 @@ chain_kernel(ChainArgs A, const ChunkDesc *__restrict__ chunks, int n_chunks, un
         __syncwarp();
         const unsigned int n_odd = min(*(volatile unsigned int *)A.n_odd, A.odd_cap);
         unsigned long long new_bloom = 0;
+        // the entries of the next batch and the 32 draws a batch can toss with are fetched ahead, so that a batch waits for
+        // one round trip to memory (mates, handled flags) instead of three
+        PlpEntry e_pref; e_pref.skip = 1; e_pref.bq = 0; e_pref.mate = -1; e_pref.base = 0; e_pref.ord = 0; e_pref.qpos = 0; e_pref.pad = 0;
+        uint32_t pref_j0 = 0xffffffffu;
         while (j0 < n) {
             const uint32_t j = j0 + lane;
             const bool in = j < n;
-            PlpEntry e; e.skip = 1; e.bq = 0; e.mate = -1; e.base = 0; e.ord = 0; e.qpos = 0;
-            if (in) e = ents[j];
+            PlpEntry e; e.skip = 1; e.bq = 0; e.mate = -1; e.base = 0; e.ord = 0; e.qpos = 0; e.pad = 0;
+            if (pref_j0 == j0) e = e_pref; else if (in) e = ents[j];
+            {
+                const uint32_t jn = j0 + 32u + lane;
+                e_pref.skip = 1; e_pref.bq = 0; e_pref.mate = -1; e_pref.base = 0; e_pref.ord = 0; e_pref.qpos = 0;
+                if (jn < n) e_pref = ents[jn];
+                pref_j0 = j0 + 32u;
+            }
+            const bool r_ok = k + 96ull <= A.M;
+            const uint32_t r_spec = r_ok ? (uint32_t)A.R[k + lane] : 0u;
             const bool handled = in ? hf[j] != 0 : true;
             uint8_t mate_base = 0, mate_bq = 0; PlpEntry me_; me_.ord = 0; me_.qpos = 0; me_.skip = 0;
             bool mate_handled = false;
@@ -646,8 +660,10 @@ chain_kernel(ChainArgs A, const ChunkDesc *__restrict__ chunks, int n_chunks, un
                 tosses = base != 'N';
             }
             const unsigned tossmask = __ballot_sync(0xffffffffu, tosses);
-            const unsigned long long my_k = k + __popc(tossmask & ((1u << lane) - 1u));
-            EntryOut o = entry_eval(A, e, mate_base, mate_bq, mate_handled, handled, my_k, ht.thresh, Fb, allele);
+            const uint32_t my_idx = __popc(tossmask & ((1u << lane) - 1u));
+            const unsigned long long my_k = k + my_idx;
+            const uint32_t my_r = __shfl_sync(0xffffffffu, r_spec, my_idx);
+            EntryOut o = entry_eval(A, e, mate_base, mate_bq, mate_handled, handled, my_k, ht.thresh, Fb, allele, r_ok, my_r);
             // a lane "breaks" the speculation of the lanes after it when it used more than its one draw, or
             // when it marks an entry of this batch as handled
             const bool marks_in_batch = in && o.mark_mate && e.mate >= 0 && (uint32_t)e.mate < j0 + 32;
