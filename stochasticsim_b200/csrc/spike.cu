@@ -59,7 +59,8 @@ struct MaxOp { template <typename T> __device__ __forceinline__ T operator()(con
 __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ kord,
                                const unsigned long long *__restrict__ pkey, const unsigned long long *__restrict__ pmax,
                                uint32_t *__restrict__ k_rec, unsigned long long *__restrict__ k_start, unsigned long long *__restrict__ k_end,
-                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ fold, unsigned int *__restrict__ maxspan, DevErr *err)
+                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ k_hash, uint32_t *__restrict__ k_hash32,
+                               unsigned long long *__restrict__ fold, unsigned int *__restrict__ maxspan, DevErr *err)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long span = 0;
@@ -72,6 +73,7 @@ __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const 
             k_start[o] = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.pos;
             k_end[o] = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.end;
             k_len[o] = r.line_len + ((r.bits & REC_NO_NL) ? 1u : 0u);
+            k_hash[o] = r.qhash; k_hash32[o] = (uint32_t)r.qhash ^ (uint32_t)(r.qhash >> 32);
             span = (unsigned long long)(r.end - r.pos);
         }
     }
@@ -108,13 +110,13 @@ __device__ bool same_qname(const uint8_t *sam, const SamRec &a, const SamRec &b)
 
 __global__ void mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
                              const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ k_end,
-                             const unsigned long long *__restrict__ k_hash, size_t K, uint32_t *__restrict__ nxt, uint32_t *__restrict__ prv,
+                             const uint32_t *__restrict__ k_hash32, size_t K, uint32_t *__restrict__ nxt, uint32_t *__restrict__ prv,
                              uint8_t *__restrict__ cplx)
 {
     size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= K) return;
     const unsigned long long lim = k_end[o];       // same tid, pos < end  <=>  start key < end key
-    const unsigned long long h = k_hash[o];
+    const uint32_t h = k_hash32[o];                // candidates by a 32-bit fold of the QNAME hash; same_qname() decides
     uint32_t first = NO_MATE; bool more = false;
     // reads that start inside this read's span: [o + 1, hi).  The bound is found once (galloping, then bisection), so the
     // scan itself only touches the hashes.
@@ -126,22 +128,25 @@ __global__ void mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__re
         if (hi > K) hi = K;
         while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (k_start[mid] < lim) lo = mid + 1; else hi = mid; }
     }
-    for (size_t b = o + 1; b < hi; b++) {
-        if (k_hash[b] != h) continue;
+    for (size_t b0 = o + 1; b0 < hi; b0 += 4) {
+      // four candidates per step: the loads do not depend on each other
+      uint32_t hb[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) hb[u] = (b0 + u < hi) ? k_hash32[b0 + u] : ~h;
+      if (hb[0] != h && hb[1] != h && hb[2] != h && hb[3] != h) continue;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const size_t b = b0 + u;
+        if (hb[u] != h || b >= hi) continue;
         if (!same_qname(sam, recs[k_rec[o]], recs[k_rec[b]])) continue;
         if (first == NO_MATE) { first = (uint32_t)b; prv[b] = (uint32_t)o; }    // injective: see DESIGN.md (mate links)
         else {
             // three or more same-name reads overlap: every member takes the exact brute-force path
             more = true; cplx[o] = 1; cplx[first] = 1; cplx[b] = 1;
         }
+      }
     }
     nxt[o] = first | (more ? MATE_MORE : 0u);
-}
-
-__global__ void khash_kernel(const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec, size_t K, unsigned long long *__restrict__ k_hash)
-{
-    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < K) k_hash[o] = recs[k_rec[o]].qhash;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1140,7 +1145,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
 
     // ---------------------------------------------------------------- keep / sortedness / compaction
     size_t K = 0;
-    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL, *prv = NULL; uint8_t *cplx = NULL; unsigned long long *err64 = NULL; unsigned int *minus = NULL; unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL;
+    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL, *prv = NULL; uint8_t *cplx = NULL; unsigned long long *err64 = NULL; unsigned int *minus = NULL; unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL; uint32_t *k_hash32 = NULL;
     unsigned long long *d_fold = ar.get<unsigned long long>(1); unsigned int *d_maxspan = ar.get<unsigned int>(1), *d_maxdepth = ar.get<unsigned int>(1);
     SPK_CHECK_ARENA(ar);
     SSB_CUDA(ctx, cudaMemsetAsync(d_fold, 0, sizeof(unsigned long long), s));
@@ -1160,10 +1165,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         K = (size_t)last_ord + last_keep;
         k_rec = ar.get<uint32_t>(K); k_len = ar.get<uint32_t>(K); nxt = ar.get<uint32_t>(K);
-        k_start = ar.get<unsigned long long>(K); k_end = ar.get<unsigned long long>(K); k_hash = ar.get<unsigned long long>(K);
+        k_start = ar.get<unsigned long long>(K); k_end = ar.get<unsigned long long>(K); k_hash = ar.get<unsigned long long>(K); k_hash32 = ar.get<uint32_t>(K);
         SPK_CHECK_ARENA(ar);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, compact_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, kord, pkey, pmax, k_rec, k_start, k_end, k_len,
-                     d_fold, d_maxspan, d_err);
+                     k_hash, k_hash32, d_fold, d_maxspan, d_err);
         if ((rc = dev_error(ctx, s, d_err, "sorted"))) return rc;
     }
     stats->n_kept = (int64_t)K;
@@ -1211,11 +1216,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     // ---------------------------------------------------------------- mates, coverage runs, classes, depth
     if (K) {
         int rc;
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, khash_kernel, grid_for(K, 256), 256, 0, s, recs, k_rec, K, k_hash);
         prv = ar.get<uint32_t>(K); cplx = ar.get<uint8_t>(K); SPK_CHECK_ARENA(ar);
         SSB_CUDA(ctx, cudaMemsetAsync(prv, 0xff, K * sizeof(uint32_t), s));
         SSB_CUDA(ctx, cudaMemsetAsync(cplx, 0, K, s));
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, mates_kernel, grid_for(K, 128), 128, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash, K, nxt, prv, cplx);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, mates_kernel, grid_for(K, 128), 128, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash32, K, nxt, prv, cplx);
         unsigned long long *pm = ar.get<unsigned long long>(K); uint32_t *rflag = ar.get<uint32_t>(K), *rid = ar.get<uint32_t>(K);
         SPK_CHECK_ARENA(ar);
         if ((rc = scan_max_excl(ar, ctx, k_end, pm, K, 0ull))) return rc;
