@@ -803,14 +803,77 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         const uint32_t first = s_first;
         uint32_t my_base = first + warp_base + incl - cnt;
         const uint32_t n_here = first + total;
-        // 3. decoupled look-back for the global index of this tile's first line.  The frontier of known inclusive
-        //    prefixes moves one window per L2 round trip, so the window is wide: warp 0 inspects 256 predecessors per hop.
+        // 3a. this tile's line count is published at once; the look-back itself (3b) runs on warp 0 while the other warps parse
+        if (tid_ == 0) atomicExch(&tile_state[tile], (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)n_here);
+        if (n_here > MAX_LINES) {                                      // > 2048 lines in 32 KiB cannot be SAM
+            if (tid_ == 0 && atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = T0;
+            // 3b. decoupled look-back for the global index of this tile's first line.  The frontier of known inclusive
+            //     prefixes moves one window per L2 round trip, so the window is wide: warp 0 inspects 256 predecessors per hop.
+            if (wid == 0) {
+                unsigned long long excl = 0;
+                volatile unsigned long long *ts = tile_state;
+                if (tile != 0) {
+                    long long j = (long long)tile - 1;
+                    for (;;) {
+                        const long long hi = j - 8 * lane;                     // this lane looks at tiles hi, hi-1, .. hi-7
+                        unsigned long long v[8];
+    #pragma unroll
+                        for (int k = 0; k < 8; k++) { v[k] = 2ull << 62; if (hi - k >= 0) v[k] = ts[hi - k]; }     // before tile 0: inclusive prefix 0
+                        unsigned long long sum = 0; bool has_inc = false;
+    #pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            if (has_inc) continue;
+                            while ((v[k] & ST_MASK) == 0) v[k] = ts[hi - k];                      // not published yet
+                            sum += v[k] & ~ST_MASK;
+                            has_inc = (v[k] & ST_MASK) == ST_INC;
+                        }
+                        const unsigned inc = __ballot_sync(0xffffffffu, has_inc);
+                        const int first = inc ? __ffs(inc) - 1 : 31;           // nearest lane that met an inclusive prefix
+                        unsigned long long c = lane <= first ? sum : 0ull;
+    #pragma unroll
+                        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                        excl += c;
+                        if (inc) break;
+                        j -= 256;
+                    }
+                    if (lane == 0) atomicExch(&tile_state[tile], ST_INC | (excl + n_here));
+                }
+                if (lane == 0) { s_base = excl; if (tile == n_tiles - 1) *n_lines_out = excl + n_here; }
+            }
+            __syncthreads();
+            continue;
+        }
+        if (tid_ == 0 && first) starts[0] = 0;
+        if (cnt) {
+#pragma unroll
+            for (int k = 0; k < CPT; k++) {
+                uint32_t m = mym[k];
+                while (m) {
+                    int b = __ffs(m) - 1; m &= m - 1;
+                    starts[my_base++] = (uint16_t)((CPT * tid_ + k) * 16 + b + 1);
+                }
+            }
+        }
+        __syncthreads();
+        // 4. one line per thread of warps 1..3.  The last line of the tile ends in the overhang (or beyond): warp 0 finds its newline.
+        Cursor cur{text, body, T0, stage_end, n};
+        if (wid == 0 && n_here > 0) {
+            size_t e = T0 + starts[n_here - 1] + lane;
+            for (;;) {
+                const bool hit = e >= n || cur.at(e) == '\n';
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) { e = e - lane + (__ffs(m) - 1); break; }
+                e += 32;
+            }
+            if (lane == 0) s_last_end = e > n ? n : e;
+        }
+        __syncthreads();
+        // 3b. decoupled look-back for the global index of this tile's first line.  The frontier of known inclusive
+        //     prefixes moves one window per L2 round trip, so the window is wide: warp 0 inspects 256 predecessors per hop.
         if (wid == 0) {
             unsigned long long excl = 0;
             volatile unsigned long long *ts = tile_state;
-            if (tile == 0) { if (lane == 0) atomicExch(&tile_state[0], ST_INC | (unsigned long long)n_here); }
-            else {
-                if (lane == 0) atomicExch(&tile_state[tile], ST_AGG | (unsigned long long)n_here);
+            if (tile != 0) {
                 long long j = (long long)tile - 1;
                 for (;;) {
                     const long long hi = j - 8 * lane;                     // this lane looks at tiles hi, hi-1, .. hi-7
@@ -838,40 +901,10 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             }
             if (lane == 0) { s_base = excl; if (tile == n_tiles - 1) *n_lines_out = excl + n_here; }
         }
-        if (n_here > MAX_LINES) {                                      // > 2048 lines in 32 KiB cannot be SAM
-            if (tid_ == 0 && atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = T0;
-            __syncthreads();
-            continue;
-        }
-        if (tid_ == 0 && first) starts[0] = 0;
-        if (cnt) {
-#pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                uint32_t m = mym[k];
-                while (m) {
-                    int b = __ffs(m) - 1; m &= m - 1;
-                    starts[my_base++] = (uint16_t)((CPT * tid_ + k) * 16 + b + 1);
-                }
-            }
-        }
-        __syncthreads();
-        const unsigned long long gbase = s_base;
-        // 4. one line per thread.  The last line of the tile ends in the overhang (or beyond): warp 0 finds its newline.
-        Cursor cur{text, body, T0, stage_end, n};
-        if (wid == 0 && n_here > 0) {
-            size_t e = T0 + starts[n_here - 1] + lane;
-            for (;;) {
-                const bool hit = e >= n || cur.at(e) == '\n';
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) { e = e - lane + (__ffs(m) - 1); break; }
-                e += 32;
-            }
-            if (lane == 0) s_last_end = e > n ? n : e;
-        }
-        __syncthreads();
-        // 4a. heads.  Thread t takes line t of the tile; the lanes of a warp stay together (parse_head_conv).  A line that is
-        //     not of the common shape, or does not end inside the staged window, is parsed by the careful functions at once.
-        const uint32_t li = (uint32_t)(lane * (THREADS / 32) + wid);      // consecutive lines go to different warps: all warps share the parsing
+        // 4a. heads.  The threads of warps 1..3 take one line each; the lanes of a warp stay together (parse_head_conv).  A line that
+        //     is not of the common shape, or does not end inside the staged window, is parsed by the careful functions at once.
+        constexpr uint32_t PARSERS = THREADS - 32;                         // warp 0 serves (look-back, last newline); the others parse
+        const uint32_t li = wid ? (uint32_t)(lane * (THREADS / 32 - 1) + (wid - 1)) : 0xffffffffu;   // consecutive lines go to different warps
         const bool have = li < n_here;
         const unsigned wmask = __ballot_sync(0xffffffffu, have);
         SamRec r; int rc = 0; bool fast = false; uint32_t qend = 0, lo = 0, len = 0; size_t ls = 0;
@@ -887,8 +920,20 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             } else rc = parse_line(cur, ls, e, names, tid_cache, r);
             if (!rc && r.tid >= 0) tid_cache = r.tid;
         }
-        // tiles of very short lines: the lines beyond the first THREADS take the careful path, one per thread (before the line starts give way to the exception buffer)
-        for (uint32_t i = li + THREADS; i < n_here; i += THREADS) {
+        // the reference window under the tile's reads: lowest (tid, pos) among the reads that align 1:1
+        const bool elig = fast && names.exc && (r.bits & REC_KEEP) && (r.bits & REC_SIMPLE) && r.l_seq < 65536u &&
+                          names.seq[r.tid] && (int64_t)r.end <= names.len[r.tid];
+        if (names.exc) {
+            const int tmin = __reduce_min_sync(0xffffffffu, elig ? r.tid : 0x7fffffff);
+            const int pmin = __reduce_min_sync(0xffffffffu, (elig && r.tid == tmin) ? r.pos : 0x7fffffff);
+            const int emax = __reduce_max_sync(0xffffffffu, (elig && r.tid == tmin) ? r.end : 0);
+            if (lane == 0) s_wkey[wid] = make_int4(tmin, pmin, emax, 0);
+        }
+        __syncthreads();
+        const unsigned long long gbase = s_base;                           // warp 0 finished the look-back before this barrier
+        const unsigned long long gi = gbase + li;
+        // tiles of very short lines: the lines beyond the first PARSERS take the careful path, one per thread (before the line starts give way to the exception buffer)
+        for (uint32_t i = wid ? li + PARSERS : 0xffffffffu; i < n_here; i += PARSERS) {
             const size_t s = T0 + starts[i];
             const size_t e = (i + 1 < n_here) ? T0 + starts[i + 1] - 1 : (size_t)s_last_end;
             SamRec r2; int rc2;
@@ -899,17 +944,6 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (g2 < rec_cap) recs[g2] = r2;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
         }
-        const unsigned long long gi = gbase + li;
-        // the reference window under the tile's reads: lowest (tid, pos) among the reads that align 1:1
-        const bool elig = fast && names.exc && (r.bits & REC_KEEP) && (r.bits & REC_SIMPLE) && r.l_seq < 65536u && gi < rec_cap && gi < (1ull << 47) &&
-                          names.seq[r.tid] && (int64_t)r.end <= names.len[r.tid];
-        if (names.exc) {
-            const int tmin = __reduce_min_sync(0xffffffffu, elig ? r.tid : 0x7fffffff);
-            const int pmin = __reduce_min_sync(0xffffffffu, (elig && r.tid == tmin) ? r.pos : 0x7fffffff);
-            const int emax = __reduce_max_sync(0xffffffffu, (elig && r.tid == tmin) ? r.end : 0);
-            if (lane == 0) s_wkey[wid] = make_int4(tmin, pmin, emax, 0);
-        }
-        __syncthreads();
         bool in_win = false; int32_t w_lo = 0; int wtid = -1;
         if (names.exc) {
             int emax = 0; int pmin = 0x7fffffff; wtid = 0x7fffffff;
@@ -929,7 +963,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                     const uint32_t x = __funnelshift_r(__ldg(rw + w), __ldg(rw + w + 1), ra * 8);
                     dw[w] = x | ((non_acgtn_bytes(x) >> 7) * 0xffu);           // anything but A C G T N can never equal a valid SEQ byte
                 }
-                in_win = elig && r.tid == wtid && r.pos >= w_lo && r.end <= w_lo + REFW;
+                in_win = elig && gi < rec_cap && gi < (1ull << 47) && r.tid == wtid && r.pos >= w_lo && r.end <= w_lo + REFW;
             } else wtid = -1;
         }
         __syncthreads();
