@@ -358,21 +358,6 @@ __device__ __forceinline__ size_t lower_bound_u64(const unsigned long long *a, s
     return lo;
 }
 
-// maxDepth (stochasticSpike.c:1216): the deepest pileup is reached at some read start
-__global__ void depth_kernel(const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ s_end, size_t K,
-                             unsigned int *__restrict__ max_depth)
-{
-    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int d = 0;
-    if (o < K && (o + 1 == K || k_start[o + 1] != k_start[o])) {          // last read of a group of equal starts
-        const unsigned long long key = k_start[o];
-        size_t ended = upper_bound_u64(s_end, K, key);                     // reads with (tid,end) <= (tid,pos): gone before this locus
-        d = (unsigned int)(o + 1 - ended);
-    }
-    for (int s = 16; s; s >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, s));
-    if ((threadIdx.x & 31) == 0 && d) atomicMax(max_depth, d);
-}
-
 // ------------------------------------------------------------------------------------------
 // targets (stochasticSpike.c:1234-1245, :1578-1619, :1630-1646)
 // ------------------------------------------------------------------------------------------
@@ -392,6 +377,31 @@ __device__ int64_t lb_ordinal(const CovRun *runs, size_t R, int64_t n_cov, int32
     const CovRun r = runs[lo];
     if (r.tid == c_tid && locus > r.start) return r.base + (locus - r.start);
     return r.base;
+}
+
+// Per covered locus g: cs[g] = kept reads that start at or before it, ce[g] = kept reads that end at or before it (end exclusive),
+// so that the pileup depth is cs[g] - ce[g] without a search.  One pass over the reads in start order and one in end order: the
+// last read of a group of equal keys fills the loci up to the next key (never more than one read span).
+__global__ void cum_fill_kernel(const unsigned long long *__restrict__ keys, size_t K, const CovRun *__restrict__ runs, size_t R, int64_t n_cov,
+                                uint32_t *__restrict__ out)
+{
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= K) return;
+    const unsigned long long key = keys[o];
+    if (o + 1 < K && keys[o + 1] == key) return;
+    const int64_t g0 = lb_ordinal(runs, R, n_cov, (int32_t)(key >> 32), (int64_t)(uint32_t)key);
+    int64_t g1 = n_cov;
+    if (o + 1 < K) { const unsigned long long nk = keys[o + 1]; g1 = lb_ordinal(runs, R, n_cov, (int32_t)(nk >> 32), (int64_t)(uint32_t)nk); }
+    for (int64_t g = g0; g < g1; g++) out[g] = (uint32_t)(o + 1);
+}
+
+// maxDepth (stochasticSpike.c:1216)
+__global__ void maxdepth_kernel(const uint32_t *__restrict__ cs, const uint32_t *__restrict__ ce, int64_t n_cov, unsigned int *__restrict__ max_depth)
+{
+    unsigned int d = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_cov; g += (int64_t)gridDim.x * blockDim.x) d = max(d, cs[g] - ce[g]);
+    for (int s = 16; s; s >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, s));
+    if ((threadIdx.x & 31) == 0 && d) atomicMax(max_depth, d);
 }
 
 __global__ void target_lb_kernel(const DevTarget *__restrict__ tg, size_t T, const CovRun *__restrict__ runs, size_t R, int64_t n_cov, long long *__restrict__ v)
@@ -902,15 +912,14 @@ __global__ void tally_flag_kernel(const unsigned long long *__restrict__ err64, 
 
 __global__ void tally_emit_kernel(const unsigned long long *__restrict__ err64, const unsigned int *__restrict__ minus, const uint32_t *__restrict__ flag,
                                   const uint32_t *__restrict__ idx, int64_t n_cov, const CovRun *__restrict__ runs, size_t R,
-                                  const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ s_end, size_t K,
+                                  const uint32_t *__restrict__ cum_s, const uint32_t *__restrict__ cum_e,
                                   const uint8_t *const *__restrict__ contig_seq, ssb_seq_error *__restrict__ out)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_cov || !flag[g]) return;
     size_t ri = run_of_ordinal(runs, R, g);
     const int tid = runs[ri].tid; const int64_t x = runs[ri].start + (g - runs[ri].base);
-    const unsigned long long key = ((unsigned long long)(uint32_t)tid << 32) | (uint32_t)x;
-    const long long depth = (long long)upper_bound_u64(k_start, K, key) - (long long)upper_bound_u64(s_end, K, key);
+    const long long depth = (long long)cum_s[g] - (long long)cum_e[g];
     ssb_seq_error e;
     memset(&e, 0, sizeof e);
     e.tid = tid; e.pos = x; e.locus_index = g;
@@ -1178,7 +1187,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
     // ---------------------------------------------------------------- output order + emit
     size_t R = 0; int64_t n_cov = 0;
     CovRun *runs = NULL; uint8_t *cls = NULL;
-    uint32_t *perm = NULL; unsigned long long *s_end = NULL, *out_off = NULL, *ord_off = NULL;
+    uint32_t *perm = NULL, *cum_s = NULL, *cum_e = NULL; unsigned long long *s_end = NULL, *out_off = NULL, *ord_off = NULL;
     unsigned long long total_out = 0;
     if (K) {
         int rc;
@@ -1241,7 +1250,11 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaMemcpyAsync(&ll, rlen + R - 1, 8, cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         n_cov = (int64_t)(lb + ll);
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, depth_kernel, grid_for(K, 256), 256, 0, s, k_start, s_end, K, d_maxdepth);
+        cum_s = ar.get<uint32_t>((size_t)n_cov + 1); cum_e = ar.get<uint32_t>((size_t)n_cov + 1); SPK_CHECK_ARENA(ar);
+        SSB_CUDA(ctx, cudaMemsetAsync(cum_e, 0, ((size_t)n_cov + 1) * sizeof(uint32_t), s));       // loci before the first read end
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, cum_fill_kernel, grid_for(K, 256), 256, 0, s, k_start, K, runs, R, n_cov, cum_s);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, cum_fill_kernel, grid_for(K, 256), 256, 0, s, s_end, K, runs, R, n_cov, cum_e);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, maxdepth_kernel, ctx->sm_count * 8, 256, 0, s, cum_s, cum_e, n_cov, d_maxdepth);
     }
     stats->n_runs = (int64_t)R;
     stats->numberOfLociCovered = n_cov;
@@ -1549,7 +1562,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         if (sp->n_se) {
             SSB_CUDA(ctx, cudaMallocAsync((void **)&sp->d_se, sp->n_se * sizeof(ssb_seq_error), s));
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, tally_emit_kernel, grid_for((size_t)n_cov, 256), 256, 0, s, err64, minus, sflag, sidx, n_cov, runs, R,
-                         k_start, s_end, K, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_se);
+                         cum_s, cum_e, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_se);
         }
     }
     dbg_mark("emit");
