@@ -179,7 +179,9 @@ typedef struct ssb_spike_stats {
 int  ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_contigs, ssb_spike **out);
 void ssb_spike_destroy(ssb_spike *sp);
 
-/* Run on alignment lines already in HBM (d_sam 16-byte aligned).  The output lines are written to
+/* Run on alignment lines already in HBM (d_sam 16-byte aligned; the allocation behind it must extend at
+ * least 32 bytes past n -- the copy kernel reads whole 16-byte words, their contents past n are ignored;
+ * ssb_spike_run_host pads its own staging buffer).  The output lines are written to
  * d_out (capacity out_cap >= n + 1 is always enough); *out_bytes gets their size.  results[] has
  * n_targets entries.  Device work is asynchronous internally but the call returns synchronised.
  * This is the call bench.py times for `value`. */

@@ -59,7 +59,7 @@ struct MaxOp { template <typename T> __device__ __forceinline__ T operator()(con
 __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ kord,
                                const unsigned long long *__restrict__ pkey, const unsigned long long *__restrict__ pmax,
                                uint32_t *__restrict__ k_rec, unsigned long long *__restrict__ k_start, unsigned long long *__restrict__ k_end,
-                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ k_hash, uint32_t *__restrict__ k_hash32,
+                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ k_hash, uint32_t *__restrict__ k_hash32, uint8_t *__restrict__ k_bits,
                                unsigned long long *__restrict__ fold, unsigned int *__restrict__ maxspan, DevErr *err)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +73,7 @@ __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const 
             k_start[o] = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.pos;
             k_end[o] = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.end;
             k_len[o] = r.line_len + ((r.bits & REC_NO_NL) ? 1u : 0u);
-            k_hash[o] = r.qhash; k_hash32[o] = (uint32_t)r.qhash ^ (uint32_t)(r.qhash >> 32);
+            k_hash[o] = r.qhash; k_hash32[o] = (uint32_t)r.qhash ^ (uint32_t)(r.qhash >> 32); k_bits[o] = r.bits;
             span = (unsigned long long)(r.end - r.pos);
         }
     }
@@ -620,7 +620,7 @@ __device__ __forceinline__ void base_at(const ReadView &v, int32_t x, uint8_t &b
 }
 
 struct TallyArgs {
-    const uint8_t *sam; const SamRec *recs; const uint32_t *k_rec; const unsigned long long *k_start, *k_end, *k_hash; size_t K;
+    const uint8_t *sam; const SamRec *recs; const uint32_t *k_rec; const unsigned long long *k_start, *k_end, *k_hash; const uint8_t *k_bits; size_t K;
     const uint32_t *nxt, *prv; const uint8_t *cplx; unsigned int maxspan;
     const CovRun *runs; size_t R; const uint8_t *const *contig_seq; const int64_t *contig_len;
     unsigned long long *err64; unsigned int *minus; DevErr *err;
@@ -667,7 +667,7 @@ __device__ __forceinline__ void tally_add(const TallyArgs &A, int64_t g, int con
 // patch touched any of them.
 __device__ __forceinline__ bool tally_simple_read(const TallyArgs &A, size_t o, unsigned int n_odd, unsigned long long bloom)
 {
-    if (!(A.recs[A.k_rec[o]].bits & REC_SIMPLE) || A.cplx[o]) return false;
+    if (!(A.k_bits[o] & REC_SIMPLE) || A.cplx[o]) return false;
     if (n_odd && (bloom & odd_bit((uint32_t)o))) return false;
     return true;
 }
@@ -687,10 +687,10 @@ __device__ __forceinline__ bool tally_is_fast(const TallyArgs &A, size_t o, cons
 // read is self-contained work of tally_kernel.
 __device__ __forceinline__ bool tally_is_listed(const TallyArgs &A, size_t o, const SamRec &r, unsigned int n_odd, unsigned long long bloom)
 {
-    if (!(r.bits & REC_EXC_DONE) || !tally_is_fast(A, o, r, n_odd, bloom)) return false;
+    if (!(A.k_bits[o] & REC_EXC_DONE) || !tally_is_fast(A, o, r, n_odd, bloom)) return false;
     const uint32_t p = A.prv[o], q = A.nxt[o] & ~MATE_MORE;
-    if (p != PRV_NONE && !(A.recs[A.k_rec[p]].bits & REC_EXC_DONE)) return false;
-    if (q != NO_MATE && !(A.recs[A.k_rec[q]].bits & REC_EXC_DONE)) return false;
+    if (p != PRV_NONE && !(A.k_bits[p] & REC_EXC_DONE)) return false;
+    if (q != NO_MATE && !(A.k_bits[q] & REC_EXC_DONE)) return false;
     return true;
 }
 
@@ -820,7 +820,7 @@ tally_resolve_kernel(TallyArgs A, const unsigned long long *__restrict__ list, u
     if (own) tally_add(A, g, chain_contribution(cov, nc, sc, x, F));
     for (int m = 0; m < nc; m++) {
         if (m == sc) continue;
-        if (!(A.recs[A.k_rec[cord[m]]].bits & REC_SIMPLE)) continue;      // a neighbour with indels is never list-settled
+        if (!(A.k_bits[cord[m]] & REC_SIMPLE)) continue;                 // a neighbour with indels is never list-settled
         uint8_t b; int bq; bool sk;
         base_at(cov[m], x, b, bq, sk);
         // a plain base of a list-settled neighbour has no entry of its own: it matters only if it was marked handled here
@@ -1154,7 +1154,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
 
     // ---------------------------------------------------------------- keep / sortedness / compaction
     size_t K = 0;
-    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL, *prv = NULL; uint8_t *cplx = NULL; unsigned long long *err64 = NULL; unsigned int *minus = NULL; unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL; uint32_t *k_hash32 = NULL;
+    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL, *prv = NULL; uint8_t *cplx = NULL; unsigned long long *err64 = NULL; unsigned int *minus = NULL; unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL; uint32_t *k_hash32 = NULL; uint8_t *k_bits = NULL;
     unsigned long long *d_fold = ar.get<unsigned long long>(1); unsigned int *d_maxspan = ar.get<unsigned int>(1), *d_maxdepth = ar.get<unsigned int>(1);
     SPK_CHECK_ARENA(ar);
     SSB_CUDA(ctx, cudaMemsetAsync(d_fold, 0, sizeof(unsigned long long), s));
@@ -1174,10 +1174,10 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         K = (size_t)last_ord + last_keep;
         k_rec = ar.get<uint32_t>(K); k_len = ar.get<uint32_t>(K); nxt = ar.get<uint32_t>(K);
-        k_start = ar.get<unsigned long long>(K); k_end = ar.get<unsigned long long>(K); k_hash = ar.get<unsigned long long>(K); k_hash32 = ar.get<uint32_t>(K);
+        k_start = ar.get<unsigned long long>(K); k_end = ar.get<unsigned long long>(K); k_hash = ar.get<unsigned long long>(K); k_hash32 = ar.get<uint32_t>(K); k_bits = ar.get<uint8_t>(K);
         SPK_CHECK_ARENA(ar);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, compact_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, kord, pkey, pmax, k_rec, k_start, k_end, k_len,
-                     k_hash, k_hash32, d_fold, d_maxspan, d_err);
+                     k_hash, k_hash32, k_bits, d_fold, d_maxspan, d_err);
         if ((rc = dev_error(ctx, s, d_err, "sorted"))) return rc;
     }
     stats->n_kept = (int64_t)K;
@@ -1528,7 +1528,7 @@ extern "C" int ssb_spike_run_device(ssb_spike *sp, const uint8_t *d_sam, size_t 
         SSB_CUDA(ctx, cudaMemcpyAsync(&h_maxspan, d_maxspan, 4, cudaMemcpyDeviceToHost, s));
         SSB_CUDA(ctx, cudaStreamSynchronize(s));
         TallyArgs TA;
-        TA.sam = d_sam; TA.recs = recs; TA.k_rec = k_rec; TA.k_start = k_start; TA.k_end = k_end; TA.k_hash = k_hash; TA.K = K;
+        TA.sam = d_sam; TA.recs = recs; TA.k_rec = k_rec; TA.k_start = k_start; TA.k_end = k_end; TA.k_hash = k_hash; TA.k_bits = k_bits; TA.K = K;
         TA.nxt = nxt; TA.prv = prv; TA.cplx = cplx; TA.maxspan = h_maxspan; TA.runs = runs; TA.R = R;
         TA.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; TA.contig_len = sp->d_lens; TA.err64 = err64; TA.minus = minus; TA.err = d_err;
         TA.odd = d_odd; TA.n_odd = d_nodd; TA.odd_bloom = d_bloom;
