@@ -2,15 +2,19 @@
 // needs, apply the reference's read filter.  (Stands in for htslib's sam_read1 + read_bam,
 // stochasticSpike.c:243-268, for SAM text input.)
 //
-// Shape: persistent blocks pull 32 KiB tiles of the body in order (atomic ticket).  A block
-//   1. stages its tile (+ an overhang for the line that runs past the end) in shared memory with
-//      16-byte loads;
+// Shape: persistent blocks (exactly the resident ones) pull 32 KiB tiles of the body in order (atomic ticket).  A block
+//   1. asks the tile it is likely to draw next into L2 and stages its own tile (+ an overhang for the line that runs past
+//      the end) in shared memory with asynchronous 16-byte copies;
 //   2. finds newlines byte-parallel: SWAR zero-byte test per 32-bit word, 16-bit mask per 16-byte
 //      chunk, block-wide exclusive scan of the per-thread popcounts -> ordered line starts;
-//   3. learns the global index of its first line from a decoupled look-back over per-tile line
-//      counts (single pass, no separate counting kernel);
-//   4. parses one line per thread out of shared memory and writes a 64-byte SamRec.
-// HBM traffic: the text is read once; 64 B per line are written.
+//   3. publishes its line count at once; warp 0 then finds the end of the tile's last line and learns the global index of
+//      the first one from a decoupled look-back over per-tile line counts (single pass, no separate counting kernel)
+//      WHILE
+//   4. warps 1..3 parse the heads (QNAME .. TLEN) of one line per thread, lanes kept together (parse_head_conv);
+//   5. all threads stage the reference window under the tile's reads; warps 1..3 then check SEQ, QUAL and the reference
+//      in one pass (long_fields), list the exceptional bases and write the 64-byte SamRecs.
+// Shared-memory regions change hands inside a tile (newline masks -> reference window, line starts -> exception buffer).
+// HBM traffic: the text is read once; 64 B per line and 8 B per exceptional base are written.
 #pragma once
 #include "common.cuh"
 #include "spike_types.cuh"
