@@ -47,6 +47,7 @@ def c2_params(L, seed, coverage):
     L.synth_default_params(C.byref(p))
     p.seed, p.read_len, p.frag_mean, p.frag_sd, p.coverage = seed, 150, 350.0, 35.0, coverage
     p.sub_rate, p.indel_rate = 0.001, 0.0001
+    p.aux_tags = int(os.environ.get("SSB_BENCH_AUX", "0"))          # development only: NM:i / RG:Z fields on every line
     return p
 
 

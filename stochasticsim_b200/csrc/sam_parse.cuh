@@ -114,44 +114,55 @@ __device__ __forceinline__ int name_lookup(const Cursor &cur, size_t p0, size_t 
 }
 
 // One optional field [p, q): TAG:TYPE:VALUE in the form htslib prints back unchanged.
-__device__ int aux_ok(const Cursor &cur, size_t p, size_t q)
+template <typename AT>       // at(i): byte i of the body
+__device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
 {
-    if (q - p < 5 || cur.at(p + 2) != ':' || cur.at(p + 4) != ':') return SSB_E_FORMAT;
-    uint8_t ty = cur.at(p + 3);
+    if (q - p < 5 || at(p + 2) != ':' || at(p + 4) != ':') return SSB_E_FORMAT;
+    uint8_t ty = at(p + 3);
     size_t v = p + 5;
     auto canon_int = [&](size_t a, size_t b) {
-        if (a < b && cur.at(a) == '-') a++;
+        if (a < b && at(a) == '-') a++;
         if (a >= b) return false;
-        if (b - a > 1 && cur.at(a) == '0') return false;
+        if (b - a > 1 && at(a) == '0') return false;
         if (b - a > 10) return false;
-        for (size_t i = a; i < b; i++) { uint8_t c = cur.at(i); if (c < '0' || c > '9') return false; }
-        return !(b - a == 1 && cur.at(a) == '0' && a > v && cur.at(a - 1) == '-');      // "-0"
+        for (size_t i = a; i < b; i++) { uint8_t c = at(i); if (c < '0' || c > '9') return false; }
+        return !(b - a == 1 && at(a) == '0' && a > v && at(a - 1) == '-');      // "-0"
     };
     switch (ty) {
-    case 'A': return (q - v == 1 && cur.at(v) >= '!' && cur.at(v) <= '~') ? 0 : SSB_E_FORMAT;
+    case 'A': return (q - v == 1 && at(v) >= '!' && at(v) <= '~') ? 0 : SSB_E_FORMAT;
     case 'i': return canon_int(v, q) ? 0 : SSB_E_FORMAT;
-    case 'Z': for (size_t i = v; i < q; i++) { uint8_t c = cur.at(i); if (c < ' ' || c > '~') return SSB_E_FORMAT; } return 0;
+    case 'Z': for (size_t i = v; i < q; i++) { uint8_t c = at(i); if (c < ' ' || c > '~') return SSB_E_FORMAT; } return 0;
     case 'H': if ((q - v) & 1) return SSB_E_FORMAT;
-              for (size_t i = v; i < q; i++) { uint8_t c = cur.at(i); if (!((c >= '0' && c <= '9') || (c >= 'A' && c <= 'F'))) return SSB_E_FORMAT; } return 0;
+              for (size_t i = v; i < q; i++) { uint8_t c = at(i); if (!((c >= '0' && c <= '9') || (c >= 'A' && c <= 'F'))) return SSB_E_FORMAT; } return 0;
     case 'B': {
         if (q - v < 1) return SSB_E_FORMAT;
-        uint8_t st = cur.at(v);
+        uint8_t st = at(v);
         if (st != 'c' && st != 'C' && st != 's' && st != 'S' && st != 'i' && st != 'I') return SSB_E_FORMAT;   // float arrays: %g round trip not guaranteed
         size_t a = v + 1;
         while (a < q) {
-            if (cur.at(a) != ',') return SSB_E_FORMAT;
-            size_t b = a + 1; while (b < q && cur.at(b) != ',') b++;
+            if (at(a) != ',') return SSB_E_FORMAT;
+            size_t b = a + 1; while (b < q && at(b) != ',') b++;
             size_t vv = v; (void)vv;
             size_t s0 = a + 1;
-            if (s0 < b && cur.at(s0) == '-') s0++;
-            if (s0 >= b || (b - s0 > 1 && cur.at(s0) == '0')) return SSB_E_FORMAT;
-            for (size_t i = s0; i < b; i++) { uint8_t c = cur.at(i); if (c < '0' || c > '9') return SSB_E_FORMAT; }
+            if (s0 < b && at(s0) == '-') s0++;
+            if (s0 >= b || (b - s0 > 1 && at(s0) == '0')) return SSB_E_FORMAT;
+            for (size_t i = s0; i < b; i++) { uint8_t c = at(i); if (c < '0' || c > '9') return SSB_E_FORMAT; }
             a = b;
         }
         return 0;
     }
     default: return SSB_E_FORMAT;      // 'f' and unknown types are outside the byte-exact pass-through envelope
     }
+}
+
+__device__ int aux_ok(const Cursor &cur, size_t p, size_t q)
+{
+    return aux_ok_t([&](size_t i) -> uint8_t { return cur.at(i); }, p, q);
+}
+// the same for a line that lies in the staged window: L = first byte of the line, offsets relative to it
+__device__ int aux_ok_smem(const uint8_t *L, uint32_t p, uint32_t q)
+{
+    return aux_ok_t([=](size_t i) -> uint8_t { return L[i]; }, (size_t)p, (size_t)q);
 }
 
 // ---- SWAR helpers for the long fields (SEQ, QUAL) of a line that sits in the staged shared-memory window ----
@@ -982,10 +993,10 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                     if (!(bad & 2u)) r.bits |= REC_EXC_DONE;               // buffer full: the generic tally takes this read
                     bad &= 1u;
                 } else bad = long_fields<false>(L, r.seq_off, r.l_seq, r.qual_off, qstar, NULL, NULL, li, excbuf, &s_nexc);
-                for (size_t q = ls + qend; q < ls + len;) {
-                    size_t a = q + 1, b = a;
-                    while (b < ls + len && cur.at(b) != '\t') b++;
-                    if (aux_ok(cur, a, b)) bad = 1;
+                for (uint32_t q = qend; q < len;) {                      // optional fields, straight from shared memory
+                    uint32_t a = q + 1, b = a;
+                    while (b < len && L[b] != '\t') b++;
+                    if (aux_ok_smem(L, a, b)) bad = 1;
                     q = b;
                 }
                 if (bad) rc = SSB_E_FORMAT;
