@@ -289,9 +289,11 @@ __device__ __forceinline__ void emit_store(const EmitJob &j, uint32_t i, const u
 }
 __device__ __forceinline__ void emit_edges(const EmitJob &j, int lane)
 {
-    if ((uint32_t)lane < j.head) j.dst[lane] = j.src[lane];                 // < 16 bytes up to the first aligned destination address
+    // < 16 bytes up to the first aligned destination address (lanes 0..15) and < 16 tail bytes (lanes 16..31) in one pass
     const uint32_t done = j.head + (j.nvec << 4);
-    if (done + lane < j.len) j.dst[done + lane] = j.src[done + lane];       // < 16 tail bytes
+    const uint32_t off = lane < 16 ? (uint32_t)lane : done + (uint32_t)lane - 16u;
+    const bool on = lane < 16 ? (uint32_t)lane < j.head : off < j.len;
+    if (on) j.dst[off] = j.src[off];
     if (lane == 0 && j.add_nl) j.dst[j.len] = '\n';
 }
 
