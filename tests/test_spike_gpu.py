@@ -259,3 +259,44 @@ def test_large_properties(ctx, monkeypatch):
     assert out_p == out_s and out_p == out_p2
     assert st_p.rng_draws == st_s.rng_draws == st_p2.rng_draws
     assert [key(r) for r in res_p] == [key(r) for r in res_s] == [key(r) for r in res_p2]
+
+
+def _long_read_case(dirname, read_lens, seed=7):
+    """Single-end reads far longer than the tokeniser's overhang (3 KiB) and tile (32 KiB): written here, the generator's reads stop at 1 kb."""
+    import random
+    rng = random.Random(seed)
+    n = 260_000
+    ref = "".join(rng.choice("ACGT") for _ in range(n))
+    reads = []
+    for i, L in enumerate(read_lens):
+        pos = rng.randrange(0, n - L)
+        seq = list(ref[pos:pos + L])
+        for _ in range(max(1, L // 400)):
+            k = rng.randrange(L); seq[k] = rng.choice("ACGTN")
+        qual = "".join(rng.choice("#5AFI") for _ in range(L))
+        reads.append((pos, "r%d" % i, "".join(seq), qual, L))
+    reads.sort()
+    prefix = os.path.join(dirname, "in")
+    with open(prefix + ".fa", "w") as f:
+        f.write(">chrL\n" + "\n".join(ref[i:i + 60] for i in range(0, n, 60)) + "\n")
+    with open(prefix + ".sam", "w") as f:
+        f.write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chrL\tLN:%d\n" % n)
+        for pos, name, seq, qual, L in reads:
+            f.write("%s\t0\tchrL\t%d\t60\t%dM\t*\t0\t0\t%s\t%s\tNM:i:0\n" % (name, pos + 1, L, seq, qual))
+    with open(prefix + ".spike", "w") as f:
+        f.write("#CHROM\tPOS\tALT\tAF\n")
+        for p in sorted(rng.sample(range(1000, n - 1000), 60)):
+            f.write("chrL\t%d\t%s\t%.4g\n" % (p, rng.choice(".ACGT"), rng.uniform(0.05, 0.6)))
+    return prefix
+
+
+@pytest.mark.parametrize("read_lens", [[5000] * 150, [40000] * 12 + [5000] * 40 + [150] * 300, [100000, 90000, 70000]])
+def test_long_reads(read_lens, tmp_path, ctx):
+    """Lines longer than the staged overhang, than a whole tile, and tiles that hold no line start at all."""
+    prefix = _long_read_case(str(tmp_path), read_lens)
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    assert want[0] == 0 and got[0] == 0, got[4]
+    assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
+    assert got[1] == want[1]
+    assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
