@@ -300,3 +300,16 @@ def test_long_reads(read_lens, tmp_path, ctx):
     assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
     assert got[1] == want[1]
     assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
+
+
+def test_short_reads_many_lines_per_tile(tmp_path, ctx):
+    """36 bp reads: ~300 lines per 32 KiB tile, more than the tokeniser has parsing threads, so every tile also takes its
+    second-round path (careful parser, no exception list for those reads)."""
+    prefix = sc.generate("plain", str(tmp_path), contigs="chr19:20000", read_len=36, frag_mean=60, frag_sd=6, coverage=60, spikes=80)
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    assert want[0] == 0 and got[0] == 0, got[4]
+    assert len(want[2]) > 3_000_000
+    assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
+    assert got[1] == want[1]
+    assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
