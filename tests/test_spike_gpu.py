@@ -313,3 +313,15 @@ def test_short_reads_many_lines_per_tile(tmp_path, ctx):
     assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
     assert got[1] == want[1]
     assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
+
+
+def test_error_rich_reads_overflow_the_tile_exception_buffer(tmp_path, ctx):
+    """15 % substitutions, 10 % BQ-0 bases, 2 % N: far more than 1024 exceptional bases per tile, so the tokeniser's per-tile
+    buffer fills up and the reads that no longer fit are left to the generic tally."""
+    prefix = sc.generate("plain", str(tmp_path), contigs="chr19:12000", coverage=40, sub=0.15, q0=0.1, nrate=0.02, spikes=60)
+    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    assert want[0] == 0 and got[0] == 0, got[4]
+    assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
+    assert got[1] == want[1]
+    assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
