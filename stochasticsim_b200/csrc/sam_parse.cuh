@@ -142,7 +142,6 @@ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
         while (a < q) {
             if (at(a) != ',') return SSB_E_FORMAT;
             size_t b = a + 1; while (b < q && at(b) != ',') b++;
-            size_t vv = v; (void)vv;
             size_t s0 = a + 1;
             if (s0 < b && at(s0) == '-') s0++;
             if (s0 >= b || (b - s0 > 1 && at(s0) == '0')) return SSB_E_FORMAT;
@@ -225,7 +224,7 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
     size_t p0 = p;
     while (p < e && cur.at(p) != '\t') p++;
     if (p >= e || p == p0) return SSB_E_FORMAT;
-    size_t rname0 = p0, rname_len = p - p0;
+    const size_t rname_len = p - p0;
     if (rname_len == 1 && cur.at(p0) == '*') r.tid = -1;
     else {
         r.tid = name_lookup(cur, p0, rname_len, names, tid_cache);
@@ -279,7 +278,6 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
         int mt = name_lookup(cur, p0, p - p0, names, -1);
         if (mt < 0 || mt == r.tid) return SSB_E_FORMAT;
     } else if (cur.at(p0) == '=' && r.tid < 0) return SSB_E_FORMAT;
-    (void)rname0;
     p++;
     // PNEXT
     if (parse_udec(cur, p, e, 0x7fffffffull, v)) return SSB_E_FORMAT;
