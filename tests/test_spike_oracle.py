@@ -65,3 +65,42 @@ def test_usage_exit_status():
     import subprocess
     r = subprocess.run([sc.ORACLE], capture_output=True)
     assert r.returncode == 0 and b"Usage" in r.stderr
+
+
+def _fuzz_args(k):
+    """The generator settings of tests/test_spike_gpu.py::test_fuzz_configs (same seeded draws)."""
+    import random
+    rng = random.Random(1000 + k)
+    rl = rng.choice([36, 50, 76, 100, 151])
+    return dict(seed=2000 + k, contigs=rng.choice(["c1:9000", "chrA:6000,chrB:5000", "chr1:4000,chr2:4000,chr3:3000"]),
+                coverage=rng.choice([3, 12, 40, 150]), read_len=rl, frag_mean=int(rl * rng.choice([1.05, 1.4, 2.2, 3.0])), frag_sd=rng.choice([3, 15, 40]),
+                sub=rng.choice([0.0, 0.002, 0.03]), indel=rng.choice([0.0, 0.01, 0.08]), nrate=rng.choice([0.0, 0.005]), q0=rng.choice([0.0, 0.02]),
+                softclip=rng.choice([0.0, 0.1]), refskip=rng.choice([0.0, 0.04]), filt=rng.choice([0.0, 0.1]), lower=rng.choice([0.0, 0.2]),
+                spikes=rng.choice([5, 60, 400]), alt_mode=rng.choice([0, 1]), aux=rng.choice([0, 1]), af=rng.choice(["0.01:0.5", "0.3:1.0", "0.001:0.02"]))
+
+
+EXTRA_CASES = {
+    "short36": dict(contigs="chr19:20000", read_len=36, frag_mean=60, frag_sd=6, coverage=60, spikes=80),
+    "error_rich": dict(contigs="chr19:12000", coverage=40, sub=0.15, q0=0.1, nrate=0.02, spikes=60),
+}
+EXTRA_CASES.update({"fuzz%d" % k: _fuzz_args(k) for k in range(8)})
+LONG_READS = {"long5k": [5000] * 150, "long_mix": [40000] * 12 + [5000] * 40 + [150] * 300, "long100k": [100000, 90000, 70000]}
+
+
+@pytest.mark.parametrize("name", sorted(EXTRA_CASES) + sorted(LONG_READS))
+def test_restatement_matches_reference_on_gpu_test_inputs(name, tmp_path, ref_dir):
+    """Every input family the GPU parity tests use beyond spike_cases.CASES: the restatement must agree with the unmodified
+    reference over the shim there too, or those GPU tests would pin nothing."""
+    if ref_dir is None or not os.path.exists(sc.REF):
+        pytest.skip("oracle/_ref not built (reference sources not present on this box)")
+    if name in LONG_READS:
+        from test_spike_gpu import _long_read_case
+        prefix = _long_read_case(str(tmp_path), LONG_READS[name])
+    else:
+        prefix = sc.generate("plain", str(tmp_path), **EXTRA_CASES[name])
+    a = sc.run_cli(sc.REF, prefix, str(tmp_path / "ref"), seed=435)
+    b = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), seed=435, cmdname="stochasticSpike")
+    assert a[0] == b[0] == 0
+    assert a[2] == b[2], "SAM differs"
+    assert a[3] == b[3], "truth.vcf differs"
+    assert a[1] == b[1], "stdout differs"
