@@ -139,8 +139,43 @@ class Dist:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather(self, row):
+        """list of float64 rows, one per rank, in rank order (on every rank)."""
+        if not self.on:
+            return [list(map(float, row))]
+        import torch
+        t = torch.tensor(list(map(float, row)), dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.cpu().tolist() for o in out]
+
+    def ssb_comm(self, ctx):
+        """The library's own NCCL communicator over the ranks of this job (ssb_nccl_unique_id on rank 0, the 128 bytes broadcast
+        through torch.distributed, ssb_nccl_comm_init_rank everywhere): what the product collectives and the spike exchange run on."""
+        if getattr(self, "_comm", None) is not None:
+            return self._comm
+        import torch
+        import stochasticsim_b200 as ssb
+        from stochasticsim_b200 import spike as sp
+        L = sp._bind()
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            ssb.check(L.ssb_nccl_unique_id(buf))
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        idt = idt.cuda()
+        self.dist.broadcast(idt, 0)
+        raw = bytes(idt.cpu().tolist())
+        comm = C.c_void_p()
+        ssb.check(L.ssb_nccl_comm_init_rank(ctx.handle, self.world, self.rank, raw, C.byref(comm)), ctx.handle)
+        self._comm = comm
+        return comm
+
     def close(self):
         if self.on:
+            if getattr(self, "_comm", None) is not None:
+                from stochasticsim_b200 import spike as sp
+                sp._bind().ssb_nccl_comm_destroy(self._comm)
             self.dist.destroy_process_group()
 
 
@@ -177,23 +212,44 @@ def tnc_make_fasta_device(torch, rank, scale=1.0):
     return torch.cat(parts), n_bases
 
 
-def run_tnc(args, D):
+def run_tnc(args, D, ctx=None):
+    """C3: whole-FASTA trinucleotide scan.  At N > 1 ONE FASTA is cut by byte range (rank g takes [g n / N, (g+1) n / N)), every rank gets
+    the scanner state at its cut from ssb_tnc_carry_after, and the 64 counters are combined by ssb_tnc_allreduce INSIDE the timed region
+    (the path's only collective).  `value` is whole-job bases/s: the FASTA is the same at every N (strong scaling)."""
     import numpy as np
     import torch
     import stochasticsim_b200 as ssb
     peak, peak_src = measured_peaks()
     torch.cuda.set_device(D.local)
-    ctx = ssb.Context(D.local)
+    own_ctx = ctx is None
+    if own_ctx:
+        ctx = ssb.Context(D.local)
     ctx.profile_enable(True)
-    fasta, n_bases = tnc_make_fasta_device(torch, D.rank, args.scale)
-    n = fasta.numel()
+    fasta, n_bases = tnc_make_fasta_device(torch, 0, args.scale)       # the same file on every rank
+    n_all = fasta.numel()
     torch.cuda.synchronize()
+    N = D.world
+    lo = (n_all * D.rank // N) & ~31
+    hi = n_all if D.rank == N - 1 else (n_all * (D.rank + 1) // N) & ~31
+    piece = fasta[lo:hi]
+    n = hi - lo
+    carry = None
+    L = ssb.lib()
+    if lo:
+        # scanner state at the cut from the bytes before it (host, counts nothing); the last 16 MiB are far more than it ever looks at here
+        tail0 = max(0, lo - (16 << 20))
+        tail = fasta[tail0:lo].cpu().numpy()
+        carry = ssb.tnc.carry_after(tail)
+    comm = D.ssb_comm(ctx) if D.on else None
     d_counts = torch.zeros(64, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
-    log(f"[bench rank {D.rank}] tnc: {n} FASTA bytes, {n_bases} bases resident in HBM")
+    log(f"[bench rank {D.rank}] tnc: bytes [{lo}, {hi}) of a {n_all}-byte FASTA ({n_bases} bases) resident in HBM")
 
     def step():
-        ssb.tnc.count_device(ctx, fasta.data_ptr(), n, d_counts.data_ptr())
+        ctx.memset(d_counts.data_ptr(), 0, 512)
+        ssb.tnc.count_device(ctx, piece.data_ptr(), n, d_counts.data_ptr(), carry_in=carry)
+        if comm is not None:
+            ssb.check(L.ssb_tnc_allreduce(ctx.handle, comm, d_counts.data_ptr()), ctx.handle)
 
     for _ in range(args.warmup):
         step()
@@ -214,20 +270,29 @@ def run_tnc(args, D):
     scan_ms, scan_n = ctx.profile_read(0)
     fix_ms, fix_n = ctx.profile_read(1)
     ms = D.max(ms)
-    total_bases = D.sum(float(n_bases))
+    counts = d_counts.cpu().numpy().copy()                                 # after the all-reduce: the whole file's counts on every rank
 
-    counts = d_counts.cpu().numpy() // (args.steps + args.warmup)          # this rank's shard
+    # the sharded counts must equal the one-GPU counts of the whole file (rank 0 checks, outside the timed region)
+    if D.on and D.rank == 0:
+        d_whole = torch.zeros(64, dtype=torch.int64, device="cuda")
+        ssb.tnc.count_device(ctx, fasta.data_ptr(), n_all, d_whole.data_ptr())
+        ctx.sync()
+        assert np.array_equal(d_whole.cpu().numpy(), counts), "sharded TNC counts differ from the single-GPU counts"
 
-    # ---- e2e: host buffers through ssb_tnc_count_host (H2D inside the timed region, counts back on the host)
+    # ---- e2e: host buffers through ssb_tnc_count_host (H2D inside the timed region, counts back on the host, all-reduce included)
     e2e_steps = max(1, min(args.steps, 5))
-    hp = ctx.host_alloc(n)
-    ctx.d2h(hp, fasta.data_ptr(), n)
+    hp = ctx.host_alloc(max(n, 1))
+    ctx.d2h(hp, piece.data_ptr(), n)
     ctx.sync()
     out = np.zeros(64, dtype=np.int64)
-    L = ssb.lib()
 
     def e2e_step():
-        ssb.check(L.ssb_tnc_count_host(ctx.handle, hp, n, None, None, out.ctypes.data_as(C.POINTER(C.c_int64))), ctx.handle)
+        ssb.check(L.ssb_tnc_count_host(ctx.handle, hp, n, C.byref(carry) if carry is not None else None, None, out.ctypes.data_as(C.POINTER(C.c_int64))), ctx.handle)
+        if comm is not None:
+            ctx.h2d(d_counts.data_ptr(), out.ctypes.data, 512)
+            ssb.check(L.ssb_tnc_allreduce(ctx.handle, comm, d_counts.data_ptr()), ctx.handle)
+            ctx.d2h(out.ctypes.data, d_counts.data_ptr(), 512)
+            ctx.sync()
 
     e2e_step()
     D.barrier()
@@ -237,31 +302,31 @@ def run_tnc(args, D):
     e2e_s = D.max(time.perf_counter() - t0)
     assert np.array_equal(out, counts), "device-resident and host-streamed counts differ"
     ctx.host_free(hp)
-    # the path's only collective: sum the 64 counters over ranks (NCCL through torch.distributed)
-    if D.on:
-        tot = torch.from_numpy(counts).cuda()
-        D.dist.all_reduce(tot)
-        counts = tot.cpu().numpy()
 
+    scan_gbs = n * args.steps / (scan_ms / 1e3) / 1e9 if scan_ms else None
     res = {
-        "metric": "tnc_ref_bases_per_s", "value": total_bases * args.steps / (ms / 1e3), "unit": "bases/s",
+        "metric": "tnc_ref_bases_per_s", "value": n_bases * args.steps / (ms / 1e3), "unit": "bases/s",
         "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C3 tncCountsProfile whole-FASTA scan, GRCh38-shaped 24-contig 60-col FASTA per GPU"
-                               + ("" if args.scale == 1.0 else f" (scaled x{args.scale})"),
-                   "fasta_bytes_per_gpu": n, "bases_per_gpu": n_bases, "l2": "input (%.2f GB) larger than L2, no flush" % (n / 1e9),
-                   "collective": "one all-reduce of 64 int64 (outside the timed region)" if D.on else "none"},
-        "e2e": {"value": total_bases * e2e_steps / e2e_s, "unit": "bases/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 512,
-                "steps": e2e_steps, "api": "ssb_tnc_count_host (pinned host FASTA -> 64 host counters)"},
+        "higher_is_better": True, "scaling": "strong" if D.on else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C3 tncCountsProfile whole-FASTA scan, ONE GRCh38-shaped 24-contig 60-col FASTA"
+                               + (" cut by byte range over %d GPUs" % N if D.on else "") + ("" if args.scale == 1.0 else f" (scaled x{args.scale})"),
+                   "fasta_bytes": n_all, "fasta_bytes_per_gpu": n, "bases": n_bases, "l2": "input (%.2f GB per GPU) larger than L2, no flush" % (n / 1e9),
+                   "collective": "ssb_tnc_allreduce: one NCCL all-reduce of 64 int64 over NVLink, inside the timed region" if D.on else "none"},
+        "e2e": {"value": n_bases * e2e_steps / e2e_s, "unit": "bases/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 512,
+                "steps": e2e_steps, "api": "ssb_tnc_count_host (pinned host FASTA -> 64 host counters)" + (" + ssb_tnc_allreduce" if D.on else "")},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "tnc_scan_kernel", "achieved": n * args.steps / (scan_ms / 1e3) / 1e9 if scan_ms else None,
-                     "peak": peak, "unit": "GB/s", "frac": (n * args.steps / (scan_ms / 1e3) / 1e9 / peak) if scan_ms else None,
+        "roofline": {"bound": "hbm", "kernel": "tnc_scan_kernel", "achieved": scan_gbs,
+                     "peak": peak, "unit": "GB/s", "frac": (scan_gbs / peak) if scan_gbs else None,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * args.steps // max(1, scan_n),
                      "kernel_ms_avg": scan_ms / max(1, scan_n), "kernel_share_of_step": scan_ms / ms if ms else None,
-                     "fixup_kernel_ms_avg": fix_ms / max(1, fix_n)},
+                     "fixup_kernel_ms_avg": fix_ms / max(1, fix_n),
+                     "whole_path": {"achieved": n * args.steps / (ms / 1e3) / 1e9, "frac": n * args.steps / (ms / 1e3) / 1e9 / peak}},
         "clocks": clk.summary(),
     }
-    ctx.close()
+    del fasta, piece
+    torch.cuda.empty_cache()
+    if own_ctx:
+        ctx.close()
     return res, counts
 
 
@@ -348,6 +413,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SSB_BENCH_WORKLOAD", "auto"), choices=["auto", "spike", "tnc"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only; the judged run uses 1.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tnc", action="store_true", help="spike workload only (development)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # only the JSON line may reach stdout: libraries (NCCL prints its version there) go to stderr meanwhile
@@ -384,23 +450,39 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
+    import numpy as np
+    import stochasticsim_b200 as ssb
     if workload == "spike":
         import bench_spike
-        res = bench_spike.run(args, D)
+        res, ctx = bench_spike.run(args, D)
+        # the other hot path rides in the same line (BASELINE's metric names both)
+        if not args.no_tnc:
+            tnc_args = argparse.Namespace(**vars(args))
+            tnc_args.steps = max(args.steps, 10)
+            tnc, counts = run_tnc(tnc_args, D, ctx)
+            if D.rank == 0 and not args.no_cpu_baseline:
+                tnc["cpu_baseline"] = tnc_parity_baseline(ctx)
+            res["tnc"] = tnc
+        ctx.close()
     else:
         res, counts = run_tnc(args, D)
         if D.rank == 0 and not args.no_cpu_baseline:
-            import numpy as np
-            import stochasticsim_b200 as ssb
-            cb, data, ref_out = tnc_cpu_baseline()
-            with ssb.Context(D.local) as ctx:          # parity of the sample: GPU path vs the reference binary's stdout
-                got = ssb.tnc.format_counts(ssb.tnc.count_host(ctx, np.frombuffer(data, dtype=np.uint8)))
-            cb["sample_parity"] = "bit-exact" if got.encode() == ref_out else "MISMATCH"
-            assert got.encode() == ref_out, "GPU counts differ from the reference binary on the CPU sample"
-            res["cpu_baseline"] = cb
+            with ssb.Context(D.local) as ctx:
+                res["cpu_baseline"] = tnc_parity_baseline(ctx)
     if D.rank == 0:
         emit(res)
     D.close()
+
+
+def tnc_parity_baseline(ctx):
+    """The reference binary on a bounded sample, and the GPU path against its stdout on that sample."""
+    import numpy as np
+    import stochasticsim_b200 as ssb
+    cb, data, ref_out = tnc_cpu_baseline()
+    got = ssb.tnc.format_counts(ssb.tnc.count_host(ctx, np.frombuffer(data, dtype=np.uint8)))
+    cb["sample_parity"] = "bit-exact" if got.encode() == ref_out else "MISMATCH"
+    assert got.encode() == ref_out, "GPU counts differ from the reference binary on the CPU sample"
+    return cb
 
 
 if __name__ == "__main__":

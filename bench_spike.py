@@ -1,9 +1,15 @@
 """Spike workload of bench.py (BASELINE.json configs[1]): chr19-length reference, 150 bp paired
-reads at 100x (39.1 M reads, ~14 GB of SAM text), 10,000 SBS spike loci, seed 434, one B200 per rank.
+reads at 100x (39.1 M reads, ~14 GB of SAM text), 10,000 SBS spike loci, seed 434.
+
+At N GPUs the input is ONE coordinate-sorted SAM over N chr19-sized contigs (the shape of C4: one generator seed, one
+`.spike` table with N x 10,000 loci, one rand() stream), cut by coordinate range: rank g holds the reads that start on
+contig g and runs as shard g of a cooperative group (ssb_spike_run_shard_device over an NCCL exchange).  The shards hand
+the exact rand() offset on (8 bytes, rank 0 -> 1 -> ...) after simulating the window of offsets they can be entered with;
+the concatenated outputs are what one GPU (or the reference) makes of the whole file (tests/test_spike_shards.py).
 
 The synthetic input comes from tools/gen_synth.c (counter based, so any coordinate range can be generated on its
 own: ranks and host threads build their shards independently).  All compute goes through the C ABI
-(ssb_spike_run_device for `value`, ssb_spike_run_host for `e2e`)."""
+(ssb_spike_run[_shard]_device for `value`, ssb_spike_run[_shard]_host for `e2e`)."""
 import ctypes as C
 import os
 import subprocess
@@ -51,11 +57,19 @@ def c2_params(L, seed, coverage):
     return p
 
 
-def make_workload(L, seed, contig_len, coverage, n_spikes, name=b"chr19", threads=None, log=None):
-    """Returns (ref bytes ndarray, body chunks list[bytes-like ndarray], n_reads, spike text bytes)."""
+def spike_table(L, seed, coverage, contig_len, n_spikes, name=b"chr19", cidx=0):
+    p = c2_params(L, seed, coverage)
+    sn = L.synth_spike_table(C.byref(p), cidx, name, 0, contig_len, n_spikes, 1, 0.01, 0.5, None, 0)
+    sb = C.create_string_buffer(sn + 1)
+    L.synth_spike_table(C.byref(p), cidx, name, 0, contig_len, n_spikes, 1, 0.01, 0.5, sb, sn)
+    return sb.raw[:sn]
+
+
+def make_workload(L, seed, contig_len, coverage, n_spikes, name=b"chr19", threads=None, log=None, cidx=0):
+    """Returns (ref bytes ndarray, body chunks list[bytes-like ndarray], n_reads, spike text bytes) of contig `cidx`."""
     p = c2_params(L, seed, coverage)
     ref = np.empty(contig_len + 1, dtype=np.uint8)
-    L.synth_ref_contig(C.byref(p), 0, contig_len, 0, contig_len, 0, ref.ctypes.data)
+    L.synth_ref_contig(C.byref(p), cidx, contig_len, 0, contig_len, 0, ref.ctypes.data)
     step = 200_000
     ranges = [(lo, min(contig_len, lo + step)) for lo in range(0, contig_len, step)]
     per_pos = coverage / 150.0 * 420.0 * 1.25 + 64          # generous bytes per reference position
@@ -65,26 +79,37 @@ def make_workload(L, seed, contig_len, coverage, n_spikes, name=b"chr19", thread
         cap = int((hi - lo) * per_pos) + (1 << 16)
         buf = np.empty(cap, dtype=np.uint8)
         nr = C.c_int64()
-        need = L.synth_sam_range(C.byref(p), 0, name, ref.ctypes.data, contig_len, 0, contig_len, lo, hi, buf.ctypes.data, cap, C.byref(nr))
+        need = L.synth_sam_range(C.byref(p), cidx, name, ref.ctypes.data, contig_len, 0, contig_len, lo, hi, buf.ctypes.data, cap, C.byref(nr))
         if need > cap:
             buf = np.empty(need, dtype=np.uint8)
-            L.synth_sam_range(C.byref(p), 0, name, ref.ctypes.data, contig_len, 0, contig_len, lo, hi, buf.ctypes.data, need, C.byref(nr))
+            L.synth_sam_range(C.byref(p), cidx, name, ref.ctypes.data, contig_len, 0, contig_len, lo, hi, buf.ctypes.data, need, C.byref(nr))
         return buf[:need], nr.value
 
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 8)) as ex:
         parts = list(ex.map(gen, ranges))
     n_reads = sum(nr for _, nr in parts)
-    sn = L.synth_spike_table(C.byref(p), 0, name, 0, contig_len, n_spikes, 1, 0.01, 0.5, None, 0)
-    sb = C.create_string_buffer(sn + 1)
-    L.synth_spike_table(C.byref(p), 0, name, 0, contig_len, n_spikes, 1, 0.01, 0.5, sb, sn)
     if log:
         log(f"[bench] generated {n_reads} reads, {sum(b.size for b, _ in parts)} SAM bytes in {time.perf_counter() - t0:.1f} s")
-    return ref[:contig_len], [b for b, _ in parts], n_reads, sb.raw[:sn]
+    return ref[:contig_len], [b for b, _ in parts], n_reads, spike_table(L, seed, coverage, contig_len, n_spikes, name, cidx)
 
 
 def header_for(name, contig_len):
     return ("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n@PG\tID:gen_synth\tPN:gen_synth\n" % (name, contig_len)).encode()
+
+
+def traffic_from_profile(scale):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step, summed over every kernel of one pass, from the committed ncu capture of
+    this exact workload (profiles/r02_spike_traffic.json, written by tools/ncu_traffic.py); None when there is none."""
+    p = os.path.join(ROOT, "profiles", "r02_spike_traffic.json")
+    if scale != 1.0 or not os.path.exists(p):
+        return None, None
+    try:
+        import json
+        j = json.load(open(p))
+        return float(j["dram_bytes_per_step"]), j.get("per_kernel")
+    except Exception:
+        return None, None
 
 
 def run(args, D):
@@ -98,7 +123,11 @@ def run(args, D):
     coverage = 100.0 * args.scale
     contig_len = CHR19
     n_spikes = 10_000
-    ref, parts, n_reads, spike_text = make_workload(L, 2 + 1000 * D.rank, contig_len, coverage, n_spikes, log=log)
+    N = D.world
+    names = ["chr19"] if N == 1 else ["chr19.%d" % g for g in range(N)]
+    # ONE input: contig g of the same generator seed on rank g; the .spike table covers every contig
+    ref, parts, n_reads, _ = make_workload(L, 2, contig_len, coverage, n_spikes, name=names[D.rank].encode(), log=log, cidx=D.rank)
+    spike_text = b"".join(spike_table(L, 2, coverage, contig_len, n_spikes, names[g].encode(), g) for g in range(N))
     n = sum(b.size for b in parts)
     ctx = ssb.Context(D.local)
     ctx.profile_enable(True)
@@ -114,15 +143,21 @@ def run(args, D):
     d_out = ctx.dev_alloc(n + 64)
     ctx.h2d(d_in, hp, n)
     ctx.sync()
-    names = ["chr19"]
     targets = sp.parse_spike(spike_text, names)
-    S = sp.Spike(ctx, names, {"chr19": ref.tobytes()})
+    S = sp.Spike(ctx, names, {names[D.rank]: ref.tobytes()})        # a shard only ever touches its own contig
     tarr = S.make_targets(targets)
     res = (sp.TargetResult * len(targets))()
     st = sp.Stats()
+    shard, xc, comm = None, None, None
+    if N > 1:
+        shard = sp.Shard(index=D.rank, count=N, lo_tid=D.rank, hi_tid=(D.rank + 1 if D.rank + 1 < N else 0x7fffffff), lo_pos=0, hi_pos=0, halo_bytes=0)
+        comm = D.ssb_comm(ctx)
+        x = C.c_void_p()
+        ssb.check(sp._bind().ssb_exchange_nccl_create(ctx.handle, comm, D.rank, N, C.byref(x)), ctx.handle)
+        xc = x
 
     def step():
-        return S.run_device(d_in, n, d_out, n + 1, tarr, len(targets), SPIKE_SEED, res, st)
+        return S.run_shard_device(shard, xc, d_in, n, d_out, n + 1, tarr, len(targets), SPIKE_SEED, res, st)
 
     for _ in range(args.warmup):
         out_bytes = step()
@@ -147,15 +182,25 @@ def run(args, D):
     prof = {name: ctx.profile_read(slot) for name, slot in (("parse", 2), ("emit", 3), ("chain", 4), ("other", 5), ("tally", 6))}
     ms = D.max(ms)
     total_reads = D.sum(float(n_reads))
+    total_bytes = D.sum(float(n + out_bytes))
     stats = st.as_dict()
+    # one stream over all shards: every rank starts where its predecessor stopped
+    chain = D.gather([stats["rng_k_in"], stats["rng_k_out"], stats["n_hits"], stats["chain_mode"],
+                      stage_ms.get("ms_chain", 0.0) / args.steps, stage_ms.get("ms_phase1", 0.0) / args.steps,
+                      stage_ms.get("ms_handoff_wait", 0.0) / args.steps, stage_ms.get("ms_exchange", 0.0) / args.steps])
+    if D.rank == 0:
+        for a, b in zip(chain, chain[1:]):
+            assert int(a[1]) == int(b[0]), "rand() offset hand-off broken: %r" % (chain,)
+        assert int(chain[0][0]) == 0
 
     # ---- e2e: pinned host SAM body in, spiked SAM body back on the host
     e2e_steps = max(1, min(args.steps, 3))
     outn = C.c_size_t()
-    Lb = ssb.lib()
+    Lb = sp._bind()
 
     def e2e_step():
-        ssb.check(Lb.ssb_spike_run_host(S.handle, hp, n, hout, n + 1, tarr, len(targets), SPIKE_SEED, res, C.byref(st), C.byref(outn)), ctx.handle)
+        ssb.check(Lb.ssb_spike_run_shard_host(S.handle, C.byref(shard) if shard is not None else None, xc, hp, n, hout, n + 1, tarr, len(targets), SPIKE_SEED,
+                                              res, C.byref(st), C.byref(outn)), ctx.handle)
 
     e2e_step()
     D.barrier()
@@ -169,46 +214,59 @@ def run(args, D):
     assert stats["alignmentCount"] == stats["n_kept"] and out_bytes == stats["out_bytes"]
     emit_ms, emit_n = prof["emit"]
     parse_ms, parse_n = prof["parse"]
-    emit_bytes = 2.0 * out_bytes * args.steps
+    chain_ms, chain_n = prof["chain"]
+    traffic, traffic_per_kernel = traffic_from_profile(args.scale)
+    whole = total_bytes * args.steps / (ms / 1e3) / 1e9 / N          # per GPU
     res_json = {
         "metric": "sam_reads_spiked_per_s", "value": total_reads * args.steps / (ms / 1e3), "unit": "reads/s",
         "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C2 chr19 full-length synthetic 150bp paired reads at %gx with 10k SBS spike loci, per GPU" % coverage
+        "config": {"workload": ("C2 chr19 full-length synthetic 150bp paired reads at %gx with 10k SBS spike loci" % coverage if N == 1 else
+                                "ONE coordinate-sorted SAM over %d chr19-sized contigs (C2 per contig: 150bp paired reads at %gx, 10k SBS spike loci each; one seed, one "
+                                ".spike table, one rand() stream), cut by coordinate range, shard g on GPU g" % (N, coverage))
                                + ("" if args.scale == 1.0 else f" (depth scaled x{args.scale})"),
-                   "reads_per_gpu": n_reads, "sam_bytes_per_gpu": n, "covered_loci": stats["numberOfLociCovered"], "spike_seed": SPIKE_SEED,
-                   "targets_hit": stats["n_hits"], "l2": "input (%.2f GB) larger than L2, no flush" % (n / 1e9), "collective": "none"},
+                   "reads_per_gpu": n_reads, "sam_bytes_per_gpu": n, "covered_loci_per_gpu": stats["numberOfLociCovered"], "spike_seed": SPIKE_SEED,
+                   "targets": len(targets), "targets_hit_on_rank0": stats["n_hits"], "l2": "input (%.2f GB) larger than L2, no flush" % (n / 1e9),
+                   "collective": "none" if N == 1 else
+                   "NCCL over NVLink, inside the timed region: all-gather of 5 scalars per shard, max-reduction of one int64 per .spike record (%d), "
+                   "all-gather of the expected draw counts, the exact rand() offset as an 8-byte send/recv from shard g to g+1, all-gather of the verdict; "
+                   "no alignment text moves" % len(targets)},
         "e2e": {"value": total_reads * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(out_bytes),
-                "steps": e2e_steps, "api": "ssb_spike_run_host (pinned host SAM body -> spiked SAM body on the host)"},
+                "steps": e2e_steps, "api": "ssb_spike_run%s_host (pinned host SAM body -> spiked SAM body on the host)" % ("" if N == 1 else "_shard")},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "emit_kernel", "achieved": emit_bytes / (emit_ms / 1e3) / 1e9 if emit_ms else None,
-                     "peak": peak, "unit": "GB/s", "frac": emit_bytes / (emit_ms / 1e3) / 1e9 / peak if emit_ms else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one emit_kernel launch of this exact workload, from the
-                     # ncu --set full capture summarised in profiles/r01_emit_kernel_ncu.txt (15.294 GB + 14.206 GB)
-                     "traffic": 29.499585e9 if args.scale == 1.0 else None,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": 2 * out_bytes, "kernel_ms_avg": emit_ms / max(1, emit_n),
-                     "kernel_share_of_step": emit_ms / ms if ms else None,
+        # the whole pass is the unit the north star's "sustained" bandwidth means; the kernels below explain it
+        "roofline": {"bound": "hbm", "kernel": "whole pass (every kernel of one step, per GPU)", "achieved": whole,
+                     "peak": peak, "unit": "GB/s", "frac": whole / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": n + out_bytes, "kernel_ms_avg": ms / args.steps,
+                     "kernel_share_of_step": 1.0,
+                     "emit_kernel": {"achieved": 2.0 * out_bytes * args.steps / (emit_ms / 1e3) / 1e9 if emit_ms else None, "kernel_ms_avg": emit_ms / max(1, emit_n),
+                                     "algorithmic_bytes_per_launch": 2 * out_bytes, "frac": 2.0 * out_bytes * args.steps / (emit_ms / 1e3) / 1e9 / peak if emit_ms else None,
+                                     "note": "runs on a second stream beside the chain branch"},
                      "parse_kernel": {"achieved": n * args.steps / (parse_ms / 1e3) / 1e9 if parse_ms else None, "kernel_ms_avg": parse_ms / max(1, parse_n),
-                                      "algorithmic_bytes_per_launch": n},
-                     "whole_path": {"algorithmic_bytes_per_step": n + out_bytes, "achieved": (n + out_bytes) * args.steps / (ms / 1e3) / 1e9,
-                                    "frac": (n + out_bytes) * args.steps / (ms / 1e3) / 1e9 / peak}},
+                                      "algorithmic_bytes_per_launch": n, "frac": n * args.steps / (parse_ms / 1e3) / 1e9 / peak if parse_ms else None},
+                     "chain_kernels": {"ms_per_step": chain_ms / args.steps, "note": "phase 1 + compose + boundaries + phase 3: issue bound, no credited bytes"},
+                     "traffic_per_kernel": traffic_per_kernel},
         "stages_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
         "kernel_groups_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
         "chain_chunks": stats["chain_mode"],
-        "rng_chain": {"ms_per_step": stage_ms.get("ms_chain", 0.0) / args.steps, "draws": stats["rng_draws"],
-                      "note": "serial by construction: one glibc rand() stream consumed at every covered locus (stochasticSpike.c:1197)"},
+        "rng_chain": {"ms_per_step": stage_ms.get("ms_chain", 0.0) / args.steps, "phase1_ms_per_step": stage_ms.get("ms_phase1", 0.0) / args.steps,
+                      "draws_after_last_shard": int(chain[-1][1]) if D.rank == 0 else None,
+                      "per_shard": [{"k_in": int(c[0]), "k_out": int(c[1]), "hits": int(c[2]), "chunks": int(c[3]), "chain_ms": c[4], "phase1_ms": c[5],
+                                     "handoff_wait_ms": c[6], "exchange_ms": c[7]} for c in chain] if D.rank == 0 else None,
+                      "note": "one glibc rand() stream consumed at every covered locus (stochasticSpike.c:1197): window maps per shard, exact 8-byte hand-off"},
         "clocks": clk.summary(),
     }
     # ---- CPU baseline + parity of the sample (rank 0)
     if D.rank == 0 and not args.no_cpu_baseline:
         res_json["cpu_baseline"] = cpu_baseline(L, S_ctx=(ctx, sp), target_s=15.0)
+    if xc is not None:
+        sp.exchange_destroy(xc)
     S.close()
     for p_ in (hp, hout):
         ctx.host_free(p_)
     ctx.dev_free(d_in)
     ctx.dev_free(d_out)
-    ctx.close()
-    return res_json
+    return res_json, ctx
 
 
 def cpu_exe():

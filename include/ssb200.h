@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 
 enum {
     SSB_OK            =  0,
@@ -37,7 +37,9 @@ enum {
     SSB_E_DEPTH       = -7,   /* pileup deeper than MAX_PILEUP_SIZE (stochasticSpike.c:38) */
     SSB_E_REF         = -8,   /* contig missing from / longer than the reference FASTA  */
     SSB_E_STATE       = -9,   /* call order violated                                    */
-    SSB_E_NCCL        = -10
+    SSB_E_NCCL        = -10,
+    SSB_E_SHARD       = -11,  /* a shard's alignment lines do not match its coordinate range / halo too small */
+    SSB_E_PEER        = -12   /* another shard of the cooperative run failed                                  */
 };
 
 typedef struct ssb_ctx ssb_ctx;
@@ -153,7 +155,8 @@ typedef struct ssb_target {
     float   af;               /* (float)atof(AF)                                                     */
 } ssb_target;
 
-enum { SSB_T_HIT = 0, SSB_T_NOCOV = 1, SSB_T_NOCOV_SILENT = 2, SSB_T_TAIL = 3 };
+enum { SSB_T_HIT = 0, SSB_T_NOCOV = 1, SSB_T_NOCOV_SILENT = 2, SSB_T_TAIL = 3,
+       SSB_T_ELSEWHERE = 4 /* sharded runs: the target is consumed at a locus another shard owns */ };
 enum { SSB_F_NONE = 0, SSB_F_PASS = 1, SSB_F_MASKED = 2, SSB_F_MASKED_OVL = 3, SSB_F_UNDETECTED = 4 };
 
 typedef struct ssb_target_result {
@@ -174,6 +177,12 @@ typedef struct ssb_spike_stats {
     int64_t n_lines, n_kept, in_bytes, out_bytes, n_runs, n_hits, rng_draws;
     int64_t chain_mode;       /* chunks the RNG chain ran as: 1 = serial, P > 1 = P parallel chunk maps      */
     float   ms_parse, ms_sort, ms_emit, ms_cover, ms_gather, ms_rng, ms_chain, ms_patch, ms_total;
+    /* sharded runs (ssb_spike_run_shard_*): where this shard sits in the one rand() stream and what the hand-off cost */
+    int64_t rng_k_in, rng_k_out;      /* rand() calls consumed before the shard's first / after its last covered locus */
+    int64_t locus_base;               /* covered loci owned by the shards before this one (added to locus_index)       */
+    int64_t n_forwarded;              /* spiked bases handed to the next shard (reads that end in its range)           */
+    float   ms_handoff_wait;          /* host time blocked on the predecessor's 8-byte offset                          */
+    float   ms_phase1, ms_tally, ms_exchange;
 } ssb_spike_stats;
 
 int  ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_contigs, ssb_spike **out);
@@ -210,6 +219,67 @@ typedef struct ssb_seq_error {
 } ssb_seq_error;
 int ssb_spike_seq_error_count(ssb_spike *sp, size_t *count);
 int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t cap);
+
+/* ------------------------------------------------------------------------------------------
+ * Hot path 1 on several GPUs: ONE coordinate-sorted input cut into coordinate ranges, one range
+ * ("shard") per ssb_spike object / GPU / process.  The reference has one rand() stream and one
+ * pileup (stochasticSpike.c:948, :1129, :1197), so the shards cooperate:
+ *   - a read belongs to the input of the shard its START lies in; the shard's body is preceded by
+ *     `halo_bytes` of the previous shard's last lines (every read that can reach into this range:
+ *     start within the largest reference span before `lo`);
+ *   - a covered locus, its pileup, its truth.vcf line and its draws belong to the shard whose range
+ *     holds the locus; a read is WRITTEN by the shard whose range holds its last base, so that the
+ *     outputs of the shards, concatenated in shard order, are the reference's output (:1272-1285);
+ *   - the rand() offset at the start of a shard is handed over exactly: every shard simulates the
+ *     window of offsets it can be entered with while its predecessors are still working (phase 1 of
+ *     the chain), the 8-byte exact offset then travels shard 0 -> 1 -> ... as a table lookup each,
+ *     and the targets are applied (phase 3) once it is known;
+ *   - bases spiked into a read that a LATER shard writes are forwarded to that shard.
+ * What travels between shards is: 5 scalars per shard (all-gather), one max-reduction over an
+ * int64 per .spike record (the target stream's skip logic, :1578-1619, is one global scan), the
+ * 8-byte offset (+ a flag word) and the forwarded bases -- never alignment text.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssb_exchange ssb_exchange;      /* how cooperating shards talk */
+
+/* n handles for n shards driven by n threads of ONE process (any mix of devices): out[i] belongs to shard i. */
+int  ssb_exchange_local_create(int n_shards, ssb_exchange **out);
+/* One handle per process over an NCCL communicator (rank = shard index).  ctx supplies the device staging. */
+int  ssb_exchange_nccl_create(ssb_ctx *ctx, void *nccl_comm, int rank, int n_ranks, ssb_exchange **out);
+void ssb_exchange_destroy(ssb_exchange *xc);
+/* NCCL plumbing for callers that have no communicator of their own (bench.py under torchrun, the C mains):
+ * rank 0 makes the id, ships the 128 bytes to the others by any means, every rank then joins. */
+int  ssb_nccl_unique_id(uint8_t id128[128]);
+int  ssb_nccl_comm_init_rank(ssb_ctx *ctx, int n_ranks, int rank, const uint8_t id128[128], void **comm_out);
+void ssb_nccl_comm_destroy(void *nccl_comm);
+
+typedef struct ssb_spike_shard {
+    int32_t  index, count;        /* this is shard `index` of `count`, in coordinate order                       */
+    int32_t  lo_tid, hi_tid;      /* owned loci: (lo_tid, lo_pos) <= (tid, pos) < (hi_tid, hi_pos), @SQ order;   */
+    int64_t  lo_pos, hi_pos;      /* first shard: lo = (0, 0); last shard: hi_tid = INT32_MAX                    */
+    uint64_t halo_bytes;          /* leading bytes of the body that repeat the predecessor's last lines          */
+} ssb_spike_shard;
+
+/* One shard of a cooperative run; every shard of the group must make the same call (same targets, seed).
+ * Body, output and results as in ssb_spike_run_device / _host; results[t].status == SSB_T_ELSEWHERE for the
+ * targets other shards consume (SSB_T_TAIL is reported by the last shard only), locus_index is global.
+ * stats are this shard's share: the stats block of stochasticSpike.c:1668 is the sum over shards
+ * (maxDepth: the maximum).  xc == NULL is allowed for count == 1. */
+int ssb_spike_run_shard_device(ssb_spike *sp, const ssb_spike_shard *shard, ssb_exchange *xc,
+                               const uint8_t *d_sam, size_t n, uint8_t *d_out, size_t out_cap,
+                               const ssb_target *targets, size_t n_targets, unsigned seed,
+                               ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes);
+int ssb_spike_run_shard_host(ssb_spike *sp, const ssb_spike_shard *shard, ssb_exchange *xc,
+                             const uint8_t *sam, size_t n, uint8_t *out, size_t out_cap,
+                             const ssb_target *targets, size_t n_targets, unsigned seed,
+                             ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes);
+
+/* Host helper: cuts a coordinate-sorted SAM body into `count` shards of about equal bytes.  contig_names are the
+ * @SQ names (index = tid).  halo_bases = the largest reference span a read can have (reads that start less than
+ * this before a cut are repeated in front of the next shard).  Fills shards[i] and the byte range
+ * [body_off[i], body_off[i] + body_len[i]) of shard i's body inside `sam` (halo included, so ranges overlap).
+ * Fewer than `count` shards are made when the body is too small; returns the number made (>= 1) or < 0. */
+int ssb_spike_plan_shards(const uint8_t *sam, size_t n, const char *const *contig_names, int n_contigs,
+                          int count, int64_t halo_bases, ssb_spike_shard *shards, size_t *body_off, size_t *body_len);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,8 @@ extern "C" const char *ssb_strerror(int code)
     case SSB_E_REF:      return "contig missing from the reference FASTA or read past its end";
     case SSB_E_STATE:    return "call order violated";
     case SSB_E_NCCL:     return "NCCL error";
+    case SSB_E_PEER:     return "another shard of the cooperative run failed";
+    case SSB_E_SHARD:    return "a shard's alignment lines do not match its coordinate range (or its halo is too small)";
     default:             return "unknown error";
     }
 }

@@ -46,7 +46,16 @@ struct ContigNames {          // device: concatenated names + offsets, for RNAME
     const uint8_t *const *seq; const int64_t *len;
     // exceptional bases found while tokenising: (global line index << 16) | query offset.  The tally stage resolves them.
     unsigned long long *exc; unsigned long long *exc_count; unsigned long long exc_cap;
+    // shard support: a read whose last base lies before keep_lo = (tid << 32 | pos) belongs to an earlier shard's pileups only
+    // (it is one of the halo lines in front of this shard's own) and is not kept; n_keep counts the kept lines.
+    unsigned long long keep_lo; unsigned long long *n_keep;
 };
+
+// applies the shard's lower bound to a parsed record
+__device__ __forceinline__ void shard_keep(SamRec &r, const ContigNames &names)
+{
+    if ((r.bits & REC_KEEP) && ((((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.end) - 1 < names.keep_lo)) r.bits &= (uint8_t)~REC_KEEP;
+}
 
 __device__ __forceinline__ uint32_t nl_mask16(uint4 v)
 {
@@ -953,6 +962,8 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (e <= stage_end && e - s < 0x40000000ull) rc2 = parse_line_smem(cur, text + (s - T0), (uint32_t)(e - s), s, e < n, names, tid_cache, r2);
             else rc2 = parse_line(cur, s, e, names, tid_cache, r2);
             if (rc2) { if (atomicCAS(&err->code, 0, rc2) == 0) err->where = s; memset(&r2, 0, sizeof r2); r2.line_off = s; r2.tid = -1; }
+            shard_keep(r2, names);
+            if (r2.bits & REC_KEEP) atomicAdd(names.n_keep, 1ull);
             const unsigned long long g2 = gbase + i;
             if (g2 < rec_cap) recs[g2] = r2;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
@@ -1000,8 +1011,13 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 if (bad) rc = SSB_E_FORMAT;
             }
             if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = ls; memset(&r, 0, sizeof r); r.line_off = ls; r.tid = -1; }
+            shard_keep(r, names);
             if (gi < rec_cap) recs[gi] = r;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = ls;
+        }
+        {   // kept lines of this tile: one atomic per warp
+            const unsigned km = __ballot_sync(0xffffffffu, have && (r.bits & REC_KEEP));
+            if (lane == 0 && km) atomicAdd(names.n_keep, (unsigned long long)__popc(km));
         }
         // 5. hand the tile's exceptional bases over: one reservation per tile, coalesced stores
         if (names.exc) {

@@ -99,7 +99,8 @@ struct ChainArgs {
     DevErr *err;
 };
 
-struct ChunkDesc { int64_t g0, g1; unsigned long long k_in, k_out; };            // k_out = ~0: unknown (no check)
+struct ChunkDesc { int64_t g0, g1; unsigned long long k_in, k_out; };            // k_out = ~0: unknown (stop after the last target, no check)
+constexpr unsigned long long CHUNK_WALK_ONLY = ~0ull - 1;                        // k_out: walk to the end of the chunk, nothing to compare with
 enum { CHAIN_OVERRUN = 1, CHAIN_MISS = 2, CHAIN_COMPLEX = 4, CHAIN_INCONSISTENT = 8 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -545,14 +546,14 @@ __device__ __forceinline__ bool boundary_lookup(const GroupDesc &gd, int r, unsi
     return true;
 }
 
-// phase 2a: one warp walks the group maps in order.  gk[q] = exact draw offset at the start of group q.
+// phase 2a: one warp walks the group maps in order from the exact entry offset k_in.  gk[q] = exact draw offset at the start of group q.
 __global__ void __launch_bounds__(32)
 compose_kernel(int G, const GroupDesc *__restrict__ groups, const BoundaryList *__restrict__ lists, int max_nf,
                const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo,
-               unsigned long long *__restrict__ gk, unsigned int *__restrict__ flags)
+               const unsigned long long *__restrict__ k_in, unsigned long long *__restrict__ gk, unsigned long long *__restrict__ k_end, unsigned int *__restrict__ flags)
 {
     const int lane = threadIdx.x;
-    unsigned long long k = 0;
+    unsigned long long k = *k_in;
     for (int q = 0; q < G; q++) {
         const GroupDesc gd = groups[q];
         if (lane == 0) gk[q] = k;
@@ -571,6 +572,47 @@ compose_kernel(int G, const GroupDesc *__restrict__ groups, const BoundaryList *
         }
         k = pool_k[bl.off + best];
     }
+    if (lane == 0) *k_end = k;
+}
+
+// A shard that is entered with an offset it does not know yet (its predecessors are still working) prepares the answer:
+// for every survivor class of the FIRST group's last boundary, the offset at the end of the shard's last group.  When the exact
+// entry offset arrives, the exit offset is one lookup (entry_kernel) and can travel on at once.
+__global__ void precompose_kernel(int G, const GroupDesc *__restrict__ groups, const BoundaryList *__restrict__ lists, int max_nf,
+                                  const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo, unsigned long long *__restrict__ exit_k)
+{
+    const GroupDesc g0 = groups[0];
+    for (uint32_t sl = blockIdx.x; sl < g0.S; sl += gridDim.x) {
+        const BoundaryList bl = lists[(size_t)(g0.b0 + sl) * max_nf + (g0.nf - 1)];
+        for (uint32_t i = threadIdx.x; i < bl.cnt; i += blockDim.x) {
+            unsigned long long k = pool_k[bl.off + i];
+            bool ok = true;
+            for (int q = 1; q < G && ok; q++) {
+                const GroupDesc gd = groups[q];
+                unsigned long long kn;
+                ok = boundary_lookup(gd, gd.nf - 1, k, lists, max_nf, pool_k, pool_lo, kn);
+                k = kn;
+            }
+            exit_k[bl.off + i] = ok ? k : ~0ull;
+        }
+    }
+}
+
+// exact entry offset -> offset at the end of the shard (one thread); ~0 when the offset lies outside the simulated window
+__global__ void entry_kernel(const GroupDesc *__restrict__ groups, const BoundaryList *__restrict__ lists, int max_nf, const uint32_t *__restrict__ pool_lo,
+                             const unsigned long long *__restrict__ exit_k, const unsigned long long *__restrict__ k_in, unsigned long long *__restrict__ k_out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const GroupDesc gd = groups[0];
+    const unsigned long long k = *k_in;
+    if (k < gd.klo || k - gd.klo >= gd.W) { *k_out = ~0ull; return; }
+    const uint32_t idx = (uint32_t)(k - gd.klo);
+    uint32_t sl = idx / gd.w; if (sl >= gd.S) sl = gd.S - 1;
+    const BoundaryList bl = lists[(size_t)(gd.b0 + sl) * max_nf + (gd.nf - 1)];
+    const uint32_t *lo = pool_lo + bl.off;
+    uint32_t a = 0, b = bl.cnt;
+    while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (lo[mid] <= idx) a = mid; else b = mid; }
+    *k_out = bl.cnt ? exit_k[bl.off + a] : ~0ull;
 }
 
 // phase 2b: every chunk learns its exact entry and exit offsets from its group's boundary lists
@@ -602,7 +644,7 @@ chain_kernel(ChainArgs A, const ChunkDesc *__restrict__ chunks, int n_chunks, un
     if (c >= n_chunks) return;
     const ChunkDesc cd = chunks[c];
     int64_t g = cd.g0; unsigned long long k = cd.k_in;
-    unsigned long long odd_bloom = 0;
+    unsigned long long odd_bloom = (n_chunks == 1) ? *A.odd_bloom : 0ull;       // one chunk = the serial chain: odd patches handed in by an earlier shard are in the list already
     size_t h = first_hit_at_or_after(A.hits, A.H, g);
     for (; h < A.H && A.hits[h].locus_index < cd.g1; h++) {
         const HitTarget ht = A.hits[h];
@@ -723,7 +765,7 @@ chain_kernel(ChainArgs A, const ChunkDesc *__restrict__ chunks, int n_chunks, un
     if (cd.k_out != ~0ull) {
         // finish the chunk and compare with what phase 1/2 predicted
         if (!walk_loci<true>(A, g, cd.g1, k)) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_OVERRUN); return; }
-        if (k != cd.k_out && lane == 0) atomicOr(flags, (unsigned int)CHAIN_INCONSISTENT);
+        if (cd.k_out != CHUNK_WALK_ONLY && k != cd.k_out && lane == 0) atomicOr(flags, (unsigned int)CHAIN_INCONSISTENT);
     }
     if (lane == 0) { if (c == n_chunks - 1) *draws_out = k; if (n_chunks == 1) *A.odd_bloom = odd_bloom; }
 }

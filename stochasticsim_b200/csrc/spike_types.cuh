@@ -53,6 +53,9 @@ static_assert(sizeof(PlpEntry) == 16, "PlpEntry layout");
 
 struct __align__(16) Patch { uint32_t ord; uint32_t qpos; uint32_t base; uint32_t pad; };
 
+// a spiked base of a read that the NEXT shard writes: the read is named by its line index counted from the end of the body
+struct __align__(16) FwdPatch { uint32_t from_end; uint32_t qpos; uint32_t base; uint32_t order; };
+
 // a spike target that coincides with a covered locus, in covered order
 struct HitTarget {
     int64_t  locus_index;  // ordinal among covered loci

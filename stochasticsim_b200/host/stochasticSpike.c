@@ -15,7 +15,11 @@
  * decoded on the host (bam_input.h: parallel BGZF inflate + sam_format1-style printing) into the SAM text the
  * GPU tokeniser consumes.
  *
- * Environment: SSB_DEVICE=i selects the CUDA device (default 0).
+ * Environment: SSB_DEVICE=i selects the (first) CUDA device (default 0).  SSB_GPUS=N spreads ONE input over N GPUs: the body is
+ * cut into coordinate ranges (ssb_spike_plan_shards), one thread drives each shard, the shards hand the rand() offset on
+ * and the outputs are concatenated in shard order (ssb_spike_run_shard_host).  SSB_SHARDS=M (default N) makes M shards and
+ * places shard g on device g mod N; SSB_HALO=<bases> is the largest reference span a read may have (default 4096; the run
+ * is repeated with the measured value when a read turns out longer).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,6 +31,7 @@
 #include <unistd.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <pthread.h>
 #include "ssb200.h"
 #include "bam_input.h"
 
@@ -171,6 +176,48 @@ static void print_no_coverage(FILE *vcf, const target_rec *t)                   
     fprintf(vcf, "%s\t%ld\t.\t.\t.\t.\tNO_COVERAGE\t.\t.\n", t->contig, (long)t->t.locus + 1);
 }
 
+/* one shard of the input on one GPU (SSB_GPUS / SSB_SHARDS); a plain run is the single shard of a group of one */
+#define MAX_SHARDS 64
+typedef struct {
+    int device; ssb_spike_shard shard; ssb_exchange *xc;
+    const uint8_t *body; size_t n;
+    char **names; int n_names; const fasta_t *fa;
+    const ssb_target *targets; size_t T; unsigned seed;
+    ssb_target_result *res; uint8_t *out; size_t out_n; ssb_spike_stats st;
+    ssb_seq_error *se; size_t n_se;
+    int rc; char errtext[600];
+} shard_job;
+
+static void *shard_main(void *arg)
+{
+    shard_job *j = (shard_job *)arg;
+    ssb_ctx *ctx = NULL; ssb_spike *sp = NULL;
+    j->rc = ssb_ctx_create(j->device, &ctx);
+    if (j->rc) { snprintf(j->errtext, sizeof j->errtext, "device %d", j->device); goto fail; }
+    {
+        /* only the contigs this shard can touch are uploaded */
+        ssb_contig *contigs = xrealloc(NULL, sizeof(ssb_contig) * (size_t)(j->n_names + 1));
+        for (int t = 0; t < j->n_names; t++) {
+            contigs[t].name = j->names[t]; contigs[t].len = 0; contigs[t].seq = NULL;
+            if (j->shard.count > 1 && (t < j->shard.lo_tid || t > j->shard.hi_tid)) continue;
+            for (int i = 0; i < j->fa->n; i++) if (!strcmp(j->fa->name[i], j->names[t])) { contigs[t].len = j->fa->len[i]; contigs[t].seq = j->fa->seq[i]; break; }
+        }
+        j->rc = ssb_spike_create(ctx, contigs, j->n_names, &sp);
+        free(contigs);
+    }
+    if (!j->rc) j->rc = ssb_spike_run_shard_host(sp, &j->shard, j->xc, j->body, j->n, j->out, j->n + 1, j->targets, j->T, j->seed, j->res, &j->st, &j->out_n);
+    if (!j->rc) {
+        ssb_spike_seq_error_count(sp, &j->n_se);
+        j->se = xrealloc(NULL, sizeof(ssb_seq_error) * (j->n_se + 1));
+        j->rc = ssb_spike_seq_errors(sp, j->se, j->n_se);
+    }
+    if (j->rc) snprintf(j->errtext, sizeof j->errtext, "%s", ssb_last_error(ctx));
+fail:
+    if (sp) ssb_spike_destroy(sp);
+    if (ctx) ssb_ctx_destroy(ctx);
+    return NULL;
+}
+
 int main(int argc, char **argv)
 {
     char *cmd = strrchr(argv[0], '/'); cmd = cmd ? cmd + 1 : argv[0];                       /* :931-936 */
@@ -259,35 +306,76 @@ int main(int argc, char **argv)
     target_rec *tg; size_t T = load_targets(cfg, names, n_names, &tg);
     fclose(cfg);
 
-    /* ---- GPU ---- */
-    ssb_ctx *ctx; ssb_spike *sp;
+    /* ---- GPU(s) ---- */
     int dev = getenv("SSB_DEVICE") ? atoi(getenv("SSB_DEVICE")) : 0;
-    int rc = ssb_ctx_create(dev, &ctx);
-    if (rc) { fprintf(stderr, "%s: device %d: %s\n", cmd, dev, ssb_strerror(rc)); return 3; }
-    ssb_contig *contigs = xrealloc(NULL, sizeof(ssb_contig) * (size_t)(n_names + 1));
-    for (int t = 0; t < n_names; t++) {
-        contigs[t].name = names[t]; contigs[t].len = 0; contigs[t].seq = NULL;
-        for (int i = 0; i < fa.n; i++) if (!strcmp(fa.name[i], names[t])) { contigs[t].len = fa.len[i]; contigs[t].seq = fa.seq[i]; break; }
-    }
-    if ((rc = ssb_spike_create(ctx, contigs, n_names, &sp))) { fprintf(stderr, "%s: %s (%s)\n", cmd, ssb_strerror(rc), ssb_last_error(ctx)); return 3; }
+    int ngpu = getenv("SSB_GPUS") ? atoi(getenv("SSB_GPUS")) : 1;
+    int want = getenv("SSB_SHARDS") ? atoi(getenv("SSB_SHARDS")) : ngpu;
+    int64_t halo = getenv("SSB_HALO") ? atoll(getenv("SSB_HALO")) : 4096;
+    if (ngpu < 1) ngpu = 1;
+    if (want < 1) want = 1;
+    if (want > MAX_SHARDS) want = MAX_SHARDS;
     ssb_target *tarr = xrealloc(NULL, sizeof(ssb_target) * (T + 1));
     ssb_target_result *res = xrealloc(NULL, sizeof(ssb_target_result) * (T + 1));
     for (size_t t = 0; t < T; t++) tarr[t] = tg[t].t;
     size_t body_n = n_in - hdr_end, out_n = 0;
     uint8_t *body_out = xrealloc(NULL, body_n + 2);
     ssb_spike_stats st;
-    rc = ssb_spike_run_host(sp, in + hdr_end, body_n, body_out, body_n + 1, tarr, T, seed, res, &st, &out_n);
-    if (rc) {
-        fprintf(stderr, "%s: %s (%s)\n", cmd, ssb_strerror(rc), ssb_last_error(ctx));
-        return rc == SSB_E_REF ? 1 : 3;
+    ssb_seq_error *se = NULL; size_t n_se = 0;
+    int rc;
+    for (int round = 0;; round++) {
+        shard_job job[MAX_SHARDS]; ssb_spike_shard plan[MAX_SHARDS]; size_t off[MAX_SHARDS], len[MAX_SHARDS]; ssb_exchange *xcs[MAX_SHARDS];
+        int made = ssb_spike_plan_shards(in + hdr_end, body_n, (const char *const *)names, n_names, want, halo, plan, off, len);
+        if (made < 1) { fprintf(stderr, "%s: cannot cut the input into shards\n", cmd); return 3; }
+        if (made > 1 && ssb_exchange_local_create(made, xcs)) { fprintf(stderr, "%s: exchange\n", cmd); return 3; }
+        memset(job, 0, sizeof job);
+        for (int g = 0; g < made; g++) {
+            job[g].device = dev + g % ngpu; job[g].shard = plan[g]; job[g].xc = made > 1 ? xcs[g] : NULL;
+            job[g].body = in + hdr_end + off[g]; job[g].n = len[g];
+            job[g].names = names; job[g].n_names = n_names; job[g].fa = &fa;
+            job[g].targets = tarr; job[g].T = T; job[g].seed = seed;
+            job[g].res = xrealloc(NULL, sizeof(ssb_target_result) * (T + 1));
+            job[g].out = xrealloc(NULL, len[g] + 2);
+        }
+        pthread_t th[MAX_SHARDS];
+        for (int g = 1; g < made; g++) pthread_create(&th[g], NULL, shard_main, &job[g]);
+        shard_main(&job[0]);
+        for (int g = 1; g < made; g++) pthread_join(th[g], NULL);
+        if (made > 1) for (int g = 0; g < made; g++) ssb_exchange_destroy(xcs[g]);
+        rc = 0; int shard_err = 0; unsigned maxspan_msg = 0;
+        for (int g = 0; g < made; g++) if (job[g].rc && job[g].rc != SSB_E_PEER) { if (!rc) rc = job[g].rc; if (job[g].rc == SSB_E_SHARD) shard_err = 1; }
+        if (!rc) for (int g = 0; g < made; g++) if (job[g].rc) rc = job[g].rc;
+        if (shard_err && round == 0 && made > 1) {
+            /* a read is longer than the halo: take the next power of two that surely covers it and cut again */
+            halo = halo < 65536 ? 65536 : halo * 16; (void)maxspan_msg;
+            for (int g = 0; g < made; g++) { free(job[g].res); free(job[g].out); free(job[g].se); }
+            continue;
+        }
+        if (rc) {
+            for (int g = 0; g < made; g++) if (job[g].rc == rc) { fprintf(stderr, "%s: %s (%s)\n", cmd, ssb_strerror(job[g].rc), job[g].errtext); break; }
+            return rc == SSB_E_NODEVICE ? 3 : (rc == SSB_E_REF ? 1 : 3);
+        }
+        /* the shards' outputs in shard order are the reference's output; the stats block is their sum (maxDepth: maximum) */
+        memset(&st, 0, sizeof st);
+        for (int g = 0; g < made; g++) {
+            memcpy(body_out + out_n, job[g].out, job[g].out_n); out_n += job[g].out_n;
+            st.alignmentCount += job[g].st.alignmentCount; st.numberOfLociCovered += job[g].st.numberOfLociCovered;
+            st.totalFoldCoverage += job[g].st.totalFoldCoverage; if (job[g].st.maxDepth > st.maxDepth) st.maxDepth = job[g].st.maxDepth;
+            n_se += job[g].n_se;
+        }
+        se = xrealloc(NULL, sizeof(ssb_seq_error) * (n_se + 1));
+        size_t k = 0;
+        for (int g = 0; g < made; g++) { if (job[g].n_se) memcpy(se + k, job[g].se, job[g].n_se * sizeof *se); k += job[g].n_se; }
+        for (size_t t = 0; t < T; t++) {
+            int found = 0;
+            for (int g = 0; g < made; g++) if (job[g].res[t].status != SSB_T_ELSEWHERE) { res[t] = job[g].res[t]; found = 1; break; }
+            if (!found) { fprintf(stderr, "%s: target %zu was claimed by no shard\n", cmd, t); return 3; }
+        }
+        for (int g = 0; g < made; g++) { free(job[g].res); free(job[g].out); free(job[g].se); }
+        break;
     }
     if (out_n && fwrite(body_out, 1, out_n, out) != out_n) { fprintf(stderr, "Couldn't write out ...\n"); return 1; }   /* :275-278 */
 
     /* ---- truth.vcf: per covered locus its own line, then the NO_COVERAGE line of a target passed there ---- */
-    size_t n_se = 0;
-    ssb_spike_seq_error_count(sp, &n_se);
-    ssb_seq_error *se = xrealloc(NULL, sizeof(ssb_seq_error) * (n_se + 1));
-    ssb_spike_seq_errors(sp, se, n_se);
     size_t si = 0, t = 0;
     for (; t < T && res[t].status != SSB_T_TAIL; t++) {
         int64_t li = res[t].locus_index;
@@ -303,7 +391,6 @@ int main(int argc, char **argv)
     for (; t < T; t++) print_no_coverage(vcf, &tg[t]);                                        /* :1630-1646 */
 
     fclose(vcf); fclose(out);
-    ssb_spike_destroy(sp); ssb_ctx_destroy(ctx);
     fflush(stderr);
     if (st.numberOfLociCovered == 0) { fflush(stdout); raise(SIGFPE); }                       /* the reference divides by zero at :1668 */
     printf("\nDONE...\nalignmentCount (#reads) = %ld,\nnumberOfLociCovered = %ld\ntotalFoldCoverage = %ld\nmaxDepth = %ld, Avg. coverage = %ld\n",

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 from ._lib import lib, check
 
-T_HIT, T_NOCOV, T_NOCOV_SILENT, T_TAIL = 0, 1, 2, 3
+T_HIT, T_NOCOV, T_NOCOV_SILENT, T_TAIL, T_ELSEWHERE = 0, 1, 2, 3, 4
 FILTER_NAME = ["NONE", "PASS", "MASKED", "MASKED_OVL", "UNDETECTED"]
 
 
@@ -30,10 +30,18 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("alignmentCount", "numberOfLociCovered", "totalFoldCoverage", "maxDepth",
                                           "n_lines", "n_kept", "in_bytes", "out_bytes", "n_runs", "n_hits", "rng_draws", "chain_mode")] + \
                [(n, C.c_float) for n in ("ms_parse", "ms_sort", "ms_emit", "ms_cover", "ms_gather", "ms_rng", "ms_chain",
-                                          "ms_patch", "ms_total")]
+                                          "ms_patch", "ms_total")] + [("_pad0", C.c_float)] + \
+               [(n, C.c_int64) for n in ("rng_k_in", "rng_k_out", "locus_base", "n_forwarded")] + \
+               [(n, C.c_float) for n in ("ms_handoff_wait", "ms_phase1", "ms_tally", "ms_exchange")]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}
+
+
+class Shard(C.Structure):
+    """struct ssb_spike_shard: one coordinate range of a cooperative run."""
+    _fields_ = [("index", C.c_int32), ("count", C.c_int32), ("lo_tid", C.c_int32), ("hi_tid", C.c_int32),
+                ("lo_pos", C.c_int64), ("hi_pos", C.c_int64), ("halo_bytes", C.c_uint64)]
 
 
 class SeqError(C.Structure):
@@ -58,6 +66,24 @@ def _bind():
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [vp, vp, sz, vp, sz, C.POINTER(Target), sz, C.c_uint, C.POINTER(TargetResult), C.POINTER(Stats), C.POINTER(sz)]
+    for name in ("ssb_spike_run_shard_device", "ssb_spike_run_shard_host"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, C.POINTER(Shard), vp, vp, sz, vp, sz, C.POINTER(Target), sz, C.c_uint, C.POINTER(TargetResult), C.POINTER(Stats), C.POINTER(sz)]
+    L.ssb_exchange_local_create.restype = C.c_int
+    L.ssb_exchange_local_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.ssb_exchange_nccl_create.restype = C.c_int
+    L.ssb_exchange_nccl_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.ssb_exchange_destroy.restype = None
+    L.ssb_exchange_destroy.argtypes = [vp]
+    L.ssb_nccl_unique_id.restype = C.c_int
+    L.ssb_nccl_unique_id.argtypes = [vp]
+    L.ssb_nccl_comm_init_rank.restype = C.c_int
+    L.ssb_nccl_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.ssb_nccl_comm_destroy.restype = None
+    L.ssb_nccl_comm_destroy.argtypes = [vp]
+    L.ssb_spike_plan_shards.restype = C.c_int
+    L.ssb_spike_plan_shards.argtypes = [vp, sz, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int64, C.POINTER(Shard), C.POINTER(sz), C.POINTER(sz)]
     L.ssb_spike_rand.restype = C.c_int
     L.ssb_spike_rand.argtypes = [vp, C.c_uint, C.c_uint64, sz, vp]
     L.ssb_spike_seq_error_count.restype = C.c_int
@@ -181,6 +207,24 @@ class Spike:
                                            res, C.byref(st), C.byref(outn)), self.ctx.handle)
         return outn.value
 
+    def run_shard_host(self, shard, xc, body: bytes, targets, seed: int):
+        """One shard of a cooperative run (every shard of the group calls this, each from its own thread)."""
+        n = len(body)
+        src = np.frombuffer(body, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
+        dst = np.empty(n + 2, dtype=np.uint8)
+        tarr = self.make_targets(targets)
+        res = (TargetResult * max(1, len(targets)))()
+        st, outn = Stats(), C.c_size_t()
+        check(self._L.ssb_spike_run_shard_host(self.handle, C.byref(shard) if shard is not None else None, xc, src.ctypes.data, n, dst.ctypes.data, n + 1,
+                                               tarr, len(targets), seed & 0xFFFFFFFF, res, C.byref(st), C.byref(outn)), self.ctx.handle)
+        return dst[:outn.value].tobytes(), list(res)[:len(targets)], st
+
+    def run_shard_device(self, shard, xc, d_sam, n, d_out, out_cap, tarr, n_targets, seed, res, st):
+        outn = C.c_size_t()
+        check(self._L.ssb_spike_run_shard_device(self.handle, C.byref(shard) if shard is not None else None, xc, d_sam, n, d_out, out_cap, tarr, n_targets,
+                                                 seed & 0xFFFFFFFF, res, C.byref(st), C.byref(outn)), self.ctx.handle)
+        return outn.value
+
     def rand(self, seed, k0, n):
         out = np.zeros(n, dtype=np.int32)
         check(self._L.ssb_spike_rand(self.handle, seed & 0xFFFFFFFF, k0, n, out.ctypes.data), self.ctx.handle)
@@ -192,3 +236,77 @@ class Spike:
         arr = (SeqError * max(1, n.value))()
         check(self._L.ssb_spike_seq_errors(self.handle, arr, n.value))
         return list(arr)[:n.value]
+
+
+def plan_shards(body: bytes, names, count: int, halo_bases: int):
+    """[(Shard, body bytes of that shard)] -- ssb_spike_plan_shards over a host-resident SAM body."""
+    L = _bind()
+    shards = (Shard * count)()
+    off = (C.c_size_t * count)()
+    ln = (C.c_size_t * count)()
+    arr = (C.c_char_p * max(1, len(names)))(*[n.encode() for n in names])
+    buf = np.frombuffer(body, dtype=np.uint8) if len(body) else np.zeros(1, dtype=np.uint8)
+    made = L.ssb_spike_plan_shards(buf.ctypes.data, len(body), arr, len(names), count, halo_bases, shards, off, ln)
+    if made < 0:
+        check(made)
+    out = []
+    for g in range(made):
+        sh = Shard()
+        C.memmove(C.byref(sh), C.byref(shards[g]), C.sizeof(Shard))
+        out.append((sh, body[off[g]:off[g] + ln[g]]))
+    return out
+
+
+def local_exchange(n: int):
+    """n exchange handles for n shards driven by n threads of this process."""
+    L = _bind()
+    arr = (C.c_void_p * n)()
+    check(L.ssb_exchange_local_create(n, arr))
+    return [C.c_void_p(arr[i]) for i in range(n)]
+
+
+def exchange_destroy(xc):
+    _bind().ssb_exchange_destroy(xc)
+
+
+def run_sharded(ctxs, names, seqs, body: bytes, targets, seed: int, count: int, halo_bases: int):
+    """Cuts `body` into `count` coordinate shards and runs them as one cooperative group, one thread per shard (ctxs[i % len(ctxs)]
+    is the device context of shard i).  Returns (concatenated output, merged [TargetResult], [Stats per shard], [SeqError], n_shards)."""
+    import threading
+    plan = plan_shards(body, names, count, halo_bases)
+    n = len(plan)
+    xcs = local_exchange(n)
+    outs, errs = [None] * n, [None] * n
+    spikes = [Spike(ctxs[g % len(ctxs)], names, seqs) for g in range(n)]
+
+    def work(g):
+        try:
+            sh, piece = plan[g]
+            out, res, st = spikes[g].run_shard_host(sh, xcs[g], piece, targets, seed)
+            outs[g] = (out, res, st, spikes[g].seq_errors())
+        except Exception as e:  # noqa: BLE001 -- reported to the caller below
+            errs[g] = e
+
+    th = [threading.Thread(target=work, args=(g,)) for g in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for s_ in spikes:
+        s_.close()
+    for x in xcs:
+        exchange_destroy(x)
+    for e in errs:
+        if e is not None:
+            raise e
+    merged = []
+    for t in range(len(targets)):
+        pick = None
+        for g in range(n):
+            r = outs[g][1][t]
+            if r.status != T_ELSEWHERE:
+                assert pick is None, "two shards claim target %d" % t
+                pick = r
+        assert pick is not None, "no shard claims target %d" % t
+        merged.append(pick)
+    return b"".join(o[0] for o in outs), merged, [o[2] for o in outs], [e for o in outs for e in o[3]], n

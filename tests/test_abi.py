@@ -34,7 +34,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_abi_version_and_strerror():
     L = ssb.lib()
-    assert L.ssb_abi_version() == 1
+    assert L.ssb_abi_version() == 2
     assert b"no CPU fallback" in L.ssb_strerror(-2)
 
 
