@@ -124,7 +124,7 @@ __device__ __forceinline__ int name_lookup(const Cursor &cur, size_t p0, size_t 
 
 // One optional field [p, q): TAG:TYPE:VALUE in the form htslib prints back unchanged.
 template <typename AT>       // at(i): byte i of the body
-__device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
+__host__ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
 {
     if (q - p < 5 || at(p + 2) != ':' || at(p + 4) != ':') return SSB_E_FORMAT;
     uint8_t ty = at(p + 3);
@@ -137,7 +137,42 @@ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
         for (size_t i = a; i < b; i++) { uint8_t c = at(i); if (c < '0' || c > '9') return false; }
         return !(b - a == 1 && at(a) == '0' && a > v && at(a - 1) == '-');      // "-0"
     };
+    // Float text that htslib prints back unchanged: it parses the value into a 32-bit float and prints it with "%g" (six
+    // significant digits, trailing zeros dropped, exponent form outside 1e-4 .. 1e6).  A decimal of at most six significant
+    // digits survives the trip through a float (FLT_DIG = 6), so the text is its own "%g" image exactly when it has the shape
+    // "%g" produces: [-]ddd[.ddd] without superfluous zeros for exponents -4 .. 5, [-]d[.ddddd]e[+-]XX otherwise (normal range
+    // only), or inf / nan.
+    auto canon_float = [&](size_t a, size_t b) {
+        if (a < b && at(a) == '-') a++;
+        if (a >= b) return false;
+        if (b - a == 3 && ((at(a) == 'i' && at(a + 1) == 'n' && at(a + 2) == 'f') || (at(a) == 'n' && at(a + 1) == 'a' && at(a + 2) == 'n'))) return true;
+        size_t e = a; while (e < b && at(e) != 'e') e++;                       // mantissa [a, e), exponent text (e, b)
+        size_t dot = a; while (dot < e && at(dot) != '.') dot++;
+        const size_t ni = dot - a, nf = dot < e ? e - dot - 1 : 0;             // integer / fraction digits
+        if (ni == 0 || (dot < e && nf == 0)) return false;
+        for (size_t i = a; i < e; i++) { if (i == dot) continue; const uint8_t c = at(i); if (c < '0' || c > '9') return false; }
+        if (ni > 1 && at(a) == '0') return false;
+        if (nf && at(e - 1) == '0') return false;                              // "%g" drops trailing zeros
+        if (e == b) {
+            // fixed notation: decimal exponent X in [-4, 6)
+            if (at(a) != '0') return ni <= 6 && ni + nf <= 6;
+            if (nf == 0) return true;                                          // "0", "-0"
+            size_t z = 0; while (z < nf && at(dot + 1 + z) == '0') z++;
+            return z < nf && z <= 3 && nf - z <= 6;
+        }
+        // exponent notation: one non-zero digit before the point, sign, at least two exponent digits
+        if (ni != 1 || at(a) == '0' || 1 + nf > 6) return false;
+        size_t x = e + 1;
+        if (x >= b || (at(x) != '+' && at(x) != '-')) return false;
+        const bool neg = at(x) == '-'; x++;
+        if (b - x != 2) return false;
+        if (at(x) < '0' || at(x) > '9' || at(x + 1) < '0' || at(x + 1) > '9') return false;
+        const int X = (at(x) - '0') * 10 + (at(x + 1) - '0');
+        if (X > 37) return false;                                              // keep clear of overflow / denormals
+        return neg ? X >= 5 : X >= 6;                                          // inside -4 .. 5 "%g" would have used fixed notation
+    };
     switch (ty) {
+    case 'f': return canon_float(v, q) ? 0 : SSB_E_FORMAT;
     case 'A': return (q - v == 1 && at(v) >= '!' && at(v) <= '~') ? 0 : SSB_E_FORMAT;
     case 'i': return canon_int(v, q) ? 0 : SSB_E_FORMAT;
     case 'Z': for (size_t i = v; i < q; i++) { uint8_t c = at(i); if (c < ' ' || c > '~') return SSB_E_FORMAT; } return 0;
@@ -146,11 +181,12 @@ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
     case 'B': {
         if (q - v < 1) return SSB_E_FORMAT;
         uint8_t st = at(v);
-        if (st != 'c' && st != 'C' && st != 's' && st != 'S' && st != 'i' && st != 'I') return SSB_E_FORMAT;   // float arrays: %g round trip not guaranteed
+        if (st != 'c' && st != 'C' && st != 's' && st != 'S' && st != 'i' && st != 'I' && st != 'f') return SSB_E_FORMAT;
         size_t a = v + 1;
         while (a < q) {
             if (at(a) != ',') return SSB_E_FORMAT;
             size_t b = a + 1; while (b < q && at(b) != ',') b++;
+            if (st == 'f') { if (!canon_float(a + 1, b)) return SSB_E_FORMAT; a = b; continue; }
             size_t s0 = a + 1;
             if (s0 < b && at(s0) == '-') s0++;
             if (s0 >= b || (b - s0 > 1 && at(s0) == '0')) return SSB_E_FORMAT;
@@ -159,7 +195,7 @@ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
         }
         return 0;
     }
-    default: return SSB_E_FORMAT;      // 'f' and unknown types are outside the byte-exact pass-through envelope
+    default: return SSB_E_FORMAT;      // unknown types are outside the byte-exact pass-through envelope
     }
 }
 

@@ -964,9 +964,10 @@ tally_kernel(TallyArgs A)
         int64_t first = (int64_t)r.pos - (int64_t)A.maxspan + 1; if (first < 0) first = 0;
         size_t lo = lower_bound_u64(A.k_start, A.K, ((unsigned long long)(uint32_t)tid << 32) | (uint32_t)first);
         const unsigned long long lim = A.k_end[o];
-        for (size_t b = lo; b < A.K && A.k_start[b] < lim && n < 8; b++) {
+        for (size_t b = lo; b < A.K && A.k_start[b] < lim; b++) {
             if (b != o && (A.k_hash[b] != h || !same_qname(A.sam, r, A.recs[A.k_rec[b]]))) continue;
             if (b != o && (uint32_t)(A.k_end[b]) <= (uint32_t)r.pos) continue;
+            if (n == 8) { set_err(A.err, SSB_E_FORMAT, r.line_off); return; }       // more than eight overlapping alignments of one QNAME: refused, never miscounted
             if (b == o) self = n;
             mem[n++] = view_of(A.sam, A.recs[A.k_rec[b]], (uint32_t)b, A.odd, n_odd, bloom);
         }

@@ -173,7 +173,7 @@ struct ssb_spike {
     ssb_seq_error *d_se; size_t n_se;          // SEQ_ERROR records of the last run (device resident until asked for)
     // run plumbing
     cudaStream_t sA;                           // second stream: the output branch and the tallies
-    cudaEvent_t ev_pub, ev_pubA, ev_k, ev_sort, ev_emit, ev_cover, ev_tally, ev_t[16];
+    cudaEvent_t ev_pub, ev_pubA, ev_k, ev_sort, ev_outoff, ev_emit, ev_cover, ev_tally, ev_t[16];
     RunScalars *d_sc, *h_sc; RunScalarsA *d_scA, *h_scA;       // device scalars and their mapped pinned mirrors
     uint8_t *h_map; size_t h_map_bytes;        // mapped pinned scratch: descriptors kernels read, small arrays kernels write
     DevTarget *d_tg; std::vector<DevTarget> tg_host;           // targets of the last run (uploaded again only when they change)
@@ -196,7 +196,7 @@ void spike_free(ssb_spike *sp)
     if (sp->h_scA) cudaFreeHost(sp->h_scA);
     if (sp->h_map) cudaFreeHost(sp->h_map);
     if (sp->sA) cudaStreamDestroy(sp->sA);
-    cudaEvent_t *evs[] = {&sp->ev_pub, &sp->ev_pubA, &sp->ev_k, &sp->ev_sort, &sp->ev_emit, &sp->ev_cover, &sp->ev_tally};
+    cudaEvent_t *evs[] = {&sp->ev_pub, &sp->ev_pubA, &sp->ev_k, &sp->ev_sort, &sp->ev_outoff, &sp->ev_emit, &sp->ev_cover, &sp->ev_tally};
     for (cudaEvent_t *e : evs) if (*e) cudaEventDestroy(*e);
     for (int i = 0; i < 16; i++) if (sp->ev_t[i]) cudaEventDestroy(sp->ev_t[i]);
     delete sp;
@@ -212,7 +212,7 @@ extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_c
     sp->ctx = ctx; sp->n_contigs = n_contigs; sp->d_se = NULL; sp->n_se = 0;
     sp->d_names = NULL; sp->d_name_off = NULL; sp->d_seq_ptrs = NULL; sp->d_lens = NULL; sp->d_rng_tab = NULL;
     sp->sA = NULL; sp->d_sc = sp->h_sc = NULL; sp->d_scA = sp->h_scA = NULL; sp->h_map = NULL; sp->h_map_bytes = 0; sp->d_tg = NULL;
-    sp->ev_pub = sp->ev_pubA = sp->ev_k = sp->ev_sort = sp->ev_emit = sp->ev_cover = sp->ev_tally = NULL;
+    sp->ev_pub = sp->ev_pubA = sp->ev_k = sp->ev_sort = sp->ev_outoff = sp->ev_emit = sp->ev_cover = sp->ev_tally = NULL;
     for (int i = 0; i < 16; i++) sp->ev_t[i] = NULL;
     // every exit below releases what has been allocated so far
 #define SPK_CREATE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); spike_free(sp); return SSB_E_CUDA; } } while (0)
@@ -259,7 +259,7 @@ extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_c
         SPK_CREATE(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
         SPK_CREATE(cudaStreamCreateWithPriority(&sp->sA, cudaStreamNonBlocking, lo_prio));
     }
-    cudaEvent_t *evs[] = {&sp->ev_pub, &sp->ev_pubA, &sp->ev_k, &sp->ev_sort, &sp->ev_emit, &sp->ev_cover, &sp->ev_tally};
+    cudaEvent_t *evs[] = {&sp->ev_pub, &sp->ev_pubA, &sp->ev_k, &sp->ev_sort, &sp->ev_outoff, &sp->ev_emit, &sp->ev_cover, &sp->ev_tally};
     for (cudaEvent_t *e : evs) SPK_CREATE(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < 16; i++) SPK_CREATE(cudaEventCreate(&sp->ev_t[i]));
     SPK_CREATE(cudaMalloc(&sp->d_sc, sizeof(RunScalars)));
@@ -338,7 +338,10 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
 {
     ssb_ctx *ctx = sp->ctx;
     SSB_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream, sA = sp->sA;
+    // SSB_SCHED: 0 = one stream, every stage in issue order; 1 = output branch (emit, tallies) on the second stream beside phase 1;
+    // 2 = only the tallies beside phase 1, the copy of the text on the main stream in front of it
+    const int sched = getenv("SSB_SCHED") ? atoi(getenv("SSB_SCHED")) : 0;
+    cudaStream_t s = ctx->stream, sA = sched == 0 ? ctx->stream : sp->sA;
     memset(stats, 0, sizeof *stats);
     *out_bytes = 0;
     const char *dbg_env = getenv("SSB_CHAIN_DEBUG");
@@ -471,6 +474,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
 
     // ---------------------------------------------------------------- A: output order + emit (beside the chain branch)
     uint32_t *perm = NULL; unsigned long long *s_end = NULL, *out_off = NULL, *ord_off = NULL;
+    EmitDesc *d_edesc = NULL;
     SSB_CUDA(ctx, cudaStreamWaitEvent(sA, sp->ev_k, 0));
     if (K) {
         int rc;
@@ -490,20 +494,32 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         if ((rc = scan_sum(arA, ctx, olen, out_off, K))) return rc;
         SSB_LAUNCH(ctx, out_total_kernel, 1, 32, 0, sA, out_off, olen, K, &dscA->total_out);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, ordoff_kernel, grid_for(K, 256), 256, 0, sA, perm, out_off, K, ord_off);
+        SSB_CUDA(ctx, cudaEventRecord(sp->ev_outoff, sA));
         if (out_cap < n + 1) {                 // the output may not fit: look before writing
             if ((rc = publishA())) return rc;
             if (hscA->total_out > out_cap) { snprintf(ctx->err, sizeof ctx->err, "spike: output needs %llu bytes, capacity %zu", (unsigned long long)hscA->total_out, out_cap); return SSB_E_ARG; }
         }
-        SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[8], sA));
-        {
-            const char *ev_ = getenv("SSB_EMIT_VARIANT"); const int v = ev_ ? atoi(ev_) : 0;
-            const int per_sm = (v >= 2 && v <= 8) ? v : 5;           // resident emit blocks per SM: fewer than the 8 that fit leave room for the chain branch
-            if (v == 1) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, (emit_kernel<2, 4>), ctx->sm_count * 4, 256, 0, sA, d_sam, n, edesc, out_off, K, d_out);
-            else SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, (emit_kernel<1, 8>), ctx->sm_count * per_sm, 256, 0, sA, d_sam, n, edesc, out_off, K, d_out);
-        }
-        SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[9], sA));
+        d_edesc = edesc;
     } else SSB_CUDA(ctx, cudaEventRecord(sp->ev_sort, sA));
-    SSB_CUDA(ctx, cudaEventRecord(sp->ev_emit, sA));
+    // The copy of the text (DRAM bound) and the tallies are held back until the chain branch reaches its long issue-bound stretch
+    // (phase 1), so that they run beside it instead of slowing the short kernels before it down.
+    bool emit_launched = false;
+    auto launch_emit = [&]() -> int {
+        if (emit_launched) return SSB_OK;
+        emit_launched = true;
+        cudaStream_t se = sched == 1 ? sA : s;
+        if (K) {
+            if (se != sA) SSB_CUDA(ctx, cudaStreamWaitEvent(se, sp->ev_outoff, 0));
+            SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[8], se));
+            const char *ev_ = getenv("SSB_EMIT_VARIANT"); const int v = ev_ ? atoi(ev_) : 0;
+            const int per_sm = (v >= 2 && v <= 8) ? v : (sched == 1 ? 3 : 8);   // resident emit blocks per SM (beside the chain branch: fewer)
+            if (v == 1) SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, (emit_kernel<2, 4>), ctx->sm_count * 4, 256, 0, se, d_sam, n, d_edesc, out_off, K, d_out);
+            else SSB_LAUNCH_P(ctx, SSB_K_SPIKE_EMIT, (emit_kernel<1, 8>), ctx->sm_count * per_sm, 256, 0, se, d_sam, n, d_edesc, out_off, K, d_out);
+            SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[9], se));
+        }
+        SSB_CUDA(ctx, cudaEventRecord(sp->ev_emit, se));
+        return SSB_OK;
+    };
 
     // ---------------------------------------------------------------- M: mates, coverage runs
     size_t R = 0; int64_t n_cov = 0;
@@ -564,20 +580,28 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_TALLY, tally_kernel, grid_for(K, 128), 128, 0, st, TA);
         return SSB_OK;
     };
-    if (n_cov) {
-        int rc;
-        err64 = arA.get<unsigned long long>((size_t)n_cov + 1); minus = arA.get<unsigned int>((size_t)n_cov + 1);
-        SPK_CHECK_ARENA(arA);
-        TA.sam = d_sam; TA.recs = recs; TA.k_rec = k_rec; TA.k_start = k_start; TA.k_end = k_end; TA.k_hash = k_hash; TA.k_bits = k_bits; TA.K = K;
-        TA.nxt = nxt; TA.prv = prv; TA.cplx = cplx; TA.maxspan = h_maxspan; TA.runs = runs; TA.R = R;
-        TA.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; TA.contig_len = sp->d_lens; TA.err64 = err64; TA.minus = minus; TA.err = d_err;
-        TA.odd = d_odd; TA.n_odd = d_nodd; TA.odd_bloom = d_bloom; TA.listed_only = use_list ? 1 : 0; TA.rg = rg;
-        SSB_CUDA(ctx, cudaStreamWaitEvent(sA, sp->ev_cover, 0));
-        SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[10], sA));
-        if ((rc = tally_pass(sA))) return rc;
-        SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[11], sA));
-    }
-    SSB_CUDA(ctx, cudaEventRecord(sp->ev_tally, sA));
+    bool tally_launched = false;
+    auto launch_tally = [&]() -> int {
+        if (tally_launched) return SSB_OK;
+        tally_launched = true;
+        if (n_cov) {
+            int rc;
+            err64 = arA.get<unsigned long long>((size_t)n_cov + 1); minus = arA.get<unsigned int>((size_t)n_cov + 1);
+            SPK_CHECK_ARENA(arA);
+            TA.sam = d_sam; TA.recs = recs; TA.k_rec = k_rec; TA.k_start = k_start; TA.k_end = k_end; TA.k_hash = k_hash; TA.k_bits = k_bits; TA.K = K;
+            TA.nxt = nxt; TA.prv = prv; TA.cplx = cplx; TA.maxspan = h_maxspan; TA.runs = runs; TA.R = R;
+            TA.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; TA.contig_len = sp->d_lens; TA.err64 = err64; TA.minus = minus; TA.err = d_err;
+            TA.odd = d_odd; TA.n_odd = d_nodd; TA.odd_bloom = d_bloom; TA.listed_only = use_list ? 1 : 0; TA.rg = rg;
+            SSB_CUDA(ctx, cudaStreamWaitEvent(sA, sp->ev_cover, 0));
+            SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[10], sA));
+            if ((rc = tally_pass(sA))) return rc;
+            SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[11], sA));
+        }
+        SSB_CUDA(ctx, cudaEventRecord(sp->ev_tally, sA));
+        return SSB_OK;
+    };
+    // held: the output branch starts beside phase 1 (see launch_emit)
+    auto launch_output_branch = [&]() -> int { int rc; if ((rc = launch_emit())) return rc; return launch_tally(); };
 
     // ---------------------------------------------------------------- shards: who owns how many loci
     long long ord_base = 0, total_cov = n_cov;
@@ -832,6 +856,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     }
     SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[5], s));
     dbg_mark("gathered");
+    { int rc; if ((rc = launch_output_branch())) return rc; }
 
     // ---- shards: where in the stream does this shard begin (expected), and how sure is that
     double c_in = (double)k_in, v_in = 0;
@@ -1334,4 +1359,10 @@ extern "C" int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t ca
         SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return SSB_OK;
+}
+
+// test hook (host only): the optional-field check of the tokeniser on one TAG:TYPE:VALUE text
+extern "C" int ssb_test_aux_ok(const char *field, size_t n)
+{
+    return samparse::aux_ok_t([=](size_t i) -> uint8_t { return (uint8_t)field[i]; }, (size_t)0, n);
 }

@@ -9,6 +9,9 @@ GEN = os.path.join(ROOT, "tools", "_build", "gen_synth")
 ORACLE = os.path.join(ROOT, "oracle", "_build", "spike_oracle")
 REF = os.path.join(ROOT, "oracle", "_ref", "stochasticSpike")
 PRODUCT = os.path.join(ROOT, "stochasticsim_b200", "lib", "stochasticSpike")
+# what the GPU path is diffed against: the UNMODIFIED reference over the htslib shim when it has been built (it travels to the
+# GPU box as a binary), else the restatement (which tests/test_spike_oracle.py pins to that binary on every input family)
+CHECKER = REF if os.path.exists(REF) else ORACLE
 
 # name -> gen_synth arguments (+ optional edits of the .spike table)
 CASES = {

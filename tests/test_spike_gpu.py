@@ -1,5 +1,6 @@
-"""GPU parity: the spike path of libssb200 (through the C ABI and through the drop-in C main) against the
-oracle restatement -- SAM bytes, truth.vcf and the stats block must be identical."""
+"""GPU parity: the spike path of libssb200 (through the C ABI and through the drop-in C main) against the reference binary
+(oracle/_ref/stochasticSpike = the unmodified reference over the htslib shim; the restated oracle when that binary is absent)
+-- SAM bytes, truth.vcf and the stats block must be identical."""
 import os
 import shutil
 import subprocess
@@ -58,7 +59,7 @@ def test_rand_stream_matches_glibc(ctx):
 @pytest.mark.parametrize("name", sorted(sc.CASES))
 def test_cli_parity(name, tmp_path, ctx):
     prefix = sc.generate(name, str(tmp_path))
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
     assert want[0] == 0
     assert got[0] == 0, got[4]
@@ -70,7 +71,7 @@ def test_cli_parity(name, tmp_path, ctx):
 @pytest.mark.parametrize("seed", [1, 434, 99991])
 def test_seeds(seed, tmp_path, ctx):
     prefix = sc.generate("overlap_heavy", str(tmp_path), coverage=25, contigs="chr19:8000", spikes=60)
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), seed=seed, cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), seed=seed, cmdname="stochasticSpike")
     got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"), seed=seed)
     assert got[0] == 0, got[4]
     assert got[2] == want[2], first_diff(want[2], got[2])
@@ -83,7 +84,7 @@ def test_parallel_chain_matches_serial(name, chunk, group, slice_, tmp_path, ctx
     """The chunked chain (windows of candidate offsets cut into slices, merging walkers, recorded chunk boundaries, composed
     group maps) against the oracle, and against the one-warp serial chain: same SAM, same per-target results, same draw count."""
     prefix = sc.generate(name, str(tmp_path))
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     sam = open(prefix + ".sam", "rb").read()
     hdr, body, names = sp.split_header(sam)
     seqs = sp.parse_fasta(open(prefix + ".fa", "rb").read())
@@ -110,7 +111,7 @@ def test_bam_input(name, tmp_path, ctx):
     """argv[1] as a real BGZF BAM (what bin/spikeIn.bash passes): same SAM, truth.vcf body and stats as from the SAM text."""
     import bam_writer
     prefix = sc.generate(name, str(tmp_path))
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     bam = tmp_path / "in.bam"
     bam.write_bytes(bam_writer.sam_to_bam(open(prefix + ".sam", "rb").read()))
     # the reference insists on an index next to the BAM (stochasticSpike.c:1035-1039)
@@ -144,7 +145,7 @@ def test_fuzz_configs(k, tmp_path, ctx, monkeypatch):
         monkeypatch.setenv("SSB_CHAIN_SLICE", str(rng.choice([2, 33, 4096])))
     if k % 3 == 0:
         monkeypatch.setenv("SSB_NO_EXC_LIST", "1")
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), seed=434 + k, cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), seed=434 + k, cmdname="stochasticSpike")
     got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"), seed=434 + k)
     assert want[0] == 0 and got[0] == 0, got[4]
     assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
@@ -167,7 +168,7 @@ def test_golden_fixture(tmp_path, ctx):
 def test_abi_run_host(tmp_path, ctx):
     """The same through the ctypes binding: body in, body out, per-target results."""
     prefix = sc.generate("plain", str(tmp_path))
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     sam = open(prefix + ".sam", "rb").read()
     hdr, body, names = sp.split_header(sam)
     seqs = sp.parse_fasta(open(prefix + ".fa", "rb").read())
@@ -294,7 +295,7 @@ def _long_read_case(dirname, read_lens, seed=7):
 def test_long_reads(read_lens, tmp_path, ctx):
     """Lines longer than the staged overhang, than a whole tile, and tiles that hold no line start at all."""
     prefix = _long_read_case(str(tmp_path), read_lens)
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
     assert want[0] == 0 and got[0] == 0, got[4]
     assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
@@ -306,7 +307,7 @@ def test_short_reads_many_lines_per_tile(tmp_path, ctx):
     """36 bp reads: ~300 lines per 32 KiB tile, more than the tokeniser has parsing threads, so every tile also takes its
     second-round path (careful parser, no exception list for those reads)."""
     prefix = sc.generate("plain", str(tmp_path), contigs="chr19:20000", read_len=36, frag_mean=60, frag_sd=6, coverage=60, spikes=80)
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
     assert want[0] == 0 and got[0] == 0, got[4]
     assert len(want[2]) > 3_000_000
@@ -319,7 +320,7 @@ def test_error_rich_reads_overflow_the_tile_exception_buffer(tmp_path, ctx):
     """15 % substitutions, 10 % BQ-0 bases, 2 % N: far more than 1024 exceptional bases per tile, so the tokeniser's per-tile
     buffer fills up and the reads that no longer fit are left to the generic tally."""
     prefix = sc.generate("plain", str(tmp_path), contigs="chr19:12000", coverage=40, sub=0.15, q0=0.1, nrate=0.02, spikes=60)
-    want = sc.run_cli(sc.ORACLE, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
     got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
     assert want[0] == 0 and got[0] == 0, got[4]
     assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])

@@ -12,7 +12,7 @@ import spike_cases as sc
 import stochasticsim_b200 as ssb
 from stochasticsim_b200 import spike as sp
 
-CHECKER = sc.REF if os.path.exists(sc.REF) else sc.ORACLE
+CHECKER = sc.CHECKER
 
 
 def _load(prefix):
