@@ -199,8 +199,11 @@ def run(args, D):
     Lb = sp._bind()
 
     def e2e_step():
-        ssb.check(Lb.ssb_spike_run_shard_host(S.handle, C.byref(shard) if shard is not None else None, xc, hp, n, hout, n + 1, tarr, len(targets), SPIKE_SEED,
-                                              res, C.byref(st), C.byref(outn)), ctx.handle)
+        if shard is None:       # one GPU: the body is streamed through the device in coordinate pieces, both directions of the host link busy
+            ssb.check(Lb.ssb_spike_run_host(S.handle, hp, n, hout, n + 1, tarr, len(targets), SPIKE_SEED, res, C.byref(st), C.byref(outn)), ctx.handle)
+        else:
+            ssb.check(Lb.ssb_spike_run_shard_host(S.handle, C.byref(shard), xc, hp, n, hout, n + 1, tarr, len(targets), SPIKE_SEED,
+                                                  res, C.byref(st), C.byref(outn)), ctx.handle)
 
     e2e_step()
     D.barrier()
@@ -209,6 +212,20 @@ def run(args, D):
         e2e_step()
     e2e_s = D.max(time.perf_counter() - t0)
     assert outn.value == out_bytes
+    e2e_pieces = int(st.n_forwarded) if shard is None else 0
+    # the streamed output must be the device-resident run's output, byte for byte (checked on a sample of 64 MiB windows)
+    if shard is None:
+        import torch
+        dev = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+        host = np.empty(64 << 20, dtype=np.uint8)
+        step()
+        for w0 in range(0, int(out_bytes), 1 << 30):
+            w = min(64 << 20, int(out_bytes) - w0)
+            ctx.d2h(host.ctypes.data, d_out + w0, w)
+            ctx.sync()
+            got = np.ctypeslib.as_array((C.c_uint8 * w).from_address(hout + w0))
+            assert np.array_equal(got, host[:w]), "streamed e2e output differs from the device-resident run at offset %d" % w0
+        del dev
 
     # size-independent properties at full size: every kept read written once, same multiset of bytes up to the spiked bases
     assert stats["alignmentCount"] == stats["n_kept"] and out_bytes == stats["out_bytes"]
@@ -232,7 +249,8 @@ def run(args, D):
                    "all-gather of the expected draw counts, the exact rand() offset as an 8-byte send/recv from shard g to g+1, all-gather of the verdict; "
                    "no alignment text moves" % len(targets)},
         "e2e": {"value": total_reads * e2e_steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(out_bytes),
-                "steps": e2e_steps, "api": "ssb_spike_run%s_host (pinned host SAM body -> spiked SAM body on the host)" % ("" if N == 1 else "_shard")},
+                "steps": e2e_steps, "api": "ssb_spike_run%s_host (pinned host SAM body -> spiked SAM body on the host)" % ("" if N == 1 else "_shard"),
+                "streamed_pieces": e2e_pieces},
         "gpu_launches": launches,
         # the whole pass is the unit the north star's "sustained" bandwidth means; the kernels below explain it
         "roofline": {"bound": "hbm", "kernel": "whole pass (every kernel of one step, per GPU)", "achieved": whole,

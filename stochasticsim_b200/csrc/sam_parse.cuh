@@ -49,6 +49,7 @@ struct ContigNames {          // device: concatenated names + offsets, for RNAME
     // shard support: a read whose last base lies before keep_lo = (tid << 32 | pos) belongs to an earlier shard's pileups only
     // (it is one of the halo lines in front of this shard's own) and is not kept; n_keep counts the kept lines.
     unsigned long long keep_lo; unsigned long long *n_keep;
+    unsigned long long *n_float;      // lines flagged REC_AUX_F
 };
 
 // applies the shard's lower bound to a parsed record
@@ -122,7 +123,47 @@ __device__ __forceinline__ int name_lookup(const Cursor &cur, size_t p0, size_t 
     return -1;
 }
 
+// Float text that htslib prints back unchanged: it parses the value into a 32-bit float and prints it with "%g" (six
+// significant digits, trailing zeros dropped, exponent form outside 1e-4 .. 1e6).  A decimal of at most six significant
+// digits survives the trip through a float (FLT_DIG = 6), so the text is its own "%g" image exactly when it has the shape
+// "%g" produces: [-]ddd[.ddd] without superfluous zeros for exponents -4 .. 5, [-]d[.ddddd]e[+-]XX otherwise (normal range
+// only), or inf / nan.
+template <typename AT>
+__host__ __device__ __noinline__ bool canon_float_t(const AT &at, size_t a, size_t b)
+{
+    if (a < b && at(a) == '-') a++;
+    if (a >= b) return false;
+    if (b - a == 3 && ((at(a) == 'i' && at(a + 1) == 'n' && at(a + 2) == 'f') || (at(a) == 'n' && at(a + 1) == 'a' && at(a + 2) == 'n'))) return true;
+    size_t e = a; while (e < b && at(e) != 'e') e++;                       // mantissa [a, e), exponent text (e, b)
+    size_t dot = a; while (dot < e && at(dot) != '.') dot++;
+    const size_t ni = dot - a, nf = dot < e ? e - dot - 1 : 0;             // integer / fraction digits
+    if (ni == 0 || (dot < e && nf == 0)) return false;
+    for (size_t i = a; i < e; i++) { if (i == dot) continue; const uint8_t c = at(i); if (c < '0' || c > '9') return false; }
+    if (ni > 1 && at(a) == '0') return false;
+    if (nf && at(e - 1) == '0') return false;                              // "%g" drops trailing zeros
+    if (e == b) {
+        // fixed notation: decimal exponent X in [-4, 6)
+        if (at(a) != '0') return ni <= 6 && ni + nf <= 6;
+        if (nf == 0) return true;                                          // "0", "-0"
+        size_t z = 0; while (z < nf && at(dot + 1 + z) == '0') z++;
+        return z < nf && z <= 3 && nf - z <= 6;
+    }
+    // exponent notation: one non-zero digit before the point, sign, at least two exponent digits
+    if (ni != 1 || at(a) == '0' || 1 + nf > 6) return false;
+    size_t x = e + 1;
+    if (x >= b || (at(x) != '+' && at(x) != '-')) return false;
+    const bool neg = at(x) == '-'; x++;
+    if (b - x != 2) return false;
+    if (at(x) < '0' || at(x) > '9' || at(x + 1) < '0' || at(x + 1) > '9') return false;
+    const int X = (at(x) - '0') * 10 + (at(x + 1) - '0');
+    if (X > 37) return false;                                              // keep clear of overflow / denormals
+    return neg ? X >= 5 : X >= 6;                                          // inside -4 .. 5 "%g" would have used fixed notation
+}
+
 // One optional field [p, q): TAG:TYPE:VALUE in the form htslib prints back unchanged.
+// Float-typed fields (TAG:f:..., TAG:B:f,...) are not judged while tokenising (their check is long and would cost every line
+// registers): the tokeniser answers AUX_FLOAT, the line is flagged REC_AUX_F, and aux_float_kernel judges the flagged lines.
+constexpr int AUX_FLOAT = 1;
 template <typename AT>       // at(i): byte i of the body
 __host__ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q)
 {
@@ -137,42 +178,8 @@ __host__ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q
         for (size_t i = a; i < b; i++) { uint8_t c = at(i); if (c < '0' || c > '9') return false; }
         return !(b - a == 1 && at(a) == '0' && a > v && at(a - 1) == '-');      // "-0"
     };
-    // Float text that htslib prints back unchanged: it parses the value into a 32-bit float and prints it with "%g" (six
-    // significant digits, trailing zeros dropped, exponent form outside 1e-4 .. 1e6).  A decimal of at most six significant
-    // digits survives the trip through a float (FLT_DIG = 6), so the text is its own "%g" image exactly when it has the shape
-    // "%g" produces: [-]ddd[.ddd] without superfluous zeros for exponents -4 .. 5, [-]d[.ddddd]e[+-]XX otherwise (normal range
-    // only), or inf / nan.
-    auto canon_float = [&](size_t a, size_t b) {
-        if (a < b && at(a) == '-') a++;
-        if (a >= b) return false;
-        if (b - a == 3 && ((at(a) == 'i' && at(a + 1) == 'n' && at(a + 2) == 'f') || (at(a) == 'n' && at(a + 1) == 'a' && at(a + 2) == 'n'))) return true;
-        size_t e = a; while (e < b && at(e) != 'e') e++;                       // mantissa [a, e), exponent text (e, b)
-        size_t dot = a; while (dot < e && at(dot) != '.') dot++;
-        const size_t ni = dot - a, nf = dot < e ? e - dot - 1 : 0;             // integer / fraction digits
-        if (ni == 0 || (dot < e && nf == 0)) return false;
-        for (size_t i = a; i < e; i++) { if (i == dot) continue; const uint8_t c = at(i); if (c < '0' || c > '9') return false; }
-        if (ni > 1 && at(a) == '0') return false;
-        if (nf && at(e - 1) == '0') return false;                              // "%g" drops trailing zeros
-        if (e == b) {
-            // fixed notation: decimal exponent X in [-4, 6)
-            if (at(a) != '0') return ni <= 6 && ni + nf <= 6;
-            if (nf == 0) return true;                                          // "0", "-0"
-            size_t z = 0; while (z < nf && at(dot + 1 + z) == '0') z++;
-            return z < nf && z <= 3 && nf - z <= 6;
-        }
-        // exponent notation: one non-zero digit before the point, sign, at least two exponent digits
-        if (ni != 1 || at(a) == '0' || 1 + nf > 6) return false;
-        size_t x = e + 1;
-        if (x >= b || (at(x) != '+' && at(x) != '-')) return false;
-        const bool neg = at(x) == '-'; x++;
-        if (b - x != 2) return false;
-        if (at(x) < '0' || at(x) > '9' || at(x + 1) < '0' || at(x + 1) > '9') return false;
-        const int X = (at(x) - '0') * 10 + (at(x + 1) - '0');
-        if (X > 37) return false;                                              // keep clear of overflow / denormals
-        return neg ? X >= 5 : X >= 6;                                          // inside -4 .. 5 "%g" would have used fixed notation
-    };
     switch (ty) {
-    case 'f': return canon_float(v, q) ? 0 : SSB_E_FORMAT;
+    case 'f': return AUX_FLOAT;
     case 'A': return (q - v == 1 && at(v) >= '!' && at(v) <= '~') ? 0 : SSB_E_FORMAT;
     case 'i': return canon_int(v, q) ? 0 : SSB_E_FORMAT;
     case 'Z': for (size_t i = v; i < q; i++) { uint8_t c = at(i); if (c < ' ' || c > '~') return SSB_E_FORMAT; } return 0;
@@ -181,12 +188,12 @@ __host__ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q
     case 'B': {
         if (q - v < 1) return SSB_E_FORMAT;
         uint8_t st = at(v);
-        if (st != 'c' && st != 'C' && st != 's' && st != 'S' && st != 'i' && st != 'I' && st != 'f') return SSB_E_FORMAT;
+        if (st == 'f') return AUX_FLOAT;
+        if (st != 'c' && st != 'C' && st != 's' && st != 'S' && st != 'i' && st != 'I') return SSB_E_FORMAT;
         size_t a = v + 1;
         while (a < q) {
             if (at(a) != ',') return SSB_E_FORMAT;
             size_t b = a + 1; while (b < q && at(b) != ',') b++;
-            if (st == 'f') { if (!canon_float(a + 1, b)) return SSB_E_FORMAT; a = b; continue; }
             size_t s0 = a + 1;
             if (s0 < b && at(s0) == '-') s0++;
             if (s0 >= b || (b - s0 > 1 && at(s0) == '0')) return SSB_E_FORMAT;
@@ -197,6 +204,23 @@ __host__ __device__ __forceinline__ int aux_ok_t(const AT at, size_t p, size_t q
     }
     default: return SSB_E_FORMAT;      // unknown types are outside the byte-exact pass-through envelope
     }
+}
+
+// the float-typed field [p, q) in full: TAG:f:<float> or TAG:B:f,<float>,...
+template <typename AT>
+__host__ __device__ int aux_float_ok_t(const AT &at, size_t p, size_t q)
+{
+    if (q - p < 6 || at(p + 2) != ':' || at(p + 4) != ':') return SSB_E_FORMAT;
+    if (at(p + 3) == 'f') return canon_float_t(at, p + 5, q) ? 0 : SSB_E_FORMAT;
+    if (at(p + 3) != 'B' || at(p + 5) != 'f') return SSB_E_FORMAT;
+    size_t a = p + 6;
+    while (a < q) {
+        if (at(a) != ',') return SSB_E_FORMAT;
+        size_t b = a + 1; while (b < q && at(b) != ',') b++;
+        if (!canon_float_t(at, a + 1, b)) return SSB_E_FORMAT;
+        a = b;
+    }
+    return 0;
 }
 
 __device__ int aux_ok(const Cursor &cur, size_t p, size_t q)
@@ -382,7 +406,7 @@ __device__ int parse_line(const Cursor &cur, size_t s, size_t e, const ContigNam
     while (p < e) {
         size_t a = p + 1, q = a;                    // cur.at(p) == '\t'
         while (q < e && cur.at(q) != '\t') q++;
-        if (aux_ok(cur, a, q)) return SSB_E_FORMAT;
+        { const int ar = aux_ok(cur, a, q); if (ar == AUX_FLOAT) r.bits |= REC_AUX_F; else if (ar) return SSB_E_FORMAT; }
         p = q;
     }
     // read_bam (stochasticSpike.c:253-263) + bam_plp_push's tid test
@@ -557,7 +581,7 @@ __device__ int parse_line_smem(const Cursor &cur, const uint8_t *L, uint32_t len
     for (size_t q = s + qend; q < s + len;) {
         size_t a = q + 1, b = a;
         while (b < s + len && cur.at(b) != '\t') b++;
-        if (aux_ok(cur, a, b)) return SSB_E_FORMAT;
+        { const int ar = aux_ok(cur, a, b); if (ar == AUX_FLOAT) r.bits |= REC_AUX_F; else if (ar) return SSB_E_FORMAT; }
         q = b;
     }
     // read_bam (stochasticSpike.c:253-263) + bam_plp_push's tid test
@@ -1000,6 +1024,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (rc2) { if (atomicCAS(&err->code, 0, rc2) == 0) err->where = s; memset(&r2, 0, sizeof r2); r2.line_off = s; r2.tid = -1; }
             shard_keep(r2, names);
             if (r2.bits & REC_KEEP) atomicAdd(names.n_keep, 1ull);
+            if (r2.bits & REC_AUX_F) atomicAdd(names.n_float, 1ull);
             const unsigned long long g2 = gbase + i;
             if (g2 < rec_cap) recs[g2] = r2;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
@@ -1041,7 +1066,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 for (uint32_t q = qend; q < len;) {                      // optional fields, straight from shared memory
                     uint32_t a = q + 1, b = a;
                     while (b < len && L[b] != '\t') b++;
-                    if (aux_ok_smem(L, a, b)) bad = 1;
+                    { const int ar = aux_ok_smem(L, a, b); if (ar == AUX_FLOAT) r.bits |= REC_AUX_F; else if (ar) bad = 1; }
                     q = b;
                 }
                 if (bad) rc = SSB_E_FORMAT;
@@ -1054,6 +1079,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         {   // kept lines of this tile: one atomic per warp
             const unsigned km = __ballot_sync(0xffffffffu, have && (r.bits & REC_KEEP));
             if (lane == 0 && km) atomicAdd(names.n_keep, (unsigned long long)__popc(km));
+            if (have && (r.bits & REC_AUX_F)) atomicAdd(names.n_float, 1ull);            // rare: only inputs with float-typed tags
         }
         // 5. hand the tile's exceptional bases over: one reservation per tile, coalesced stores
         if (names.exc) {
@@ -1071,6 +1097,29 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 if (lane == 0) s_nexc = 0;
             }
         }
+    }
+}
+
+// Judges the float-typed optional fields of the lines the tokeniser flagged (REC_AUX_F): one thread per line.
+__global__ void aux_float_kernel(const uint8_t *__restrict__ body, size_t n, const SamRec *__restrict__ recs, size_t N, SpikeErr *__restrict__ err)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const SamRec r = recs[i];
+    if (!(r.bits & REC_AUX_F)) return;
+    const uint8_t *L = body + r.line_off;
+    const size_t len = r.line_len - ((r.bits & REC_NO_NL) ? 0 : 1);
+    size_t q = r.qual_off;                                        // walk from QUAL to its end, then field by field
+    while (q < len && L[q] != '\t') q++;
+    auto at = [=](size_t k) -> uint8_t { return L[k]; };
+    while (q < len) {
+        size_t a = q + 1, b = a;
+        while (b < len && L[b] != '\t') b++;
+        if (b - a >= 6 && (L[a + 3] == 'f' || (L[a + 3] == 'B' && L[a + 5] == 'f')) && aux_float_ok_t(at, a, b)) {
+            if (atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = r.line_off;
+            return;
+        }
+        q = b;
     }
 }
 

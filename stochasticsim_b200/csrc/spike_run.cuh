@@ -21,18 +21,19 @@
 //   M  join A; patches; SEQ_ERROR records ............................ sync 6: record count; results back
 #include "exchange.cuh"
 #include <chrono>
+#include <string>
 
 namespace {
 
 struct RunScalars {                 // written by kernels of the main stream, mirrored to the host on demand
-    unsigned long long n_lines, n_keep, exc_count;
+    unsigned long long n_lines, n_keep, exc_count, n_float;
     DevErr err;
     unsigned long long fold; unsigned int maxspan, maxdepth;
     unsigned int n_runs, pad0; unsigned long long n_cov;
     unsigned int H, pad1; unsigned long long E; long long last_hit_locus;
     unsigned int flags, n_odd, n_patches, n_fwd;
     unsigned long long odd_bloom, draws, pool_used, k_out, k_end;
-    unsigned long long n_se, first_strad;
+    unsigned long long n_se, first_strad, halo_lines;
     long long carry_t, carry_h;
 };
 struct RunScalarsA {                // written by kernels of the second stream
@@ -43,6 +44,41 @@ __global__ void copy_words_kernel(const uint32_t *__restrict__ src, uint32_t *__
 {
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
     __threadfence_system();
+}
+// plain device-to-device copy of bytes by SM threads (keeps the copy engines free for the host link); 16-byte words where both
+// sides allow it
+__global__ void copy_bytes_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const size_t nv = n >> 4;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src); uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (size_t i = tid; i < nv; i += nt) d4[i] = s4[i];
+        for (size_t i = (nv << 4) + tid; i < n; i += nt) dst[i] = src[i];
+    } else if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) == 0) {
+        const size_t head = (16 - ((uintptr_t)dst & 15)) & 15, h = head < n ? head : n;
+        for (size_t i = tid; i < h; i += nt) dst[i] = src[i];
+        const size_t nv = (n - h) >> 4;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src + h); uint4 *d4 = reinterpret_cast<uint4 *>(dst + h);
+        for (size_t i = tid; i < nv; i += nt) d4[i] = s4[i];
+        for (size_t i = h + (nv << 4) + tid; i < n; i += nt) dst[i] = src[i];
+    } else {
+        // different alignment: aligned 16-byte stores, the source words shifted into place from 4-byte loads
+        const size_t head = (16 - ((uintptr_t)dst & 15)) & 15, h = head < n ? head : n;
+        for (size_t i = tid; i < h; i += nt) dst[i] = src[i];
+        const size_t nv = (n - h) >> 4;
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst + h);
+        const uint8_t *sb = src + h;
+        const uint32_t a = (uint32_t)((uintptr_t)sb & 3u);
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sb - a);
+        for (size_t i = tid; i + 1 < nv; i += nt) {             // the last word may not read past the end of the source
+            const uint32_t w0 = sw[4 * i], w1 = sw[4 * i + 1], w2 = sw[4 * i + 2], w3 = sw[4 * i + 3], w4 = sw[4 * i + 4];
+            uint4 o; o.x = __funnelshift_r(w0, w1, a * 8); o.y = __funnelshift_r(w1, w2, a * 8); o.z = __funnelshift_r(w2, w3, a * 8); o.w = __funnelshift_r(w3, w4, a * 8);
+            d4[i] = o;
+        }
+        const size_t done = nv ? h + ((nv - 1) << 4) : h;
+        for (size_t i = done + tid; i < n; i += nt) dst[i] = src[i];
+    }
 }
 __global__ void out_total_kernel(const unsigned long long *__restrict__ out_off, const unsigned long long *__restrict__ olen, size_t K, unsigned long long *__restrict__ total)
 {
@@ -177,6 +213,12 @@ struct ssb_spike {
     RunScalars *d_sc, *h_sc; RunScalarsA *d_scA, *h_scA;       // device scalars and their mapped pinned mirrors
     uint8_t *h_map; size_t h_map_bytes;        // mapped pinned scratch: descriptors kernels read, small arrays kernels write
     DevTarget *d_tg; std::vector<DevTarget> tg_host;           // targets of the last run (uploaded again only when they change)
+    std::vector<std::string> names;                            // @SQ names (host copy: the streamed run cuts the body by coordinate)
+    std::vector<std::pair<ssb_seq_error *, size_t>> se_chunks;  // SEQ_ERROR records of a streamed run: one device array per piece, fetched on demand
+    bool se_chunked;
+    uint8_t *h_res; size_t h_res_bytes;                        // mapped pinned buffer the per-target results are written into
+    // buffers of the streamed host run (kept between calls: allocating and freeing gigabytes per call costs more than the run)
+    uint8_t *st_staging[3], *st_work[2], *st_obuf[2]; size_t st_slot; cudaStream_t st_out; std::vector<cudaEvent_t> st_ev;
 };
 
 namespace {
@@ -195,6 +237,12 @@ void spike_free(ssb_spike *sp)
     if (sp->h_sc) cudaFreeHost(sp->h_sc);
     if (sp->h_scA) cudaFreeHost(sp->h_scA);
     if (sp->h_map) cudaFreeHost(sp->h_map);
+    if (sp->h_res) cudaFreeHost(sp->h_res);
+    for (int i = 0; i < 3; i++) if (sp->st_staging[i]) cudaFree(sp->st_staging[i]);
+    for (int i = 0; i < 2; i++) { if (sp->st_work[i]) cudaFree(sp->st_work[i]); if (sp->st_obuf[i]) cudaFree(sp->st_obuf[i]); }
+    for (cudaEvent_t e : sp->st_ev) if (e) cudaEventDestroy(e);
+    if (sp->st_out) cudaStreamDestroy(sp->st_out);
+    for (auto &c : sp->se_chunks) if (c.first) cudaFree(c.first);
     if (sp->sA) cudaStreamDestroy(sp->sA);
     cudaEvent_t *evs[] = {&sp->ev_pub, &sp->ev_pubA, &sp->ev_k, &sp->ev_sort, &sp->ev_outoff, &sp->ev_emit, &sp->ev_cover, &sp->ev_tally};
     for (cudaEvent_t *e : evs) if (*e) cudaEventDestroy(*e);
@@ -209,7 +257,11 @@ extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_c
     *out = NULL;
     SSB_CUDA(ctx, cudaSetDevice(ctx->device));
     ssb_spike *sp = new ssb_spike();
-    sp->ctx = ctx; sp->n_contigs = n_contigs; sp->d_se = NULL; sp->n_se = 0;
+    sp->ctx = ctx; sp->n_contigs = n_contigs; sp->d_se = NULL; sp->n_se = 0; sp->se_chunked = false; sp->h_res = NULL; sp->h_res_bytes = 0;
+    for (int i = 0; i < 3; i++) sp->st_staging[i] = NULL;
+    for (int i = 0; i < 2; i++) { sp->st_work[i] = NULL; sp->st_obuf[i] = NULL; }
+    sp->st_slot = 0; sp->st_out = NULL;
+    for (int i = 0; i < n_contigs; i++) sp->names.push_back(contigs[i].name ? contigs[i].name : "");
     sp->d_names = NULL; sp->d_name_off = NULL; sp->d_seq_ptrs = NULL; sp->d_lens = NULL; sp->d_rng_tab = NULL;
     sp->sA = NULL; sp->d_sc = sp->h_sc = NULL; sp->d_scA = sp->h_scA = NULL; sp->h_map = NULL; sp->h_map_bytes = 0; sp->d_tg = NULL;
     sp->ev_pub = sp->ev_pubA = sp->ev_k = sp->ev_sort = sp->ev_outoff = sp->ev_emit = sp->ev_cover = sp->ev_tally = NULL;
@@ -266,7 +318,7 @@ extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_c
     SPK_CREATE(cudaMalloc(&sp->d_scA, sizeof(RunScalarsA)));
     SPK_CREATE(cudaHostAlloc((void **)&sp->h_sc, sizeof(RunScalars), cudaHostAllocMapped));
     SPK_CREATE(cudaHostAlloc((void **)&sp->h_scA, sizeof(RunScalarsA), cudaHostAllocMapped));
-    sp->h_map_bytes = (size_t)8 << 20;
+    sp->h_map_bytes = (size_t)32 << 20;
     SPK_CREATE(cudaHostAlloc((void **)&sp->h_map, sp->h_map_bytes, cudaHostAllocMapped));
 #undef SPK_CREATE
     *out = sp;
@@ -356,6 +408,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
 
     if (sp->d_se) { cudaFreeAsync(sp->d_se, s); sp->d_se = NULL; }
     sp->n_se = 0;
+    if (!pl.seq) { for (auto &c : sp->se_chunks) if (c.first) cudaFreeAsync(c.first, s); sp->se_chunks.clear(); sp->se_chunked = false; }
     stats->in_bytes = (int64_t)n;
     Arena ar(s), arA(sA);
     // declared after the arenas, so destroyed first: nothing may still run when the arenas give their memory back
@@ -429,7 +482,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             SSB_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
             if (attempt) { SSB_CUDA(ctx, cudaMemsetAsync(dsc, 0, sizeof(RunScalars), s)); SSB_CUDA(ctx, cudaMemsetAsync(&dsc->first_strad, 0xff, sizeof(unsigned long long), s)); }
             samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_lens,
-                                        no_list ? NULL : exc_list, &dsc->exc_count, exc_cap, rg.lo, &dsc->n_keep};
+                                        no_list ? NULL : exc_list, &dsc->exc_count, exc_cap, rg.lo, &dsc->n_keep, &dsc->n_float};
             int occ = 1;
             SSB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, samparse::parse_kernel, samparse::THREADS, samparse::SMEM_BYTES));
             if (occ < 1) occ = 1;
@@ -445,6 +498,8 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     }
     stats->n_lines = (int64_t)N;
     stats->n_kept = (int64_t)K;
+    if (N && hsc->n_float)       // float-typed optional fields: judged out of line (errors surface at the next look at the error word)
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, samparse::aux_float_kernel, grid_for(N, 128), 128, 0, s, d_sam, n, recs, N, reinterpret_cast<SpikeErr *>(d_err));
     SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[1], s));
     dbg_mark("parsed");
 
@@ -452,8 +507,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     uint32_t *keep = NULL, *kord = NULL;
     uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL, *prv = NULL; uint8_t *cplx = NULL, *k_bits = NULL;
     unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL; uint32_t *k_hash32 = NULL;
-    unsigned long long *d_halo_lines = ar.get<unsigned long long>(1); SPK_CHECK_ARENA(ar);
-    SSB_CUDA(ctx, cudaMemsetAsync(d_halo_lines, 0, 8, s));
+    unsigned long long *d_halo_lines = &dsc->halo_lines;
     if (N) {
         keep = ar.get<uint32_t>(N); kord = ar.get<uint32_t>(N);
         unsigned long long *pkey = ar.get<unsigned long long>(N), *pmax = ar.get<unsigned long long>(N);
@@ -545,7 +599,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     if (hsc->err.code) return fail_dev("sorted");
     R = hsc->n_runs; n_cov = (int64_t)hsc->n_cov;
     const unsigned int h_maxspan = hsc->maxspan;
-    const unsigned long long h_first_strad = hsc->first_strad;
+    const unsigned long long h_first_strad = hsc->first_strad, h_halo_lines = hsc->halo_lines;
     stats->totalFoldCoverage = (int64_t)hsc->fold;
     stats->n_runs = (int64_t)R;
     stats->numberOfLociCovered = n_cov;
@@ -699,8 +753,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     ChainArgs A;
     memset(&A, 0, sizeof A);
     unsigned long long k_base = 0, M_abs = 0, stream_extra = 0;
-    unsigned long long halo_lines = 0;
-    if (pl.halo_bytes && N) { SSB_CUDA(ctx, cudaMemcpyAsync(&halo_lines, d_halo_lines, 8, cudaMemcpyDeviceToHost, s)); SSB_CUDA(ctx, cudaStreamSynchronize(s)); }
+    const unsigned long long halo_lines = h_halo_lines;
 
     auto import_odd = [&]() -> int {           // odd patches handed in by the shard before: part of the list before this shard's chain starts
         if (odd_in.empty()) return SSB_OK;
@@ -733,11 +786,13 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         glibc_poly_xpow(310 + k_base, cur);
         for (size_t b = 0; b < nblocks; b++) { memcpy(&bp[b * GLIBC_DEG], cur, sizeof cur); glibc_poly_mulmod(cur, stepb, tmpb); memcpy(cur, tmpb, sizeof cur); }
         const size_t ewords = (size_t)(M >> 5) + 160;
-        uint32_t *d_bp = ar.get<uint32_t>(bp.size()); int32_t *Rs = ar.get<int32_t>(M + 64);
+        int32_t *Rs = ar.get<int32_t>(M + 64);
         uint32_t *pe0 = ar.get<uint32_t>(ewords), *pe1 = ar.get<uint32_t>(ewords), *pej = ar.get<uint32_t>(ewords);
         SPK_CHECK_ARENA(ar);
-        SSB_CUDA(ctx, cudaMemcpyAsync(d_bp, bp.data(), bp.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        SSB_CUDA(ctx, cudaStreamSynchronize(s));                  // bp is a local
+        uint8_t *bp_h = NULL, *bp_d = NULL;                       // the generator reads its polynomial straight from mapped host memory (once per block)
+        { int rcm; if ((rcm = map_get(bp.size() * sizeof(uint32_t), &bp_h, &bp_d))) return rcm; }
+        memcpy(bp_h, bp.data(), bp.size() * sizeof(uint32_t));
+        const uint32_t *d_bp = (const uint32_t *)bp_d;
         SSB_CUDA(ctx, cudaMemsetAsync(pe0 + (M >> 5), 0xAA, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pe1 + (M >> 5), 0xCC, 160 * 4, s)); SSB_CUDA(ctx, cudaMemsetAsync(pej + (M >> 5), 0, 160 * 4, s));   // all four classes in every nibble: see walk_loci
         SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[12], s));
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, rng_fill_kernel, (int)nblocks, RNG_TPB, 0, s, d_bp, sp->d_rng_tab, (const uint32_t *)sw_d, Rs, M, pe0, pe1, pej);
@@ -933,9 +988,15 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             unsigned long long *d_kin = ar.get<unsigned long long>(1);
             if (!exact_entry) exit_k = ar.get<unsigned long long>(pool_cap);
             SPK_CHECK_ARENA(ar);
-            SSB_CUDA(ctx, cudaMemcpyAsync(d_groups, h_groups.data(), G * sizeof(GroupDesc), cudaMemcpyHostToDevice, s));
-            SSB_CUDA(ctx, cudaMemcpyAsync(d_slices, h_slices.data(), n_slices * sizeof(SliceDesc), cudaMemcpyHostToDevice, s));
-            SSB_CUDA(ctx, cudaStreamSynchronize(s));              // the vectors are rebuilt on a retry
+            {   // descriptors: host -> mapped scratch -> device arrays by a kernel (no copy engine: it may be busy with the host link)
+                static_assert(sizeof(GroupDesc) % 4 == 0 && sizeof(SliceDesc) % 4 == 0, "descriptor words");
+                uint8_t *gh = NULL, *gd_ = NULL, *sh_ = NULL, *sd_ = NULL;
+                if ((rc = map_get(G * sizeof(GroupDesc), &gh, &gd_))) return rc;
+                if ((rc = map_get(n_slices * sizeof(SliceDesc), &sh_, &sd_))) return rc;
+                memcpy(gh, h_groups.data(), G * sizeof(GroupDesc)); memcpy(sh_, h_slices.data(), n_slices * sizeof(SliceDesc));
+                SSB_LAUNCH(ctx, copy_words_kernel, 4, 256, 0, s, (const uint32_t *)gd_, (uint32_t *)d_groups, (unsigned int)(G * sizeof(GroupDesc) / 4));
+                SSB_LAUNCH(ctx, copy_words_kernel, 16, 256, 0, s, (const uint32_t *)sd_, (uint32_t *)d_slices, (unsigned int)(n_slices * sizeof(SliceDesc) / 4));
+            }
             SSB_LAUNCH(ctx, chunks_init_kernel, (P + 127) / 128, 128, 0, s, d_chunks, P, Lc, n_walk);
             unsigned long long *d_dbg = NULL;
             if (dbg_t) { d_dbg = ar.get<unsigned long long>(8 + 2 * n_slices); SPK_CHECK_ARENA(ar); SSB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (8 + 2 * n_slices) * 8, s)); }
@@ -1063,13 +1124,15 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         int rc;
         // bases this shard spiked into reads the next shard writes
         if ((xc || seq) && chain_ran && patches) {
-            const unsigned int fwd_cap = patch_cap;
-            FwdPatch *d_fwd = ar.get<FwdPatch>(fwd_cap); SPK_CHECK_ARENA(ar);
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, fwd_collect_kernel, 16, 256, 0, s, patches, &dsc->n_patches, k_rec, k_end, rg, (unsigned long long)N, d_fwd, &dsc->n_fwd, fwd_cap, d_err);
+            // written by the kernel straight into mapped host memory (a handful of entries: reads that straddle the cut AND were spiked)
+            const unsigned int fwd_cap = patch_cap < 32768u ? patch_cap : 32768u;
+            uint8_t *fh = NULL, *fd = NULL;
+            if ((rc = map_get((size_t)fwd_cap * sizeof(FwdPatch), &fh, &fd))) return rc;
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, fwd_collect_kernel, 16, 256, 0, s, patches, &dsc->n_patches, k_rec, k_end, rg, (unsigned long long)N, (FwdPatch *)fd, &dsc->n_fwd, fwd_cap, d_err);
             if ((rc = publish())) return rc;
+            if (hsc->err.code) return fail_dev("forward");
             const unsigned int nf = hsc->n_fwd < fwd_cap ? hsc->n_fwd : fwd_cap;
-            fwd_out.resize(nf);
-            if (nf) { SSB_CUDA(ctx, cudaMemcpyAsync(fwd_out.data(), d_fwd, nf * sizeof(FwdPatch), cudaMemcpyDeviceToHost, s)); SSB_CUDA(ctx, cudaStreamSynchronize(s)); }
+            fwd_out.assign((const FwdPatch *)fh, (const FwdPatch *)fh + nf);
         }
         if (xc) {
             unsigned long long cnt_out = fwd_out.size(), cnt_in = 0;
@@ -1089,10 +1152,10 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 for (FwdPatch &u : uniq) if (u.from_end == f.from_end && u.qpos == f.qpos) { if (f.order >= u.order) u = f; found = true; break; }
                 if (!found) uniq.push_back(f);
             }
-            FwdPatch *d_in = ar.get<FwdPatch>(uniq.size()); SPK_CHECK_ARENA(ar);
-            SSB_CUDA(ctx, cudaMemcpyAsync(d_in, uniq.data(), uniq.size() * sizeof(FwdPatch), cudaMemcpyHostToDevice, s));
-            SSB_CUDA(ctx, cudaStreamSynchronize(s));
-            SSB_LAUNCH(ctx, fwd_apply_kernel, 4, 128, 0, s, d_in, (unsigned int)uniq.size(), halo_lines, keep, kord, recs, k_end, ord_off, rg, d_out, d_err);
+            uint8_t *ih = NULL, *id_ = NULL;
+            if ((rc = map_get(uniq.size() * sizeof(FwdPatch), &ih, &id_))) return rc;
+            memcpy(ih, uniq.data(), uniq.size() * sizeof(FwdPatch));
+            SSB_LAUNCH(ctx, fwd_apply_kernel, 4, 128, 0, s, (const FwdPatch *)id_, (unsigned int)uniq.size(), halo_lines, keep, kord, recs, k_end, ord_off, rg, d_out, d_err);
         }
         if (chain_ran && patches) {
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, patch_kernel, 64, 256, 0, s, patches, &dsc->n_patches, recs, k_rec, k_end, ord_off, rg, d_out);
@@ -1122,13 +1185,34 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         }
     }
     SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[7], s));
-    if (T) {
-        if (d_res) SSB_CUDA(ctx, cudaMemcpyAsync(results, d_res, T * sizeof(ssb_target_result), cudaMemcpyDeviceToHost, s));
+    // per-target results: written by a kernel into mapped host memory.  Shards processed one after the other only report the targets
+    // they consumed (a contiguous run of the table, plus the left-over tail on the last shard): the rest is SSB_T_ELSEWHERE.
+    size_t r_lo = 0, r_hi = T;
+    if (T && d_res) {
+        { int rc; if ((rc = publish())) return rc; }
+        if (seq) { r_lo = (size_t)seq->carry_t; r_hi = is_last ? T : (size_t)hsc->carry_t; if (r_hi < r_lo) r_hi = r_lo; }
+        const size_t nb = (r_hi - r_lo) * sizeof(ssb_target_result);
+        if (nb > sp->h_res_bytes) {
+            SSB_CUDA(ctx, cudaStreamSynchronize(s));
+            if (sp->h_res) { cudaFreeHost(sp->h_res); sp->h_res = NULL; sp->h_res_bytes = 0; }
+            SSB_CUDA(ctx, cudaHostAlloc((void **)&sp->h_res, nb + (nb >> 2) + 4096, cudaHostAllocMapped));
+            sp->h_res_bytes = nb + (nb >> 2) + 4096;
+        }
+        if (nb) {
+            uint8_t *hr_dev = NULL;
+            SSB_CUDA(ctx, cudaHostGetDevicePointer((void **)&hr_dev, sp->h_res, 0));
+            static_assert(sizeof(ssb_target_result) % 4 == 0, "result words");
+            SSB_LAUNCH(ctx, copy_words_kernel, 64, 256, 0, s, (const uint32_t *)(d_res + r_lo), (uint32_t *)hr_dev, (unsigned int)(nb / 4));
+        }
     }
     { int rc; if ((rc = publish())) return rc; if ((rc = publishA())) return rc; }
     SSB_CUDA(ctx, cudaStreamSynchronize(s));
     SSB_CUDA(ctx, cudaStreamSynchronize(sA));
     if (hsc->err.code) return fail_dev("finish");
+    if (T && d_res) {
+        if (seq) for (size_t t = 0; t < T; t++) if (t < r_lo || t >= r_hi) { memset(&results[t], 0, sizeof results[t]); results[t].status = SSB_T_ELSEWHERE; results[t].at_tid = -1; results[t].at_pos = -1; results[t].rng_offset = -1; }
+        if (r_hi > r_lo) memcpy(results + r_lo, sp->h_res, (r_hi - r_lo) * sizeof(ssb_target_result));
+    }
     *out_bytes = (size_t)hscA->total_out;
     stats->out_bytes = (int64_t)hscA->total_out;
     stats->alignmentCount = (int64_t)hscA->n_owned;                                       // every read is written exactly once, by the shard that owns its last base (:1275,:1365)
@@ -1226,10 +1310,137 @@ extern "C" int ssb_spike_run_shard_host(ssb_spike *sp, const ssb_spike_shard *sh
     return rc;
 }
 
+namespace {
+// A host-resident body of any size on ONE device, in bounded device memory: the body is cut into coordinate shards of about
+// `piece` bytes that are processed one after the other, each from the exact state its predecessor left (rand() offset, targets
+// consumed, covered-locus count, spiked bases of straddling reads) -- so no windows of candidate offsets are needed -- while the
+// host link works in both directions: H2D of shard i+1, i+2 || compute of shard i || D2H of shard i-1's output.
+//   staging[3]  H2D targets (own lines of a shard)
+//   work[2]     [lines of the previous shard that reach into this one][own lines], start 16-byte aligned
+//   obuf[2]     output lines of a shard until they have gone back
+int run_stream_host(ssb_spike *sp, const uint8_t *sam, size_t n, uint8_t *out, size_t out_cap, const ssb_target *targets, size_t T, unsigned seed,
+                    ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes, size_t piece)
+{
+    ssb_ctx *ctx = sp->ctx;
+    SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+    memset(stats, 0, sizeof *stats);
+    *out_bytes = 0;
+    int count = (int)((n + piece - 1) / piece);
+    std::vector<ssb_spike_shard> plan((size_t)count); std::vector<size_t> off((size_t)count), len((size_t)count);
+    std::vector<const char *> nm; for (const std::string &x : sp->names) nm.push_back(x.c_str());
+    count = ssb_spike_plan_shards(sam, n, nm.data(), (int)nm.size(), count, 0, plan.data(), off.data(), len.data());
+    if (count < 1) return SSB_E_ARG;
+    size_t slot = 0; for (int i = 0; i < count; i++) if (len[i] > slot) slot = len[i];
+    slot = (slot + 255) & ~(size_t)255;
+    const size_t halo_cap = (size_t)64 << 20;
+    cudaStream_t sc = ctx->stream, sIn = ctx->copy_stream;
+    const double t_alloc = now_ms();
+    if (!sp->st_out) SSB_CUDA(ctx, cudaStreamCreateWithFlags(&sp->st_out, cudaStreamNonBlocking));
+    cudaStream_t sOut = sp->st_out;
+    if (slot > sp->st_slot) {
+        SSB_CUDA(ctx, cudaStreamSynchronize(sc)); SSB_CUDA(ctx, cudaStreamSynchronize(sIn)); SSB_CUDA(ctx, cudaStreamSynchronize(sOut));
+        for (int i = 0; i < 3; i++) { if (sp->st_staging[i]) cudaFree(sp->st_staging[i]); sp->st_staging[i] = NULL; }
+        for (int i = 0; i < 2; i++) { if (sp->st_work[i]) cudaFree(sp->st_work[i]); if (sp->st_obuf[i]) cudaFree(sp->st_obuf[i]); sp->st_work[i] = sp->st_obuf[i] = NULL; }
+        sp->st_slot = 0;
+        for (int i = 0; i < 3; i++) SSB_CUDA(ctx, cudaMalloc(&sp->st_staging[i], slot + 256));
+        for (int i = 0; i < 2; i++) { SSB_CUDA(ctx, cudaMalloc(&sp->st_work[i], slot + halo_cap + 512)); SSB_CUDA(ctx, cudaMalloc(&sp->st_obuf[i], slot + halo_cap + 512)); }
+        sp->st_slot = slot;
+    }
+    slot = sp->st_slot;
+    uint8_t **staging = sp->st_staging, **work = sp->st_work, **obuf = sp->st_obuf;
+    while (sp->st_ev.size() < (size_t)count * 4) { cudaEvent_t e = NULL; SSB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); sp->st_ev.push_back(e); }
+    cudaEvent_t *ev_in = sp->st_ev.data(), *ev_free = ev_in + count, *ev_done = ev_in + 2 * count, *ev_out = ev_in + 3 * count;
+    // whatever happens, nothing of this run may still be in flight when the caller gets its buffers back
+    struct Quiesce { cudaStream_t a, b, c; ~Quiesce() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); cudaStreamSynchronize(c); } } quiesce{sc, sIn, sOut};
+    if (getenv("SSB_CHAIN_DEBUG")) fprintf(stderr, "[stream] buffers and events: %.3f ms\n", now_ms() - t_alloc);
+    auto copy_in = [&](int j) -> int {              // own lines of shard j -> staging[j % 3] (once the slot's previous tenant has been consumed)
+        if (j >= count) return SSB_OK;
+        if (j >= 3) SSB_CUDA(ctx, cudaStreamWaitEvent(sIn, ev_free[j - 3], 0));
+        if (len[j]) SSB_CUDA(ctx, cudaMemcpyAsync(staging[j % 3], sam + off[j], len[j], cudaMemcpyHostToDevice, sIn));
+        SSB_CUDA(ctx, cudaEventRecord(ev_in[j], sIn));
+        return SSB_OK;
+    };
+    int rc;
+    const bool dbg = getenv("SSB_CHAIN_DEBUG") != NULL;
+    const double t_setup = now_ms();
+    for (int j = 0; j < 3; j++) if ((rc = copy_in(j))) return rc;
+    if (dbg) fprintf(stderr, "[stream] %d pieces, slot %zu bytes; first copies queued at %.3f ms\n", count, slot, now_ms() - t_setup);
+    SeqState st;
+    std::vector<ssb_target_result> res_tmp(T ? T : 1);
+    for (size_t t = 0; t < T; t++) { memset(&results[t], 0, sizeof results[t]); results[t].status = SSB_T_ELSEWHERE; }
+    for (auto &c : sp->se_chunks) if (c.first) cudaFree(c.first);
+    sp->se_chunks.clear(); sp->se_chunked = true;
+    size_t out_off = 0, prev_n = 0, n_se_total = 0; uint8_t *prev_body = NULL;
+    const double t0 = now_ms();
+    for (int i = 0; i < count; i++) {
+        const double t_piece = now_ms();
+        // ---- compose the body: the tail of the previous body that reaches into this shard, then the own lines
+        size_t halo = 0;
+        if (i > 0 && st.first_strad != ~0ull) {
+            if (st.first_strad > prev_n) return SSB_E_STATE;
+            halo = prev_n - (size_t)st.first_strad;
+            if (halo > halo_cap) { snprintf(ctx->err, sizeof ctx->err, "spike: %zu bytes of alignment lines reach from one piece of the stream into the next (limit %zu)", halo, halo_cap); return SSB_E_SHARD; }
+        }
+        uint8_t *body = work[i & 1];                                          // 16-byte aligned start (cudaMalloc); the halo goes to the very front
+        if (halo) SSB_LAUNCH(ctx, copy_bytes_kernel, ctx->sm_count * 2, 256, 0, sc, (const uint8_t *)(prev_body + st.first_strad), body, halo);
+        SSB_CUDA(ctx, cudaStreamWaitEvent(sc, ev_in[i], 0));
+        if (len[i]) SSB_LAUNCH(ctx, copy_bytes_kernel, ctx->sm_count * 8, 256, 0, sc, (const uint8_t *)staging[i % 3], body + halo, len[i]);
+        SSB_CUDA(ctx, cudaEventRecord(ev_free[i], sc));
+        if ((rc = copy_in(i + 3))) return rc;
+        const size_t nb = halo + len[i];
+        // ---- the output buffer must have gone back before it is written again
+        if (i >= 2) SSB_CUDA(ctx, cudaStreamWaitEvent(sc, ev_out[i - 2], 0));
+        ShardPlan pl;
+        pl.index = i; pl.count = count; pl.seq = &st; pl.last = i == count - 1; pl.halo_bytes = halo;
+        pl.rg.lo = i == 0 ? 0ull : (((unsigned long long)(uint32_t)plan[i].lo_tid << 32) | (unsigned long long)plan[i].lo_pos);
+        pl.rg.hi = i == count - 1 ? ~0ull : (((unsigned long long)(uint32_t)plan[i].hi_tid << 32) | (unsigned long long)plan[i].hi_pos);
+        ssb_spike_stats s1; size_t ob = 0;
+        const double t_run = now_ms();
+        if ((rc = run_shard(sp, pl, body, nb, obuf[i & 1], slot + halo_cap + 256, targets, T, seed, res_tmp.data(), &s1, &ob))) return rc;
+        const double t_ran = now_ms();
+        SSB_CUDA(ctx, cudaEventRecord(ev_done[i], sc));
+        // ---- output lines back to the host while the next shard is at work
+        if (out_off + ob > out_cap) { snprintf(ctx->err, sizeof ctx->err, "spike: output needs more than %zu bytes", out_cap); return SSB_E_ARG; }
+        SSB_CUDA(ctx, cudaStreamWaitEvent(sOut, ev_done[i], 0));
+        if (ob) SSB_CUDA(ctx, cudaMemcpyAsync(out + out_off, obuf[i & 1], ob, cudaMemcpyDeviceToHost, sOut));
+        SSB_CUDA(ctx, cudaEventRecord(ev_out[i], sOut));
+        out_off += ob;
+        // ---- results of this shard
+        for (size_t t = 0; t < T; t++) if (res_tmp[t].status != SSB_T_ELSEWHERE) results[t] = res_tmp[t];
+        if (sp->n_se) { sp->se_chunks.push_back(std::make_pair(sp->d_se, sp->n_se)); n_se_total += sp->n_se; sp->d_se = NULL; sp->n_se = 0; }      // stays on the device until asked for
+        stats->alignmentCount += s1.alignmentCount; stats->numberOfLociCovered += s1.numberOfLociCovered; stats->totalFoldCoverage += s1.totalFoldCoverage;
+        if (s1.maxDepth > stats->maxDepth) stats->maxDepth = s1.maxDepth;
+        stats->n_lines += s1.n_lines - 0; stats->n_kept += s1.n_kept; stats->n_runs += s1.n_runs; stats->n_hits += s1.n_hits;
+        stats->ms_parse += s1.ms_parse; stats->ms_sort += s1.ms_sort; stats->ms_emit += s1.ms_emit; stats->ms_cover += s1.ms_cover; stats->ms_gather += s1.ms_gather;
+        stats->ms_rng += s1.ms_rng; stats->ms_chain += s1.ms_chain; stats->ms_patch += s1.ms_patch; stats->ms_phase1 += s1.ms_phase1; stats->ms_tally += s1.ms_tally;
+        if (s1.chain_mode > stats->chain_mode) stats->chain_mode = s1.chain_mode;
+        stats->rng_k_out = s1.rng_k_out; stats->rng_draws = s1.rng_draws;
+        prev_body = body; prev_n = nb;
+        if (dbg) fprintf(stderr, "[stream] piece %d: queued %.3f ms, run %.3f ms, after %.3f ms (halo %zu bytes, out %zu)\n", i, t_run - t_piece, t_ran - t_run, now_ms() - t_ran, halo, ob);
+    }
+    const double t_loop = now_ms();
+    SSB_CUDA(ctx, cudaStreamSynchronize(sOut));
+    SSB_CUDA(ctx, cudaStreamSynchronize(sc));
+    if (dbg) fprintf(stderr, "[stream] loop %.3f ms, drain %.3f ms, setup before the loop %.3f ms\n", t_loop - t0, now_ms() - t_loop, t0 - t_setup);
+    sp->n_se = n_se_total;
+    stats->in_bytes = (int64_t)n; stats->out_bytes = (int64_t)out_off;
+    stats->n_forwarded = count;                     // pieces the body was streamed in
+    stats->ms_total = (float)(now_ms() - t0);
+    *out_bytes = out_off;
+    return SSB_OK;
+}
+} // namespace
+
 extern "C" int ssb_spike_run_host(ssb_spike *sp, const uint8_t *sam, size_t n, uint8_t *out, size_t out_cap,
                                   const ssb_target *targets, size_t n_targets, unsigned seed,
                                   ssb_target_result *results, ssb_spike_stats *stats, size_t *out_bytes)
 {
+    if (!sp || (!sam && n) || (!out && n) || (n_targets && (!targets || !results)) || !stats || !out_bytes) return SSB_E_ARG;
+    // large bodies are streamed through the device in coordinate pieces (bounded device memory, both directions of the host link busy)
+    size_t piece = (size_t)1 << 30;
+    if (const char *e = getenv("SSB_STREAM_BYTES")) { const size_t v = strtoull(e, NULL, 10); if (v >= 4096) piece = v; }
+    if (n > piece + piece / 2 && !getenv("SSB_NO_STREAM"))
+        return run_stream_host(sp, sam, n, out, out_cap, targets, n_targets, seed, results, stats, out_bytes, piece);
     return ssb_spike_run_shard_host(sp, NULL, NULL, sam, n, out, out_cap, targets, n_targets, seed, results, stats, out_bytes);
 }
 
@@ -1353,6 +1564,18 @@ extern "C" int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t ca
     if (!sp || (!dst && cap)) return SSB_E_ARG;
     ssb_ctx *ctx = sp->ctx;
     size_t n = sp->n_se < cap ? sp->n_se : cap;
+    if (sp->se_chunked) {
+        SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+        size_t k = 0;
+        for (auto &c : sp->se_chunks) {
+            if (k >= n) break;
+            const size_t m = c.second < n - k ? c.second : n - k;
+            SSB_CUDA(ctx, cudaMemcpyAsync(dst + k, c.first, m * sizeof(ssb_seq_error), cudaMemcpyDeviceToHost, ctx->stream));
+            k += m;
+        }
+        SSB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SSB_OK;
+    }
     if (n) {
         SSB_CUDA(ctx, cudaSetDevice(ctx->device));
         SSB_CUDA(ctx, cudaMemcpyAsync(dst, sp->d_se, n * sizeof(ssb_seq_error), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1364,5 +1587,7 @@ extern "C" int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t ca
 // test hook (host only): the optional-field check of the tokeniser on one TAG:TYPE:VALUE text
 extern "C" int ssb_test_aux_ok(const char *field, size_t n)
 {
-    return samparse::aux_ok_t([=](size_t i) -> uint8_t { return (uint8_t)field[i]; }, (size_t)0, n);
+    auto at = [=](size_t i) -> uint8_t { return (uint8_t)field[i]; };
+    const int rc = samparse::aux_ok_t(at, (size_t)0, n);
+    return rc == samparse::AUX_FLOAT ? samparse::aux_float_ok_t(at, (size_t)0, n) : rc;
 }

@@ -33,7 +33,8 @@ enum : uint8_t {
     REC_NO_NL    = 4,      // last line of the body without a trailing '\n'
     REC_PUSHED   = 8,      // passes read_bam and tid >= 0 (takes part in the sortedness check)
     REC_SIMPLE   = 16,     // CIGAR holds only M/=/X: query offset q aligns to reference position pos + q
-    REC_EXC_DONE = 32      // the tokeniser already listed this read's exceptional bases (see sam_parse.cuh)
+    REC_EXC_DONE = 32,     // the tokeniser already listed this read's exceptional bases (see sam_parse.cuh)
+    REC_AUX_F    = 64      // the line carries float-typed optional fields, judged by aux_float_kernel
 };
 
 // device error word: first error wins

@@ -326,3 +326,73 @@ def test_error_rich_reads_overflow_the_tile_exception_buffer(tmp_path, ctx):
     assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
     assert got[1] == want[1]
     assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
+
+
+def _with_float_tags(sam: bytes, bad_line=None) -> bytes:
+    """Every alignment line gets de:f / B:f fields in the form "%g" prints (what htslib would print back unchanged)."""
+    import random
+    rng = random.Random(3)
+    out = []
+    k = 0
+    for line in sam.split(b"\n"):
+        if line and not line.startswith(b"@"):
+            vals = [rng.choice([0.0, 0.0123, 1.5, -2e-07, 123456.0, 1e+06, 3.33333e-05, 0.5])] + [rng.uniform(-5, 5) for _ in range(2)]
+            txt = [("%g" % float(np.float32(v))).encode() for v in vals]
+            line += b"\tde:f:" + txt[0] + b"\tXF:B:f," + txt[1] + b"," + txt[2]
+            if bad_line is not None and k == bad_line:
+                line += b"\tzz:f:1.50"                      # htslib would print 1.5: not a pass-through
+            k += 1
+        out.append(line)
+    return b"\n".join(out)
+
+
+def test_float_typed_optional_fields(tmp_path, ctx):
+    """TAG:f and TAG:B:f fields (minimap2's de:f ...) in canonical "%g" form pass through, SAM and BAM; a float that htslib would print
+    differently is refused (BAM float tags used to abort the run)."""
+    import bam_writer
+    prefix = sc.generate("plain", str(tmp_path), contigs="chr19:6000", spikes=20)
+    sam = open(prefix + ".sam", "rb").read()
+    tagged = _with_float_tags(sam)
+    open(prefix + ".sam", "wb").write(tagged)
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    assert want[0] == 0 and got[0] == 0, got[4]
+    assert got[2] == want[2] and got[1] == want[1] and vcf_cmp(want[3], got[3])
+    assert b"\tde:f:" in got[2]
+    bam = tmp_path / "in.bam"
+    bam.write_bytes(bam_writer.sam_to_bam(tagged))
+    (tmp_path / "in.bam.bai").write_bytes(b"BAI\1")
+    got_b = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpub"), sam=str(bam))
+    assert got_b[0] == 0, got_b[4]
+    assert got_b[2] == want[2]
+    open(prefix + ".sam", "wb").write(_with_float_tags(sam, bad_line=17))
+    bad = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "bad"))
+    assert bad[0] == 3 and b"precondition" in bad[4]
+
+
+def test_reference_length_zero_reads(tmp_path, ctx):
+    """Reads whose CIGAR consumes no reference (all soft clip / insertion): htslib's pileup takes pos + bam_cigar2rlen as their end (not
+    bam_endpos), so they never enter a pileup, never count in depth and are never written -- but they take part in the sortedness check."""
+    prefix = sc.generate("plain", str(tmp_path), contigs="chr19:5000", spikes=20, coverage=15)
+    sam = open(prefix + ".sam", "rb").read()
+    lines = sam.split(b"\n")
+    out = []
+    k = 0
+    for line in lines:
+        out.append(line)
+        if line and not line.startswith(b"@"):
+            k += 1
+            if k % 40 == 0:
+                f = line.split(b"\t")
+                n = len(f[9])
+                f[0] = b"zero%d" % k
+                f[5] = (b"%dS" % n) if k % 80 else (b"%dI" % n)
+                f[1] = b"0"
+                f[6], f[7], f[8] = b"*", b"0", b"0"
+                out.append(b"\t".join(f[:11]))
+    open(prefix + ".sam", "wb").write(b"\n".join(out))
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    assert want[0] == 0 and got[0] == 0, got[4]
+    assert b"zero40\t" not in want[2]
+    assert got[2] == want[2] and got[1] == want[1] and vcf_cmp(want[3], got[3])

@@ -216,3 +216,40 @@ def test_two_devices_when_present(tmp_path):
     finally:
         del os.environ["SSB_GPUS"], os.environ["SSB_HALO"]
     assert got[0] == 0 and got[2] == want[2] and got[3] == want[3] and got[1] == want[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,piece", [("plain", 150_000), ("overlap_heavy", 90_000), ("two_contigs_window", 40_000), ("deep_lowvaf", 300_000), ("mask_n_ref", 64_000),
+                                        ("overlap_heavy", 30_000)])
+def test_streamed_host_run_equals_whole_run(name, piece, tmp_path, ctx, monkeypatch):
+    """ssb_spike_run_host streams a large body through the device in coordinate pieces, each from the exact state its predecessor
+    left (no offset windows); here with tiny pieces, so that dozens of hand-overs, halos and forwarded bases happen."""
+    prefix = sc.generate(name, str(tmp_path))
+    hdr, body, names, seqs, targets = _load(prefix)
+    with sp.Spike(ctx, names, seqs) as s:
+        monkeypatch.setenv("SSB_NO_STREAM", "1")
+        out1, res1, st1 = s.run_host(body, targets, 434)
+        se1 = s.seq_errors()
+        monkeypatch.delenv("SSB_NO_STREAM")
+        monkeypatch.setenv("SSB_STREAM_BYTES", str(piece))
+        out2, res2, st2 = s.run_host(body, targets, 434)
+        se2 = s.seq_errors()
+    assert st2.n_forwarded >= 3, "expected the body to be streamed in several pieces"
+    assert out2 == out1
+    assert [_res_key(r) for r in res2] == [_res_key(r) for r in res1]
+    assert [_se_key(e) for e in se2] == [_se_key(e) for e in se1]
+    for f in ("alignmentCount", "numberOfLociCovered", "totalFoldCoverage", "maxDepth", "rng_draws"):
+        assert getattr(st2, f) == getattr(st1, f), f
+
+
+@pytest.mark.gpu
+def test_streamed_cli_matches_reference_binary(tmp_path, ctx):
+    prefix = sc.generate("overlap_heavy", str(tmp_path))
+    want = sc.run_cli(CHECKER, prefix, str(tmp_path / "ref"), cmdname="stochasticSpike")
+    os.environ["SSB_STREAM_BYTES"] = "50000"
+    try:
+        got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    finally:
+        del os.environ["SSB_STREAM_BYTES"]
+    assert got[0] == 0, got[4]
+    assert got[2] == want[2] and got[1] == want[1] and got[3] == want[3]
