@@ -183,6 +183,8 @@ typedef struct ssb_spike_stats {
     int64_t n_forwarded;              /* spiked bases handed to the next shard (reads that end in its range)           */
     float   ms_handoff_wait;          /* host time blocked on the predecessor's 8-byte offset                          */
     float   ms_phase1, ms_tally, ms_exchange;
+    int32_t n_window_retries;         /* groups of the RNG chain that were walked again because the exact offset left their window */
+    int32_t reserved2;
 } ssb_spike_stats;
 
 int  ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_contigs, ssb_spike **out);

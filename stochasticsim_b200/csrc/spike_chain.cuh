@@ -426,7 +426,8 @@ __global__ void __launch_bounds__(P1_THREADS)
 phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, const SliceDesc *__restrict__ slices,
               unsigned long long *__restrict__ kbuf, uint32_t *__restrict__ lobuf, unsigned long long stride,
               BoundaryList *__restrict__ lists /* [block][max_nf] */, int max_nf, unsigned long long *__restrict__ pool_k, uint32_t *__restrict__ pool_lo,
-              unsigned long long *__restrict__ pool_used, unsigned long long pool_cap, unsigned int *__restrict__ flags, unsigned long long *__restrict__ dbg)
+              unsigned long long *__restrict__ pool_used, unsigned long long pool_cap, unsigned int *__restrict__ flags, unsigned long long *__restrict__ dbg,
+              int block0 /* index of this launch's first slice (a retry launches single slices) */)
 {
     extern __shared__ uint4 p1_smem[];
     uint4 *se = p1_smem, *sc = p1_smem + P1_EW_CAP;
@@ -434,7 +435,8 @@ phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, cons
     __shared__ int s_bad;
     __shared__ unsigned long long s_off, s_kmin, s_kmax;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const SliceDesc sd = slices[blockIdx.x];
+    const unsigned int bx = blockIdx.x + (unsigned int)block0;
+    const SliceDesc sd = slices[bx];
     const GroupDesc gd = groups[sd.q];
     const int64_t g0 = (int64_t)gd.f0 * L, gend = ((int64_t)(gd.f0 + gd.nf) * L < A.n_walk) ? (int64_t)(gd.f0 + gd.nf) * L : A.n_walk;
     unsigned long long *kb[2] = {kbuf + sd.off, kbuf + stride + sd.off};
@@ -517,7 +519,7 @@ phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, cons
             const unsigned long long off = s_off;
             if (off + alive > pool_cap) { if (tid == 0) atomicOr(flags, (unsigned int)CHAIN_COMPLEX); return; }
             for (uint32_t i = tid; i < alive; i += P1_THREADS) { pool_k[off + i] = kb[cur][i]; pool_lo[off + i] = lb[cur][i]; }
-            if (tid == 0) { BoundaryList bl; bl.off = off; bl.cnt = alive; bl.pad = 0; lists[(size_t)blockIdx.x * max_nf + r] = bl; }
+            if (tid == 0) { BoundaryList bl; bl.off = off; bl.cnt = alive; bl.pad = 0; lists[(size_t)bx * max_nf + r] = bl; }
             r++;
         }
         __syncthreads();
@@ -526,7 +528,7 @@ phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, cons
         atomicAdd(&dbg[1], (unsigned long long)alive); atomicMax(&dbg[2], (unsigned long long)alive);
         const unsigned long long tot = (unsigned long long)(clock64() - t_start);
         atomicMax(&dbg[6], tot);
-        dbg[8 + 2 * (size_t)blockIdx.x] = tot; dbg[9 + 2 * (size_t)blockIdx.x] = t_early;       // per block: total, early rounds
+        dbg[8 + 2 * (size_t)bx] = tot; dbg[9 + 2 * (size_t)bx] = t_early;       // per block: total, early rounds
     }
 }
 
@@ -550,14 +552,15 @@ __device__ __forceinline__ bool boundary_lookup(const GroupDesc &gd, int r, unsi
 __global__ void __launch_bounds__(32)
 compose_kernel(int G, const GroupDesc *__restrict__ groups, const BoundaryList *__restrict__ lists, int max_nf,
                const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo,
-               const unsigned long long *__restrict__ k_in, unsigned long long *__restrict__ gk, unsigned long long *__restrict__ k_end, unsigned int *__restrict__ flags)
+               const unsigned long long *__restrict__ k_in, unsigned long long *__restrict__ gk, unsigned long long *__restrict__ k_end, unsigned int *__restrict__ flags,
+               unsigned long long *__restrict__ miss /* [0] group whose window the walker missed, [1] its exact entry offset */)
 {
     const int lane = threadIdx.x;
     unsigned long long k = *k_in;
     for (int q = 0; q < G; q++) {
         const GroupDesc gd = groups[q];
         if (lane == 0) gk[q] = k;
-        if (k < gd.klo || k - gd.klo >= gd.W) { if (lane == 0) atomicOr(flags, (unsigned int)CHAIN_MISS); return; }
+        if (k < gd.klo || k - gd.klo >= gd.W) { if (lane == 0) { miss[0] = (unsigned long long)q; miss[1] = k; atomicOr(flags, (unsigned int)CHAIN_MISS); } return; }
         const uint32_t idx = (uint32_t)(k - gd.klo);
         uint32_t sl = idx / gd.w; if (sl >= gd.S) sl = gd.S - 1;
         const BoundaryList bl = lists[(size_t)(gd.b0 + sl) * max_nf + (gd.nf - 1)];

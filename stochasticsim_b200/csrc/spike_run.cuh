@@ -33,7 +33,7 @@ struct RunScalars {                 // written by kernels of the main stream, mi
     unsigned int H, pad1; unsigned long long E; long long last_hit_locus;
     unsigned int flags, n_odd, n_patches, n_fwd;
     unsigned long long odd_bloom, draws, pool_used, k_out, k_end;
-    unsigned long long n_se, first_strad, halo_lines;
+    unsigned long long n_se, first_strad, halo_lines, miss[2];
     long long carry_t, carry_h;
 };
 struct RunScalarsA {                // written by kernels of the second stream
@@ -930,7 +930,9 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     if (have_walk) {
         int rc;
         bool parallel = P > 1;
-        // window geometry of the groups (host): centre = expected offset, half width = 5 sigma
+        // window geometry of the groups (host): centre = expected offset, half width = `sigmas` standard deviations
+        double sigmas = 4.0;
+        if (const char *e = getenv("SSB_CHAIN_SIGMA")) { const double v = atof(e); if (v >= 0.5 && v <= 12.0) sigmas = v; }
         std::vector<GroupDesc> h_groups; std::vector<SliceDesc> h_slices;
         unsigned long long woff = 0; double cm_end = 0, cv_end = 0;
         auto make_geometry = [&](double centre, double var0, bool exact_entry) {
@@ -940,7 +942,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 GroupDesc &gd = h_groups[q];
                 gd.f0 = q * Rg; gd.nf = (gd.f0 + Rg <= P) ? Rg : P - gd.f0;
                 const bool one = q == 0 && exact_entry;
-                const double half = one ? 0.0 : 5.0 * sqrt(cv) + 48.0;       // +-5 sigma: a miss (3e-7 per group) falls back to the serial chain
+                const double half = one ? 0.0 : sigmas * sqrt(cv) + 32.0;    // a walker outside its group's window (6e-5 per group at 4 sigma) is walked again on its own
                 double lo = cm - half; if (lo < 0) lo = 0;
                 gd.klo = (unsigned long long)lo; gd.W = one ? 1u : (uint32_t)(cm + half - (double)gd.klo) + 2u;
                 uint32_t S = (gd.W + wt - 1) / wt; gd.w = (gd.W + S - 1) / S; S = (gd.W + gd.w - 1) / gd.w;
@@ -954,6 +956,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             cm_end = cm; cv_end = cv;
         };
 
+        int n_retries = 0;
         bool chain_done = false;
         for (int attempt = 0; attempt < 8 && !chain_done; attempt++) {
             if (!parallel) {
@@ -981,10 +984,12 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             const unsigned long long need_to = (unsigned long long)(cm_end + 8.0 * sqrt(cv_end)) + 3 * E + (1u << 17) + stream_extra;
             if ((rc = make_stream(h_groups[0].klo, need_to))) return rc;
             if ((rc = reset_state())) return rc;
-            BoundaryList *d_lists = ar.get<BoundaryList>(n_slices * (size_t)Rg);
-            unsigned long long *kbuf = ar.get<unsigned long long>(2 * woff), *pool_k = ar.get<unsigned long long>(pool_cap), *exit_k = NULL;
-            uint32_t *lobuf = ar.get<uint32_t>(2 * woff), *pool_lo = ar.get<uint32_t>(pool_cap);
-            GroupDesc *d_groups = ar.get<GroupDesc>((size_t)G); SliceDesc *d_slices = ar.get<SliceDesc>(n_slices);
+            constexpr int SPARE = 32;                           // single-walker slices for groups whose window the exact walker missed
+            const unsigned long long wstride = woff + SPARE;
+            BoundaryList *d_lists = ar.get<BoundaryList>((n_slices + SPARE) * (size_t)Rg);
+            unsigned long long *kbuf = ar.get<unsigned long long>(2 * wstride), *pool_k = ar.get<unsigned long long>(pool_cap), *exit_k = NULL;
+            uint32_t *lobuf = ar.get<uint32_t>(2 * wstride), *pool_lo = ar.get<uint32_t>(pool_cap);
+            GroupDesc *d_groups = ar.get<GroupDesc>((size_t)G); SliceDesc *d_slices = ar.get<SliceDesc>(n_slices + SPARE);
             unsigned long long *d_kin = ar.get<unsigned long long>(1);
             if (!exact_entry) exit_k = ar.get<unsigned long long>(pool_cap);
             SPK_CHECK_ARENA(ar);
@@ -1001,10 +1006,10 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             unsigned long long *d_dbg = NULL;
             if (dbg_t) { d_dbg = ar.get<unsigned long long>(8 + 2 * n_slices); SPK_CHECK_ARENA(ar); SSB_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (8 + 2 * n_slices) * 8, s)); }
             SSB_CUDA(ctx, cudaMemsetAsync(d_pool_used, 0, 8, s));
-            SSB_CUDA(ctx, cudaMemsetAsync(d_lists, 0, n_slices * (size_t)Rg * sizeof(BoundaryList), s));
+            SSB_CUDA(ctx, cudaMemsetAsync(d_lists, 0, (n_slices + SPARE) * (size_t)Rg * sizeof(BoundaryList), s));
             SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[14], s));
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, (int)n_slices, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, woff,
-                         d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, d_dbg);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, (int)n_slices, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
+                         d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, d_dbg, 0);
             SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[15], s));
             if (d_dbg) {
                 unsigned long long h_dbg[8];
@@ -1031,29 +1036,58 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 SSB_LAUNCH(ctx, entry_kernel, 1, 32, 0, s, d_groups, d_lists, Rg, pool_lo, exit_k, d_kin, &dsc->k_out);
                 if ((rc = publish())) return rc;
                 if (hsc->flags & CHAIN_OVERRUN) { stream_extra = stream_extra ? stream_extra * 2 : (unsigned long long)(M_abs - k_base); continue; }   // again, now from the exact offset
-                if (hsc->flags || hsc->k_out == ~0ull) { parallel = false; continue; }            // the window missed / phase 1 gave up: walk serially from the exact offset
-                if ((rc = send_offset(hsc->k_out))) return rc;
+                if (hsc->flags) { parallel = false; continue; }                                   // phase 1 gave up: walk serially from the exact offset
+                if (hsc->k_out != ~0ull) { if ((rc = send_offset(hsc->k_out))) return rc; }       // else: a window was missed on the way; the composition below finds out where
             } else {
                 uint8_t *kh = NULL, *kd = NULL;
                 if ((rc = map_get(8, &kh, &kd))) return rc;
                 *(volatile unsigned long long *)kh = k_in;
                 SSB_LAUNCH(ctx, copy_u64_kernel, 1, 32, 0, s, (const unsigned long long *)kd, d_kin);
             }
-            // ---- compose from the exact offset, chunk boundaries, phase 3
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, G, d_groups, d_lists, Rg, pool_k, pool_lo, d_kin, d_gk, &dsc->k_end, d_flags);
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, boundary_kernel, (P + 127) / 128, 128, 0, s, P, Rg, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_chunks, d_flags);
-            if (xc && pl.index + 1 < pl.count && !sent) {
-                // the entry offset was known from the start: the exit offset leaves as soon as the maps are composed
-                if ((rc = publish())) return rc;
-                if (!hsc->flags) { if ((rc = send_offset(hsc->k_end))) return rc; }
+            // ---- compose from the exact offset, chunk boundaries, phase 3.  A walker that leaves its group's window is walked through
+            //      that group again on its own (one block, exact entry), and the composition is repeated.
+            bool ok = false, restart = false;
+            for (int retry = 0; retry <= SPARE; retry++) {
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, G, d_groups, d_lists, Rg, pool_k, pool_lo, d_kin, d_gk, &dsc->k_end, d_flags, dsc->miss);
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, boundary_kernel, (P + 127) / 128, 128, 0, s, P, Rg, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_chunks, d_flags);
+                if ((rc = publish())) return rc;                                                  // did the exact walker stay inside every window?
+                if (!hsc->flags) {
+                    if ((rc = send_offset(hsc->k_end))) return rc;                                // the exit offset leaves as soon as the maps are composed
+                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, grid_for((size_t)P * 32, 128), 128, 0, s, A, d_chunks, P, d_draws, d_flags);
+                    if ((rc = publish())) return rc;                                              // sync 5
+                }
+                if (dbg_t) fprintf(stderr, "[chain %d] flags after phases 1-3: %u, odd patches %u\n", pl.index, (unsigned)hsc->flags, (unsigned)hsc->n_odd);
+                if (hsc->flags == (unsigned int)CHAIN_MISS && retry < SPARE) {
+                    const int q = (int)hsc->miss[0]; const unsigned long long km = hsc->miss[1];
+                    if (dbg_t) fprintf(stderr, "[chain %d] window of group %d missed (offset %llu, window [%llu, +%u)): walking it alone\n", pl.index, q, km, h_groups[q].klo, h_groups[q].W);
+                    if (km < k_base || km + 64 > M_abs) { restart = true; break; }                // outside the generated stream: start over with a longer one
+                    GroupDesc gd = h_groups[q];
+                    gd.klo = km; gd.W = 1; gd.w = 1; gd.S = 1; gd.b0 = (uint32_t)(n_slices + retry);
+                    h_groups[q] = gd;
+                    SliceDesc sd; sd.q = q; sd.i0 = 0; sd.n = 1; sd.off = woff + retry;
+                    uint8_t *gh = NULL, *gd_ = NULL, *sh_ = NULL, *sd_ = NULL;
+                    if ((rc = map_get(sizeof gd, &gh, &gd_))) return rc;
+                    if ((rc = map_get(sizeof sd, &sh_, &sd_))) return rc;
+                    memcpy(gh, &gd, sizeof gd); memcpy(sh_, &sd, sizeof sd);
+                    SSB_LAUNCH(ctx, copy_words_kernel, 1, 32, 0, s, (const uint32_t *)gd_, (uint32_t *)(d_groups + q), (unsigned int)(sizeof gd / 4));
+                    SSB_LAUNCH(ctx, copy_words_kernel, 1, 32, 0, s, (const uint32_t *)sd_, (uint32_t *)(d_slices + n_slices + retry), (unsigned int)(sizeof sd / 4));
+                    if ((rc = reset_state())) return rc;
+                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, 1, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
+                                 d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, (unsigned long long *)NULL, (int)(n_slices + retry));
+                    stats->n_runs += 0;
+                    n_retries++;
+                    continue;
+                }
+                ok = true;
+                break;
             }
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, grid_for((size_t)P * 32, 128), 128, 0, s, A, d_chunks, P, d_draws, d_flags);
-            if ((rc = publish())) return rc;                                                      // sync 5
-            if (dbg_t) fprintf(stderr, "[chain %d] flags after phases 1-3: %u, odd patches %u\n", pl.index, (unsigned)hsc->flags, (unsigned)hsc->n_odd);
+            if (restart) { stream_extra = stream_extra ? stream_extra * 2 : (unsigned long long)(M_abs - k_base); continue; }
+            (void)ok;
             if (hsc->flags & CHAIN_OVERRUN) { stream_extra = stream_extra ? stream_extra * 2 : (unsigned long long)(M_abs - k_base); continue; }
-            if (hsc->flags || hsc->n_odd) { parallel = false; continue; }                          // window miss / too complex / odd patches: the plain serial chain decides
+            if (hsc->flags || hsc->n_odd) { parallel = false; continue; }                          // too complex / odd patches (or misses without end): the plain serial chain decides
             k_out_final = is_last ? hsc->draws : hsc->k_end;
             stats->chain_mode = P;
+            stats->n_window_retries = n_retries;
             chain_done = true;
         }
         if (!chain_done) { snprintf(ctx->err, sizeof ctx->err, "spike/chain: rand() stream exhausted"); return SSB_E_STATE; }

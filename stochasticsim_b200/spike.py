@@ -32,7 +32,8 @@ class Stats(C.Structure):
                [(n, C.c_float) for n in ("ms_parse", "ms_sort", "ms_emit", "ms_cover", "ms_gather", "ms_rng", "ms_chain",
                                           "ms_patch", "ms_total")] + [("_pad0", C.c_float)] + \
                [(n, C.c_int64) for n in ("rng_k_in", "rng_k_out", "locus_base", "n_forwarded")] + \
-               [(n, C.c_float) for n in ("ms_handoff_wait", "ms_phase1", "ms_tally", "ms_exchange")]
+               [(n, C.c_float) for n in ("ms_handoff_wait", "ms_phase1", "ms_tally", "ms_exchange")] + \
+               [("n_window_retries", C.c_int32), ("_pad1", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("_")}

@@ -396,3 +396,23 @@ def test_reference_length_zero_reads(tmp_path, ctx):
     assert want[0] == 0 and got[0] == 0, got[4]
     assert b"zero40\t" not in want[2]
     assert got[2] == want[2] and got[1] == want[1] and vcf_cmp(want[3], got[3])
+
+
+@pytest.mark.parametrize("name,chunk,group,sigma", [("plain", 512, 2, 1.0), ("mask_n_ref", 256, 1, 0.7), ("deep_lowvaf", 96, 2, 1.5), ("plain", 256, 1, 0.5)])
+def test_window_miss_is_walked_again(name, chunk, group, sigma, tmp_path, ctx, monkeypatch):
+    """Windows far narrower than production (4 sigma): the exact walker leaves some group's window, that group is walked again from the
+    exact offset (one block) and the maps are composed again -- same bytes as the serial chain; too many misses end in the serial chain."""
+    prefix = sc.generate(name, str(tmp_path))
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    sam = open(prefix + ".sam", "rb").read()
+    hdr, body, names = sp.split_header(sam)
+    seqs = sp.parse_fasta(open(prefix + ".fa", "rb").read())
+    targets = sp.parse_spike(open(prefix + ".spike", "rb").read(), names)
+    monkeypatch.setenv("SSB_CHAIN_CHUNK", str(chunk))
+    monkeypatch.setenv("SSB_CHAIN_GROUP", str(group))
+    monkeypatch.setenv("SSB_CHAIN_SIGMA", str(sigma))
+    with sp.Spike(ctx, names, seqs) as s:
+        out, res, st = s.run_host(body, targets, 434)
+    assert hdr + out == want[2]
+    if sigma <= 0.5:
+        assert st.n_window_retries > 0 or st.chain_mode == 1, "expected misses with windows this narrow"
