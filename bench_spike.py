@@ -65,13 +65,15 @@ def spike_table(L, seed, coverage, contig_len, n_spikes, name=b"chr19", cidx=0):
     return sb.raw[:sn]
 
 
-def make_workload(L, seed, contig_len, coverage, n_spikes, name=b"chr19", threads=None, log=None, cidx=0):
-    """Returns (ref bytes ndarray, body chunks list[bytes-like ndarray], n_reads, spike text bytes) of contig `cidx`."""
+def make_workload(L, seed, contig_len, coverage, n_spikes, name=b"chr19", threads=None, log=None, cidx=0, lo=0, hi=None):
+    """Returns (ref bytes ndarray, body chunks list[bytes-like ndarray], n_reads, spike text bytes) of contig `cidx`; only the reads that
+    start in [lo, hi) when a range is given (the generator is counter based: any range can be made on its own)."""
     p = c2_params(L, seed, coverage)
     ref = np.empty(contig_len + 1, dtype=np.uint8)
     L.synth_ref_contig(C.byref(p), cidx, contig_len, 0, contig_len, 0, ref.ctypes.data)
     step = 200_000
-    ranges = [(lo, min(contig_len, lo + step)) for lo in range(0, contig_len, step)]
+    hi = contig_len if hi is None else hi
+    ranges = [(a, min(hi, a + step)) for a in range(lo, hi, step)]
     per_pos = coverage / 150.0 * 420.0 * 1.25 + 64          # generous bytes per reference position
 
     def gen(rg):
@@ -96,6 +98,53 @@ def make_workload(L, seed, contig_len, coverage, n_spikes, name=b"chr19", thread
 
 def header_for(name, contig_len):
     return ("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n@PG\tID:gen_synth\tPN:gen_synth\n" % (name, contig_len)).encode()
+
+
+# ---- where to cut ONE input of N contigs into N coordinate shards so that every GPU finishes at the same time.  A shard's cost is its
+# reads (everything but the chain) plus phase 1 of the RNG chain, whose windows widen with the square root of the loci in front of the
+# shard (the rand() offset there is only known to +-4 sigma while the shards work side by side).  Constants: measured on C2 (one contig):
+# 36 ms for everything but phase 1, phase 1 = 6.2 ms + 8.1 ms * (x1^1.5 - x0^1.5) for the contig range [x0, x1).
+COST_BASE, COST_P1_FIXED, COST_P1_GROW = 36.0, 6.2, 8.1
+
+
+def shard_cost(x0, x1):
+    return COST_BASE * (x1 - x0) + COST_P1_FIXED + COST_P1_GROW * (x1 ** 1.5 - x0 ** 1.5)
+
+
+def balanced_cuts(n_shards, n_contigs, balance=True):
+    """Cut positions x_0 = 0 < x_1 < ... < x_N = n_contigs in contig units."""
+    if not balance or n_shards == 1:
+        return [n_contigs * g / n_shards for g in range(n_shards + 1)]
+    lo_t, hi_t = 0.0, shard_cost(0.0, float(n_contigs))
+    for _ in range(60):                          # bisection on the common cost per shard
+        t = (lo_t + hi_t) / 2
+        x = 0.0
+        for _g in range(n_shards):
+            a, b = x, float(n_contigs) + 1.0
+            for _ in range(60):
+                m = (a + b) / 2
+                if shard_cost(x, m) < t:
+                    a = m
+                else:
+                    b = m
+            x = a
+        if x < n_contigs:
+            lo_t = t
+        else:
+            hi_t = t
+    cuts, x = [0.0], 0.0
+    for _g in range(n_shards - 1):
+        a, b = x, float(n_contigs)
+        for _ in range(60):
+            m = (a + b) / 2
+            if shard_cost(x, m) < hi_t:
+                a = m
+            else:
+                b = m
+        x = a
+        cuts.append(x)
+    cuts.append(float(n_contigs))
+    return cuts
 
 
 def traffic_from_profile(scale):
@@ -125,8 +174,33 @@ def run(args, D):
     n_spikes = 10_000
     N = D.world
     names = ["chr19"] if N == 1 else ["chr19.%d" % g for g in range(N)]
-    # ONE input: contig g of the same generator seed on rank g; the .spike table covers every contig
-    ref, parts, n_reads, _ = make_workload(L, 2, contig_len, coverage, n_spikes, name=names[D.rank].encode(), log=log, cidx=D.rank)
+    # ONE input: N contigs of the same generator seed, cut into N coordinate ranges of equal expected cost (SSB_BENCH_BALANCE=0: one contig each).
+    balance = os.environ.get("SSB_BENCH_BALANCE", "1") != "0"
+    cuts = balanced_cuts(N, N, balance)
+    HALO = 1024                                               # bases: 150 bp reads with a few indels span < 200
+    def to_pos(x):                                            # contig units -> (contig, position)
+        c = int(x)
+        p = int(round((x - c) * contig_len))
+        if p >= contig_len:
+            c, p = c + 1, 0
+        return c, p
+
+    x0, x1 = cuts[D.rank], cuts[D.rank + 1]
+    (c_lo, p_lo), (c_hi, p_hi) = to_pos(x0), to_pos(x1)     # the shard owns (c_lo, p_lo) <= (contig, pos) < (c_hi, p_hi)
+    refs, parts, n_reads, halo_bytes = {}, [], 0, 0
+    if p_lo > 0:                                              # the lines of the previous shard that can reach into this one
+        _, hp_parts, _, _ = make_workload(L, 2, contig_len, coverage, n_spikes, name=names[c_lo].encode(), cidx=c_lo, lo=max(0, p_lo - HALO), hi=p_lo)
+        parts += hp_parts
+        halo_bytes = sum(b.size for b in hp_parts)
+    for c in range(c_lo, min(c_hi, N - 1) + 1):
+        a = p_lo if c == c_lo else 0
+        b = p_hi if c == c_hi else contig_len
+        if b <= a:
+            continue
+        ref_c, prt, nr, _ = make_workload(L, 2, contig_len, coverage, n_spikes, name=names[c].encode(), log=log, cidx=c, lo=a, hi=b)
+        refs[names[c]] = ref_c.tobytes()
+        parts += prt
+        n_reads += nr
     spike_text = b"".join(spike_table(L, 2, coverage, contig_len, n_spikes, names[g].encode(), g) for g in range(N))
     n = sum(b.size for b in parts)
     ctx = ssb.Context(D.local)
@@ -144,17 +218,19 @@ def run(args, D):
     ctx.h2d(d_in, hp, n)
     ctx.sync()
     targets = sp.parse_spike(spike_text, names)
-    S = sp.Spike(ctx, names, {names[D.rank]: ref.tobytes()})        # a shard only ever touches its own contig
+    S = sp.Spike(ctx, names, refs)                            # a shard only ever touches the contigs of its range
     tarr = S.make_targets(targets)
     res = (sp.TargetResult * len(targets))()
     st = sp.Stats()
     shard, xc, comm = None, None, None
     if N > 1:
-        shard = sp.Shard(index=D.rank, count=N, lo_tid=D.rank, hi_tid=(D.rank + 1 if D.rank + 1 < N else 0x7fffffff), lo_pos=0, hi_pos=0, halo_bytes=0)
+        hi_tid, hi_pos = (0x7fffffff, 0) if D.rank == N - 1 else (c_hi, p_hi)
+        shard = sp.Shard(index=D.rank, count=N, lo_tid=c_lo, hi_tid=hi_tid, lo_pos=p_lo, hi_pos=hi_pos, halo_bytes=halo_bytes)
         comm = D.ssb_comm(ctx)
         x = C.c_void_p()
         ssb.check(sp._bind().ssb_exchange_nccl_create(ctx.handle, comm, D.rank, N, C.byref(x)), ctx.handle)
         xc = x
+    log(f"[bench rank {D.rank}] shard [{x0:.4f}, {x1:.4f}) of {N} contigs = ({c_lo}, {p_lo}) .. ({c_hi}, {p_hi}): {n_reads} reads, {n} bytes ({halo_bytes} halo)")
 
     def step():
         return S.run_shard_device(shard, xc, d_in, n, d_out, n + 1, tarr, len(targets), SPIKE_SEED, res, st)
@@ -187,7 +263,9 @@ def run(args, D):
     # one stream over all shards: every rank starts where its predecessor stopped
     chain = D.gather([stats["rng_k_in"], stats["rng_k_out"], stats["n_hits"], stats["chain_mode"],
                       stage_ms.get("ms_chain", 0.0) / args.steps, stage_ms.get("ms_phase1", 0.0) / args.steps,
-                      stage_ms.get("ms_handoff_wait", 0.0) / args.steps, stage_ms.get("ms_exchange", 0.0) / args.steps])
+                      stage_ms.get("ms_handoff_wait", 0.0) / args.steps, stage_ms.get("ms_exchange", 0.0) / args.steps,
+                      (stage_ms.get("ms_parse", 0.0) + stage_ms.get("ms_sort", 0.0) + stage_ms.get("ms_cover", 0.0) + stage_ms.get("ms_gather", 0.0)) / args.steps,
+                      stage_ms.get("ms_patch", 0.0) / args.steps, stage_ms.get("ms_total", 0.0) / args.steps, float(stats["n_window_retries"]), float(n_reads)])
     if D.rank == 0:
         for a, b in zip(chain, chain[1:]):
             assert int(a[1]) == int(b[0]), "rand() offset hand-off broken: %r" % (chain,)
@@ -227,8 +305,13 @@ def run(args, D):
             assert np.array_equal(got, host[:w]), "streamed e2e output differs from the device-resident run at offset %d" % w0
         del dev
 
-    # size-independent properties at full size: every kept read written once, same multiset of bytes up to the spiked bases
-    assert stats["alignmentCount"] == stats["n_kept"] and out_bytes == stats["out_bytes"]
+    # size-independent properties at full size: every read of the ONE input is written exactly once (by the shard that owns its last
+    # base: a shard also parses the few lines of its predecessor that reach into its range, and leaves its own last ones to its successor)
+    written = D.sum(float(stats["alignmentCount"]))
+    assert int(written) == int(total_reads), (written, total_reads)
+    assert out_bytes == stats["out_bytes"]
+    if N == 1:
+        assert stats["alignmentCount"] == stats["n_kept"]
     emit_ms, emit_n = prof["emit"]
     parse_ms, parse_n = prof["parse"]
     chain_ms, chain_n = prof["chain"]
@@ -242,7 +325,8 @@ def run(args, D):
                                 "ONE coordinate-sorted SAM over %d chr19-sized contigs (C2 per contig: 150bp paired reads at %gx, 10k SBS spike loci each; one seed, one "
                                 ".spike table, one rand() stream), cut by coordinate range, shard g on GPU g" % (N, coverage))
                                + ("" if args.scale == 1.0 else f" (depth scaled x{args.scale})"),
-                   "reads_per_gpu": n_reads, "sam_bytes_per_gpu": n, "covered_loci_per_gpu": stats["numberOfLociCovered"], "spike_seed": SPIKE_SEED,
+                   "cuts_in_contigs": [round(c, 4) for c in cuts], "cut_rule": ("equal expected cost per shard (reads + phase 1 of the RNG chain, whose windows widen with the loci in front of the shard)" if balance and N > 1 else "one contig per shard"),
+                   "reads_on_rank0": n_reads, "sam_bytes_on_rank0": n, "covered_loci_on_rank0": stats["numberOfLociCovered"], "spike_seed": SPIKE_SEED,
                    "targets": len(targets), "targets_hit_on_rank0": stats["n_hits"], "l2": "input (%.2f GB) larger than L2, no flush" % (n / 1e9),
                    "collective": "none" if N == 1 else
                    "NCCL over NVLink, inside the timed region: all-gather of 5 scalars per shard, max-reduction of one int64 per .spike record (%d), "
@@ -270,7 +354,8 @@ def run(args, D):
         "rng_chain": {"ms_per_step": stage_ms.get("ms_chain", 0.0) / args.steps, "phase1_ms_per_step": stage_ms.get("ms_phase1", 0.0) / args.steps,
                       "draws_after_last_shard": int(chain[-1][1]) if D.rank == 0 else None,
                       "per_shard": [{"k_in": int(c[0]), "k_out": int(c[1]), "hits": int(c[2]), "chunks": int(c[3]), "chain_ms": c[4], "phase1_ms": c[5],
-                                     "handoff_wait_ms": c[6], "exchange_ms": c[7]} for c in chain] if D.rank == 0 else None,
+                                     "handoff_wait_ms": c[6], "exchange_ms": c[7], "before_chain_ms": c[8], "after_chain_ms": c[9], "host_total_ms": c[10],
+                                     "window_retries_last_step": int(c[11]), "reads": int(c[12])} for c in chain] if D.rank == 0 else None,
                       "note": "one glibc rand() stream consumed at every covered locus (stochasticSpike.c:1197): window maps per shard, exact 8-byte hand-off"},
         "clocks": clk.summary(),
     }

@@ -119,6 +119,19 @@ int ssb_tnc_carry_after(const uint8_t *fasta, size_t n, const ssb_tnc_carry *car
  * ncclComm_t created by the caller; the reduction runs on the context's stream. */
 int ssb_tnc_allreduce(ssb_ctx *ctx, void *nccl_comm, int64_t *d_counts64);
 
+/* BED-restricted scan (BASELINE.json configs[2]: "tncCountsProfile over whole GRCh38 FASTA restricted to a synthetic exome BED").
+ * The reference has no BED input: the result is DEFINED as what tncCountsProfile.c:391-447 counts on the FASTA that holds, per
+ * interval in BED order, one header line and the interval's bases on one line (the shape `bedtools getfasta` writes); that
+ * FASTA is built on the device and scanned by the same exact kernels.  contigs[] is a .fai-style index of the genome text
+ * (ssb_fasta_index makes it); interval.contig indexes it.  Counts the windows of intervals [first, last) -- including the one
+ * straddling window the reference sees between the nearest kept earlier interval and the first of this range -- so that the
+ * counts of a partition of [0, n_intervals) add up to the whole (one range per GPU, then ssb_tnc_allreduce). */
+typedef struct ssb_fasta_contig { uint64_t seq_off; int64_t len; uint32_t line_bases, line_bytes; } ssb_fasta_contig;
+typedef struct ssb_bed_interval { int32_t contig, reserved; int64_t start, end; } ssb_bed_interval;      /* 0-based, half open */
+int ssb_fasta_index(const uint8_t *fasta, size_t n, ssb_fasta_contig *out, const char **names, uint32_t *name_lens, size_t cap, size_t *n_out);
+int ssb_tnc_count_bed_device(ssb_ctx *ctx, const uint8_t *d_fasta, size_t n, const ssb_fasta_contig *contigs, size_t n_contigs,
+                             const ssb_bed_interval *intervals, size_t n_intervals, size_t first, size_t last, int64_t *d_counts64);
+
 /* The reference's 32-line stdout (tncCountsProfile.c:452-483): "CTX\t%ld\n", ctx + reverse
  * complement, fixed order.  Returns bytes written (excluding NUL) or SSB_E_ARG if cap is short. */
 int ssb_tnc_format(const int64_t counts64[64], char *dst, size_t cap);

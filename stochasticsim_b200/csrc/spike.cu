@@ -77,7 +77,7 @@ struct MaxOp { template <typename T> __device__ __forceinline__ T operator()(con
 __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ kord,
                                const unsigned long long *__restrict__ pkey, const unsigned long long *__restrict__ pmax,
                                uint32_t *__restrict__ k_rec, unsigned long long *__restrict__ k_start, unsigned long long *__restrict__ k_end,
-                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ k_hash, uint32_t *__restrict__ k_hash32, uint8_t *__restrict__ k_bits,
+                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ k_off, unsigned long long *__restrict__ k_hash, uint32_t *__restrict__ k_hash32, uint8_t *__restrict__ k_bits,
                                unsigned long long *__restrict__ fold, unsigned int *__restrict__ maxspan, DevErr *err,
                                Range rg, unsigned long long halo_bytes)
 {
@@ -100,6 +100,7 @@ __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const 
             k_start[o] = ks;
             k_end[o] = ke;
             k_len[o] = r.line_len + ((r.bits & REC_NO_NL) ? 1u : 0u);
+            k_off[o] = r.line_off;
             k_hash[o] = r.qhash; k_hash32[o] = (uint32_t)r.qhash ^ (uint32_t)(r.qhash >> 32); k_bits[o] = r.bits;
             span = clip_e(ke, rg) - clip_s(ks, rg);            // the part of the read inside the shard's range
         }
@@ -261,8 +262,8 @@ __global__ void iota_kernel(uint32_t *p, size_t n) { size_t i = (size_t)blockIdx
 // per output line: where it comes from (one 16-byte load in the emit kernel instead of a chain of dependent loads)
 struct __align__(16) EmitDesc { unsigned long long src_off; uint32_t len; uint32_t add_nl; };
 
-__global__ void outlen_kernel(const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ s_end, const uint32_t *__restrict__ k_len, const uint32_t *__restrict__ k_rec,
-                              const SamRec *__restrict__ recs, size_t K, Range rg, unsigned long long *__restrict__ len, EmitDesc *__restrict__ desc,
+__global__ void outlen_kernel(const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ s_end, const uint32_t *__restrict__ k_len, const unsigned long long *__restrict__ k_off,
+                              const uint8_t *__restrict__ k_bits, size_t K, Range rg, unsigned long long *__restrict__ len, EmitDesc *__restrict__ desc,
                               unsigned long long *__restrict__ n_owned)
 {
     size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,9 +271,9 @@ __global__ void outlen_kernel(const uint32_t *__restrict__ perm, const unsigned 
     if (o < K) {
         const uint32_t ord = perm[o];
         mine = owns_last(s_end[o], rg);                 // a read whose last base lies beyond the range is written by the next shard
-        const SamRec &r = recs[k_rec[ord]];
-        EmitDesc d; d.src_off = r.line_off; d.len = mine ? r.line_len : 0u; d.add_nl = (mine && (r.bits & REC_NO_NL)) ? 1u : 0u;
-        len[o] = mine ? k_len[ord] : 0u;
+        const uint32_t kl = k_len[ord]; const uint32_t nonl = (k_bits[ord] & REC_NO_NL) ? 1u : 0u;       // kl counts the newline the line will get
+        EmitDesc d; d.src_off = k_off[ord]; d.len = mine ? kl - nonl : 0u; d.add_nl = mine ? nonl : 0u;
+        len[o] = mine ? kl : 0u;
         desc[o] = d;
     }
     const unsigned m = __ballot_sync(0xffffffffu, mine);

@@ -317,9 +317,9 @@ __global__ void expect_kernel(const HitTarget *__restrict__ hits, size_t H, cons
 // ------------------------------------------------------------------------------------------
 // phase 1: chunk maps
 // ------------------------------------------------------------------------------------------
-constexpr int DRY_MARKS = 48;
-
 // attemptToMutateBase over the whole pileup of hit h, counting draws only.  0 ok, else CHAIN_* bits.
+// "handled" marks only ever point forward (an entry marks the first LATER entry of its QNAME), so one bit per entry is enough;
+// the bits live in local memory (deep panels: thousands of entries per pileup, dozens of marks).
 __device__ int dry_apply(const ChainArgs &A, size_t h, int64_t g, unsigned long long &k)
 {
     const HitTarget ht = A.hits[h];
@@ -330,19 +330,20 @@ __device__ int dry_apply(const ChainArgs &A, size_t h, int64_t g, unsigned long 
     if (ht.base == 'G' || ht.base == 'C' || ht.base == 'A' || ht.base == 'T') allele = ht.base;           // :1199-1203
     const PlpEntry *ents = A.ent + A.eoff[h];
     const uint32_t n = (uint32_t)(A.eoff[h + 1] - A.eoff[h]);
-    int32_t marks[DRY_MARKS]; int nm = 0;
+    if (n > (uint32_t)MAX_PILEUP) return CHAIN_COMPLEX;
+    uint32_t marks[(MAX_PILEUP + 31) / 32];
+    const uint32_t nw = (n + 31) >> 5;
+    for (uint32_t i = 0; i < nw; i++) marks[i] = 0;
     for (uint32_t j = 0; j < n; j++) {
         const PlpEntry e = ents[j];
         if (e.skip || e.bq == 0) continue;
-        bool handled = false;
-        for (int i = 0; i < nm; i++) handled |= marks[i] == (int32_t)j;
-        if (handled) continue;
+        if ((marks[j >> 5] >> (j & 31)) & 1u) continue;
         uint8_t mb = 0, mq = 0; bool mh = false;
-        if (e.mate >= 0) { const PlpEntry y = ents[e.mate]; mb = y.base; mq = y.bq; for (int i = 0; i < nm; i++) mh |= marks[i] == e.mate; }
+        if (e.mate >= 0) { const PlpEntry y = ents[e.mate]; mb = y.base; mq = y.bq; mh = ((marks[(uint32_t)e.mate >> 5] >> ((uint32_t)e.mate & 31)) & 1u) != 0; }
         const EntryOut o = entry_eval(A, e, mb, mq, mh, false, k, ht.thresh, Fb, allele);
         if (!o.ok) return CHAIN_OVERRUN;
         k += o.draws;
-        if (o.mark_mate && e.mate >= 0) { if (nm == DRY_MARKS) return CHAIN_COMPLEX; marks[nm++] = e.mate; }
+        if (o.mark_mate && e.mate >= 0) marks[(uint32_t)e.mate >> 5] |= 1u << ((uint32_t)e.mate & 31);
     }
     return 0;
 }

@@ -20,12 +20,15 @@
 // record (one warp per exception).  In a 60-column genome FASTA that is a few thousand
 // exceptions per 3 GB.
 //
-// tnc_scan_kernel is bit-sliced: each thread classifies 32 bytes with SWAR byte tricks (PRMT
-// table lookup + zero-byte detection), transposes the per-byte flags into 32-position bit
-// planes, and counts all 64 contexts with AND + POPC into 64 register counters.  No shared
-// memory atomics in the hot loop.
+// tnc_scan_kernel: every thread takes 16 bytes per step.  A chunk whose bytes (and 2-byte halo) are all one of A C G T '\n' --
+// checked exactly with one PRMT table lookup per word -- takes the fast path: bytes -> 3-bit symbols, the 4-mers at every second
+// position -> base-6 bin by one dp4a -> a 1296-bin shared-memory histogram (8 shared atomics per 16 bytes), folded into the 64
+// contexts once per block.  Anything else (N, lower case, '>', '\r', ragged end) takes the generic per-position path.  Newline
+// positions are queued per warp and handled 32 at a time.  The per-segment "no upper-case base" counters that let the fix-up
+// kernel jump over N blocks count 16-byte chunks (256 per 4 KiB segment).
 #include "common.cuh"
 #include <stdlib.h>
+#include <vector>
 
 namespace {
 
@@ -301,7 +304,7 @@ __device__ long scan_fwd_newline(const uint8_t *b, long n, long q)
 
 // Last byte of the nearest kept, newline-terminated record that ends before line start q
 // (0 when there is none): the reference's 1-byte carry (tncCountsProfile.c:441-443).
-// every 32-byte chunk of segment s is free of upper-case bases
+// every 16-byte chunk of segment s is free of upper-case bases
 __device__ __forceinline__ bool seg_free(const uint32_t *seg, long n, long s)
 {
     const long left = n - (s << TNC_SEG_SHIFT);
@@ -437,7 +440,7 @@ struct TncScratch {
     unsigned long long *acc;         // 64 per-call accumulators
     uint32_t           *exc;
     uint32_t            exc_cap;
-    uint32_t           *seg;         // per 4 KiB segment: number of 32-byte chunks without an upper-case base
+    uint32_t           *seg;         // per 4 KiB segment: number of 16-byte chunks without an upper-case base
     size_t              seg_words;
     uint8_t            *tail;        // first byte after the scratch arrays (256-byte aligned)
 };
@@ -603,6 +606,176 @@ extern "C" int ssb_tnc_count_host(ssb_ctx *ctx, const uint8_t *fasta, size_t n, 
     }
     snprintf(ctx->err, sizeof ctx->err, "tnc: exception list overflow in safe mode");
     return SSB_E_FORMAT;
+}
+
+// ---- BED-restricted scan (BASELINE config 3) ---------------------------------------------------------------------
+// The reference has no BED input; the semantics are those of running it on the FASTA `bedtools getfasta` would make: per interval,
+// in BED order, a header line and the interval's bases on ONE line.  That FASTA is built here on the device (a gather over the
+// genome text through a .fai-style index) and scanned by the exact kernels above, so every quirk of the reference -- which records
+// are kept, the single straddling window between consecutive kept records -- is inherited rather than restated.
+namespace {
+__global__ void bed_len_kernel(const ssb_bed_interval *__restrict__ iv, size_t first, size_t n_own, long long ctx_iv, unsigned long long *__restrict__ len)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_own) return;
+    // slot 0 = the context record (the nearest earlier interval that holds an upper-case base; empty when there is none), then the own ones
+    const long long k = i == 0 ? ctx_iv : (long long)(first + i - 1);
+    len[i] = k < 0 ? 0ull : (unsigned long long)(iv[k].end - iv[k].start) + 3ull;        // ">\n" + bases + "\n"
+}
+__device__ __forceinline__ size_t fasta_byte(const ssb_fasta_contig &c, int64_t p) { return (size_t)c.seq_off + (size_t)p + (size_t)(p / c.line_bases) * (size_t)(c.line_bytes - c.line_bases); }
+// one warp per record
+__global__ void bed_gather_kernel(const uint8_t *__restrict__ fa, size_t n, const ssb_fasta_contig *__restrict__ contigs, size_t n_contigs, const ssb_bed_interval *__restrict__ iv,
+                                  size_t first, size_t n_own, long long ctx_iv, const unsigned long long *__restrict__ off, uint8_t *__restrict__ out, unsigned int *__restrict__ bad)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i > n_own) return;
+    const long long k = i == 0 ? ctx_iv : (long long)(first + i - 1);
+    if (k < 0) return;
+    const ssb_bed_interval v = iv[k];
+    if (v.contig < 0 || (size_t)v.contig >= n_contigs || v.start < 0 || v.end < v.start || v.end > contigs[v.contig].len) { if (lane == 0) atomicOr(bad, 1u); return; }
+    const ssb_fasta_contig c = contigs[v.contig];
+    uint8_t *o = out + off[i];
+    if (lane == 0) { o[0] = '>'; o[1] = '\n'; o[2 + (v.end - v.start)] = '\n'; }
+    for (int64_t p = v.start + lane; p < v.end; p += 32) {
+        const size_t b = fasta_byte(c, p);
+        const uint8_t ch = b < n ? fa[b] : (uint8_t)'\n';
+        if (ch == '\n' || ch == '>') atomicOr(bad, 2u);                  // the index does not describe this file
+        o[2 + (p - v.start)] = ch;
+    }
+}
+// nearest interval before `first` that holds an upper-case base (its last base is what the reference would carry into the next record)
+__global__ void bed_context_kernel(const uint8_t *__restrict__ fa, size_t n, const ssb_fasta_contig *__restrict__ contigs, size_t n_contigs, const ssb_bed_interval *__restrict__ iv,
+                                   size_t first, long long *__restrict__ ctx_iv)
+{
+    const int lane = threadIdx.x;
+    for (long long k = (long long)first - 1; k >= 0; k--) {
+        const ssb_bed_interval v = iv[k];
+        if (v.contig < 0 || (size_t)v.contig >= n_contigs || v.start < 0 || v.end > contigs[v.contig].len) continue;
+        const ssb_fasta_contig c = contigs[v.contig];
+        bool any = false;
+        for (int64_t p0 = v.start; p0 < v.end && !any; p0 += 32) {
+            const int64_t p = p0 + lane;
+            uint8_t ch = 0;
+            if (p < v.end) { const size_t b = fasta_byte(c, p); ch = b < n ? fa[b] : 0; }
+            any = __ballot_sync(0xffffffffu, is_base(ch)) != 0u;
+        }
+        if (any) { if (lane == 0) *ctx_iv = k; return; }
+    }
+    if (lane == 0) *ctx_iv = -1;
+}
+__global__ void sub_counts_kernel(unsigned long long *__restrict__ a, const unsigned long long *__restrict__ b) { a[threadIdx.x] -= b[threadIdx.x]; }
+} // namespace
+
+extern "C" int ssb_tnc_count_bed_device(ssb_ctx *ctx, const uint8_t *d_fasta, size_t n, const ssb_fasta_contig *contigs, size_t n_contigs,
+                                        const ssb_bed_interval *intervals, size_t n_intervals, size_t first, size_t last, int64_t *d_counts64)
+{
+    if (!ctx || (!d_fasta && n) || !d_counts64 || (n_contigs && !contigs) || (n_intervals && !intervals) || first > last || last > n_intervals) return SSB_E_ARG;
+    if (first == last) return SSB_OK;
+    SSB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t n_own = last - first;
+    size_t own_bytes = 0, max_len = 0;
+    for (size_t i = 0; i < n_intervals; i++) {
+        if (intervals[i].end < intervals[i].start) return SSB_E_ARG;
+        const size_t l = (size_t)(intervals[i].end - intervals[i].start);
+        if (i < first && l > max_len) max_len = l;
+        if (i >= first && i < last) own_bytes += l + 3;
+    }
+    struct Bufs { void *p[8]; int k = 0; ~Bufs() { for (int i = 0; i < k; i++) cudaFree(p[i]); } } bufs;
+    auto dev = [&](size_t bytes) -> void * { void *q = NULL; if (cudaMalloc(&q, bytes ? bytes : 1) != cudaSuccess) return NULL; bufs.p[bufs.k++] = q; return q; };
+    ssb_fasta_contig *d_contigs = (ssb_fasta_contig *)dev(n_contigs * sizeof *contigs);
+    ssb_bed_interval *d_iv = (ssb_bed_interval *)dev(n_intervals * sizeof *intervals);
+    unsigned long long *d_len = (unsigned long long *)dev((n_own + 2) * 8), *d_off = (unsigned long long *)dev((n_own + 2) * 8);
+    const size_t out_cap = own_bytes + max_len + 3 + 64;
+    uint8_t *d_out = (uint8_t *)dev(out_cap);
+    long long *d_ctx = (long long *)dev(64);                     // [0] context interval, [1] flags, [2..] 64 counters follow in their own buffer
+    unsigned long long *d_tmp = (unsigned long long *)dev(64 * 8);
+    if (!d_contigs || !d_iv || !d_len || !d_off || !d_out || !d_ctx || !d_tmp) { snprintf(ctx->err, sizeof ctx->err, "tnc/bed: device allocation failed"); return SSB_E_NOMEM; }
+    SSB_CUDA(ctx, cudaMemcpyAsync(d_contigs, contigs, n_contigs * sizeof *contigs, cudaMemcpyHostToDevice, s));
+    SSB_CUDA(ctx, cudaMemcpyAsync(d_iv, intervals, n_intervals * sizeof *intervals, cudaMemcpyHostToDevice, s));
+    SSB_CUDA(ctx, cudaMemsetAsync(d_ctx, 0, 64, s));
+    SSB_LAUNCH(ctx, bed_context_kernel, 1, 32, 0, s, d_fasta, n, d_contigs, n_contigs, d_iv, first, d_ctx);
+    long long h_ctx = -1;
+    SSB_CUDA(ctx, cudaMemcpyAsync(&h_ctx, d_ctx, 8, cudaMemcpyDeviceToHost, s));
+    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+    SSB_LAUNCH(ctx, bed_len_kernel, (int)((n_own + 1 + 255) / 256), 256, 0, s, d_iv, first, n_own, h_ctx, d_len);
+    // offsets: host prefix sums (a few hundred thousand intervals)
+    std::vector<unsigned long long> off(n_own + 2);
+    off[0] = 0; off[1] = h_ctx < 0 ? 0 : (unsigned long long)(intervals[h_ctx].end - intervals[h_ctx].start) + 3;
+    for (size_t i = 0; i < n_own; i++) off[i + 2] = off[i + 1] + (unsigned long long)(intervals[first + i].end - intervals[first + i].start) + 3;
+    const size_t total = (size_t)off[n_own + 1], ctx_bytes = (size_t)off[1];
+    if (total > out_cap) return SSB_E_STATE;
+    SSB_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), (n_own + 2) * 8, cudaMemcpyHostToDevice, s));
+    unsigned int *d_bad = (unsigned int *)(d_ctx + 1);
+    SSB_LAUNCH(ctx, bed_gather_kernel, (int)(((n_own + 1) * 32 + 127) / 128), 128, 0, s, d_fasta, n, d_contigs, n_contigs, d_iv, first, n_own, h_ctx, d_off, d_out, d_bad);
+    unsigned int h_bad = 0;
+    SSB_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (h_bad) { snprintf(ctx->err, sizeof ctx->err, "tnc/bed: %s", (h_bad & 1) ? "an interval lies outside its contig" : "the FASTA index does not describe the file (line widths)"); return SSB_E_FORMAT; }
+    // the built FASTA through the exact scan; then take the context record's own windows off again
+    int rc = ssb_tnc_count_device(ctx, d_out, total, NULL, NULL, d_counts64);
+    if (rc) return rc;
+    if (ctx_bytes) {
+        SSB_CUDA(ctx, cudaMemsetAsync(d_tmp, 0, 64 * 8, s));
+        if ((rc = ssb_tnc_count_device(ctx, d_out, ctx_bytes, NULL, NULL, (int64_t *)d_tmp))) return rc;
+        SSB_LAUNCH(ctx, sub_counts_kernel, 1, 64, 0, s, (unsigned long long *)d_counts64, (const unsigned long long *)d_tmp);
+    }
+    SSB_CUDA(ctx, cudaStreamSynchronize(s));
+    return SSB_OK;
+}
+
+// .fai-style index of a FASTA text (host): one entry per '>' record, in file order.  names[i] points into the text (not NUL
+// terminated).  Like faidx it takes the line geometry from a record's first sequence line and expects every line but the last to
+// have that width ('>' cannot occur inside a sequence line, so the next record is found by a byte search, not line by line).
+extern "C" int ssb_fasta_index(const uint8_t *fa, size_t n, ssb_fasta_contig *out, const char **names, uint32_t *name_lens, size_t cap, size_t *n_out)
+{
+    if ((!fa && n) || !n_out) return SSB_E_ARG;
+    size_t k = 0, p = 0;
+    while (p < n) {
+        if (fa[p] != '>') {                                   // text before the first header: skip the line
+            const uint8_t *nl = (const uint8_t *)memchr(fa + p, '\n', n - p);
+            if (!nl) break;
+            p = (size_t)(nl - fa) + 1;
+            continue;
+        }
+        const uint8_t *nl = (const uint8_t *)memchr(fa + p, '\n', n - p);
+        const size_t e = nl ? (size_t)(nl - fa) : n;          // end of the header line
+        const size_t s0 = e < n ? e + 1 : n;                  // first sequence byte
+        size_t end = n;                                       // start of the next record
+        for (size_t r = s0; r < n;) {
+            const uint8_t *g = (const uint8_t *)memchr(fa + r, '>', n - r);
+            if (!g) break;
+            const size_t gp = (size_t)(g - fa);
+            if (gp == s0 || fa[gp - 1] == '\n') { end = gp; break; }
+            r = gp + 1;
+        }
+        if (k < cap && out) {
+            size_t q = p + 1; while (q < e && fa[q] != ' ' && fa[q] != '\t' && fa[q] != '\r') q++;
+            if (names) names[k] = (const char *)fa + p + 1;
+            if (name_lens) name_lens[k] = (uint32_t)(q - p - 1);
+            ssb_fasta_contig c; c.seq_off = s0; c.len = 0; c.line_bases = 0; c.line_bytes = 0;
+            const size_t bytes = end - s0;
+            if (bytes) {
+                const uint8_t *nl2 = (const uint8_t *)memchr(fa + s0, '\n', bytes);
+                const size_t l_bytes = nl2 ? (size_t)(nl2 - (fa + s0)) + 1 : bytes;            // first line incl. its newline
+                size_t term = nl2 ? 1 : 0; if (nl2 && l_bytes >= 2 && fa[s0 + l_bytes - 2] == '\r') term = 2;
+                c.line_bytes = (uint32_t)l_bytes; c.line_bases = (uint32_t)(l_bytes - term);
+                if (c.line_bases) {
+                    const size_t full = bytes / l_bytes, rest = bytes % l_bytes;
+                    size_t tail = rest;                       // a last, shorter line (with or without terminator)
+                    if (tail && fa[s0 + bytes - 1] == '\n') tail--;
+                    if (tail && term == 2 && fa[s0 + full * l_bytes + tail - 1] == '\r') tail--;
+                    c.len = (int64_t)(full * c.line_bases + tail);
+                }
+            }
+            out[k] = c;
+        }
+        k++;
+        p = end;
+    }
+    *n_out = k;
+    return SSB_OK;
 }
 
 // Host restatement of the *state transition only* (no counting): lets a caller cut a FASTA into

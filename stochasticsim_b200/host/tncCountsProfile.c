@@ -2,6 +2,8 @@
  * tncCountsProfile -- drop-in replacement for the reference program of the same name.
  *
  *   tncCountsProfile <target fasta>            (same argv, stdout and exit codes as the reference)
+ *   tncCountsProfile <genome fasta> <bed>      (extension, BASELINE config 3: the counts the reference gives on the FASTA that
+ *                                               `bedtools getfasta -fi <genome> -bed <bed>` would write, without writing it)
  *
  * Replaces main() of tncCountsProfile.c:366-485.  This file stays in C and only does what a host
  * has to do -- open/map the file, hand byte ranges to the GPU(s), print the 32 lines.  All
@@ -35,18 +37,54 @@ typedef struct {
     ssb_tnc_carry carry_in;
     int64_t counts[64];
     int rc;
+    /* BED mode: the whole genome text goes to every GPU, the intervals [first, last) are this GPU's share */
+    const ssb_fasta_contig *contigs; size_t n_contigs; const ssb_bed_interval *iv; size_t n_iv, first, last; size_t n_all;
 } shard_t;
 
 static void *shard_main(void *arg)
 {
     shard_t *s = (shard_t *)arg;
-    s->rc = ssb_tnc_count_host(s->ctx, s->base + s->off, s->len, &s->carry_in, NULL, s->counts);
+    if (!s->iv) { s->rc = ssb_tnc_count_host(s->ctx, s->base + s->off, s->len, &s->carry_in, NULL, s->counts); return NULL; }
+    void *d_fa = NULL, *d_cnt = NULL;
+    s->rc = ssb_dev_alloc(s->ctx, s->n_all + 64, &d_fa);
+    if (!s->rc) s->rc = ssb_dev_alloc(s->ctx, sizeof s->counts, &d_cnt);
+    if (!s->rc) s->rc = ssb_memcpy_h2d(s->ctx, d_fa, s->base, s->n_all);
+    if (!s->rc) s->rc = ssb_memset_dev(s->ctx, d_cnt, 0, sizeof s->counts);
+    if (!s->rc) s->rc = ssb_tnc_count_bed_device(s->ctx, (const uint8_t *)d_fa, s->n_all, s->contigs, s->n_contigs, s->iv, s->n_iv, s->first, s->last, (int64_t *)d_cnt);
+    if (!s->rc) s->rc = ssb_memcpy_d2h(s->ctx, s->counts, d_cnt, sizeof s->counts);
+    if (!s->rc) s->rc = ssb_sync(s->ctx);
+    if (d_fa) ssb_dev_free(s->ctx, d_fa);
+    if (d_cnt) ssb_dev_free(s->ctx, d_cnt);
     return NULL;
+}
+
+/* BED rows "chrom<TAB>start<TAB>end[...]" -> intervals, chrom looked up in the FASTA index; lines starting with '#', "track" or
+ * "browser" are skipped, unknown contigs are an error */
+static ssb_bed_interval *load_bed(const char *fn, const char **names, const uint32_t *name_lens, size_t n_contigs, size_t *n_out)
+{
+    FILE *f = fopen(fn, "r");
+    if (!f) return NULL;
+    size_t n = 0, cap = 1024; ssb_bed_interval *v = malloc(cap * sizeof *v);
+    char *line = NULL; size_t lcap = 0;
+    while (getline(&line, &lcap, f) != -1) {
+        if (line[0] == '#' || line[0] == '\n' || !strncmp(line, "track", 5) || !strncmp(line, "browser", 7)) continue;
+        char *t1 = strchr(line, '\t'); if (!t1) continue;
+        const size_t nl = (size_t)(t1 - line);
+        long long a = 0, b = 0;
+        if (sscanf(t1 + 1, "%lld\t%lld", &a, &b) != 2) continue;
+        int c = -1;
+        for (size_t i = 0; i < n_contigs; i++) if (name_lens[i] == nl && !memcmp(names[i], line, nl)) { c = (int)i; break; }
+        if (c < 0) { fprintf(stderr, "tncCountsProfile: BED contig %.*s is not in the FASTA\n", (int)nl, line); free(v); fclose(f); *n_out = 0; return NULL; }
+        if (n == cap) { cap *= 2; v = realloc(v, cap * sizeof *v); }
+        v[n].contig = c; v[n].reserved = 0; v[n].start = a; v[n].end = b; n++;
+    }
+    free(line); fclose(f);
+    *n_out = n;
+    return v;
 }
 
 int main(int argc, char **argv)
 {
-    (void)argc;
     /* tncCountsProfile.c:380-382: fopen failure (or no argument) -> silent exit(EXIT_FAILURE) */
     int fd = argv[1] ? open(argv[1], O_RDONLY) : -1;
     if (fd < 0) exit(EXIT_FAILURE);
@@ -78,6 +116,17 @@ int main(int argc, char **argv)
     if (ngpu < 1) ngpu = 1;
     if (ngpu > 64) ngpu = 64;
     if ((size_t)ngpu > n / 4096 + 1) ngpu = (int)(n / 4096 + 1);
+    /* BED mode (second argument) */
+    ssb_fasta_contig *contigs = NULL; ssb_bed_interval *iv = NULL; size_t n_contigs = 0, n_iv = 0;
+    if (argc > 2 && argv[2]) {
+        ssb_fasta_index(data, n, NULL, NULL, NULL, 0, &n_contigs);
+        contigs = malloc((n_contigs + 1) * sizeof *contigs);
+        const char **names = malloc((n_contigs + 1) * sizeof *names); uint32_t *nlens = malloc((n_contigs + 1) * sizeof *nlens);
+        ssb_fasta_index(data, n, contigs, names, nlens, n_contigs, &n_contigs);
+        iv = load_bed(argv[2], names, nlens, n_contigs, &n_iv);
+        if (!iv) exit(EXIT_FAILURE);
+        if ((size_t)ngpu > n_iv / 64 + 1) ngpu = (int)(n_iv / 64 + 1);
+    }
 
     shard_t sh[64]; ssb_ctx *ctxs[64];
     memset(sh, 0, sizeof sh);
@@ -86,11 +135,13 @@ int main(int argc, char **argv)
         if (rc) { fprintf(stderr, "tncCountsProfile: device %d: %s\n", dev0 + g, ssb_strerror(rc)); return 3; }
         sh[g].ctx = ctxs[g]; sh[g].base = data;
         sh[g].off = (n / (size_t)ngpu * (size_t)g) & ~(size_t)31;
+        if (iv) { sh[g].iv = iv; sh[g].n_iv = n_iv; sh[g].contigs = contigs; sh[g].n_contigs = n_contigs; sh[g].n_all = n;
+                  sh[g].first = n_iv * (size_t)g / (size_t)ngpu; sh[g].last = n_iv * (size_t)(g + 1) / (size_t)ngpu; }
     }
     for (int g = 0; g < ngpu; g++) {
         sh[g].len = (g + 1 < ngpu ? sh[g + 1].off : n) - sh[g].off;
         /* scanner state at the shard start, from the bytes before it (no counting) */
-        if (g) ssb_tnc_carry_after(data, sh[g].off, NULL, &sh[g].carry_in);
+        if (g && !iv) ssb_tnc_carry_after(data, sh[g].off, NULL, &sh[g].carry_in);
     }
     pthread_t th[64];
     for (int g = 1; g < ngpu; g++) pthread_create(&th[g], NULL, shard_main, &sh[g]);

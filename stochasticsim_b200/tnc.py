@@ -46,6 +46,55 @@ def carry_after(data, carry_in=None):
     return out
 
 
+class FastaContig(C.Structure):
+    _fields_ = [("seq_off", C.c_uint64), ("len", C.c_int64), ("line_bases", C.c_uint32), ("line_bytes", C.c_uint32)]
+
+
+class BedInterval(C.Structure):
+    _fields_ = [("contig", C.c_int32), ("reserved", C.c_int32), ("start", C.c_int64), ("end", C.c_int64)]
+
+
+def fasta_index(data):
+    """[(name, FastaContig)] -- ssb_fasta_index (host): a .fai-style index of a FASTA text."""
+    L = lib()
+    L.ssb_fasta_index.restype = C.c_int
+    L.ssb_fasta_index.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(FastaContig), C.POINTER(C.c_char_p), C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]
+    addr, n, keep = _buf(data)
+    cnt = C.c_size_t()
+    check(L.ssb_fasta_index(addr, n, None, None, None, 0, C.byref(cnt)))
+    k = cnt.value
+    arr = (FastaContig * max(1, k))()
+    nl = (C.c_uint32 * max(1, k))()
+    names = (C.c_void_p * max(1, k))()
+    check(L.ssb_fasta_index(addr, n, arr, C.cast(names, C.POINTER(C.c_char_p)), nl, k, C.byref(cnt)))
+    out = []
+    for i in range(k):
+        name = C.string_at(names[i], nl[i]).decode()
+        c = FastaContig(arr[i].seq_off, arr[i].len, arr[i].line_bases, arr[i].line_bytes)
+        out.append((name, c))
+    return out
+
+
+def count_bed_device(ctx, d_ptr, n, index, intervals, d_counts, first=0, last=None):
+    """Adds the windows of BED intervals [first, last) (in the order given; (contig index, start, end)) to the 64 device counters."""
+    L = lib()
+    L.ssb_tnc_count_bed_device.restype = C.c_int
+    L.ssb_tnc_count_bed_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(FastaContig), C.c_size_t, C.POINTER(BedInterval), C.c_size_t,
+                                           C.c_size_t, C.c_size_t, C.c_void_p]
+    carr = (FastaContig * max(1, len(index)))(*[c for _, c in index])
+    if isinstance(intervals, np.ndarray):                      # structured rows (contig, start, end) as int64 columns
+        iv = (BedInterval * max(1, len(intervals)))()
+        flat = np.zeros((len(intervals), 3), dtype=np.int64)
+        flat[:, 0] = intervals[:, 0]; flat[:, 1] = intervals[:, 1]; flat[:, 2] = intervals[:, 2]
+        raw = np.zeros(len(intervals), dtype=[("contig", "<i4"), ("reserved", "<i4"), ("start", "<i8"), ("end", "<i8")])
+        raw["contig"], raw["start"], raw["end"] = flat[:, 0], flat[:, 1], flat[:, 2]
+        C.memmove(iv, raw.ctypes.data, raw.nbytes)
+    else:
+        iv = (BedInterval * max(1, len(intervals)))(*[BedInterval(c, 0, a, b) for c, a, b in intervals])
+    last = len(intervals) if last is None else last
+    check(L.ssb_tnc_count_bed_device(ctx.handle, d_ptr, n, carr, len(index), iv, len(intervals), first, last, d_counts), ctx.handle)
+
+
 def format_counts(counts64):
     """The reference's 32-line stdout (tncCountsProfile.c:452-483)."""
     L = lib()
