@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("SSB_BENCH_WORKLOAD", "auto"), choices=["auto", "spike", "tnc"])
+    ap.add_argument("--workload", default=os.environ.get("SSB_BENCH_WORKLOAD", "auto"), choices=["auto", "spike", "tnc", "panel"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only; the judged run uses 1.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tnc", action="store_true", help="spike workload only (development)")
@@ -452,6 +452,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
     import numpy as np
     import stochasticsim_b200 as ssb
+    if workload == "panel":
+        import bench_spike
+        res = bench_spike.run_panel(args, D)
+        if D.rank == 0:
+            emit(res)
+        D.close()
+        return
     if workload == "spike":
         import bench_spike
         res, ctx = bench_spike.run(args, D)

@@ -175,7 +175,7 @@ def run(args, D):
     N = D.world
     names = ["chr19"] if N == 1 else ["chr19.%d" % g for g in range(N)]
     # ONE input: N contigs of the same generator seed, cut into N coordinate ranges of equal expected cost (SSB_BENCH_BALANCE=0: one contig each).
-    balance = os.environ.get("SSB_BENCH_BALANCE", "1") != "0"
+    balance = os.environ.get("SSB_BENCH_BALANCE", "0") != "0"      # default: one contig per shard -- phase 1 cannot start before the slowest rank has parsed (the window centres need every earlier shard's expected draws), so equal reads per rank win
     cuts = balanced_cuts(N, N, balance)
     HALO = 1024                                               # bases: 150 bp reads with a few indels span < 200
     def to_pos(x):                                            # contig units -> (contig, position)
@@ -457,3 +457,118 @@ def run_reference(args, D):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "C2 chr19 synthetic 150bp paired reads at 100x with 10k SBS spike loci (bounded sub-region sample)"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+# ------------------------------------------------------------------------------------------------------------ C5: deep panel
+def make_panel(L, n_intervals, depth, seed=5, log=None):
+    """BASELINE configs[4] in the shape one of 8 GPUs gets when n_intervals = 625: 1 kb panel intervals (1.5 kb windows so that
+    the core reaches the full depth) on 22 contigs, 150 bp pairs with fragments N(200, 20) -- ~40 % of the pairs overlap --, a target on every
+    50th core base with AF U(0.005, 0.05).  Returns (names, {name: ref bytes}, body parts, n_reads, spike text)."""
+    p = SynthParams()
+    L.synth_default_params(C.byref(p))
+    p.seed, p.read_len, p.frag_mean, p.frag_sd, p.coverage = seed, 150, 200.0, 20.0, depth
+    p.sub_rate, p.indel_rate = 0.001, 0.0001
+    names = ["chr%d" % (i + 1) for i in range(22)]
+    per = (n_intervals + 21) // 22
+    pitch, win, core0, core = 10_000, 1_500, 250, 1_000
+    contig_len = per * pitch + 2_000
+    refs, jobs = {}, []
+    for c, nm in enumerate(names):
+        ref = np.empty(contig_len + 1, dtype=np.uint8)
+        L.synth_ref_contig(C.byref(p), c, contig_len, 0, contig_len, 0, ref.ctypes.data)
+        refs[nm] = ref
+        for i in range(per):
+            if c * per + i < n_intervals:
+                jobs.append((c, 1_000 + i * pitch))
+    jobs.sort()
+
+    def gen(job):
+        c, w0 = job
+        cap = int(depth / 150.0 * 420.0 * win * 1.3) + (1 << 16)
+        buf = np.empty(cap, dtype=np.uint8)
+        nr = C.c_int64()
+        need = L.synth_sam_range(C.byref(p), c, names[c].encode(), refs[names[c]].ctypes.data, contig_len, w0, w0 + win, w0, w0 + win, buf.ctypes.data, cap, C.byref(nr))
+        if need > cap:
+            buf = np.empty(need, dtype=np.uint8)
+            L.synth_sam_range(C.byref(p), c, names[c].encode(), refs[names[c]].ctypes.data, contig_len, w0, w0 + win, w0, w0 + win, buf.ctypes.data, need, C.byref(nr))
+        return buf[:need], nr.value
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
+        parts = list(ex.map(gen, jobs))
+    rng = np.random.default_rng(seed)
+    lines = []
+    for c, w0 in jobs:
+        for x in range(w0 + core0, w0 + core0 + core, 50):
+            lines.append("%s\t%d\t.\t%.4g\n" % (names[c], x + 1, rng.uniform(0.005, 0.05)))
+    n_reads = sum(nr for _, nr in parts)
+    if log:
+        log(f"[bench] panel: {len(jobs)} intervals, {n_reads} reads, {sum(b.size for b, _ in parts)} SAM bytes, {len(lines)} targets in {time.perf_counter() - t0:.1f} s")
+    return names, {k: v[:contig_len].tobytes() for k, v in refs.items()}, [b for b, _ in parts], n_reads, "".join(lines).encode()
+
+
+def run_panel(args, D):
+    """--workload panel: the deep-panel shape (C5).  One GPU's share of the 8-GPU split by default (625 of the 5,000 intervals); --scale 8 = all of C5."""
+    import torch
+    import stochasticsim_b200 as ssb
+    from stochasticsim_b200 import spike as sp
+    from bench import ClockSampler, measured_peaks, log
+    peak, peak_src = measured_peaks()
+    torch.cuda.set_device(D.local)
+    L = synth_lib()
+    n_intervals = max(1, int(round(625 * args.scale)))
+    names, refs, parts, n_reads, spike_text = make_panel(L, n_intervals, 2000.0, log=log)
+    n = sum(b.size for b in parts)
+    ctx = ssb.Context(D.local)
+    ctx.profile_enable(True)
+    hp = ctx.host_alloc(n + 64)
+    off = 0
+    for b in parts:
+        C.memmove(hp + off, b.ctypes.data, b.size)
+        off += b.size
+    del parts
+    d_in, d_out = ctx.dev_alloc(n + 64), ctx.dev_alloc(n + 64)
+    ctx.h2d(d_in, hp, n)
+    ctx.sync()
+    targets = sp.parse_spike(spike_text, names)
+    S = sp.Spike(ctx, names, refs)
+    tarr = S.make_targets(targets)
+    res = (sp.TargetResult * len(targets))()
+    st = sp.Stats()
+    steps, warm = max(1, min(args.steps, 5)), 1
+    for _ in range(warm):
+        out_bytes = S.run_device(d_in, n, d_out, n + 1, tarr, len(targets), SPIKE_SEED, res, st)
+    ctx.sync()
+    stage_ms = {}
+    with ClockSampler(D.local) as clk:
+        ctx.timer_start()
+        for _ in range(steps):
+            out_bytes = S.run_device(d_in, n, d_out, n + 1, tarr, len(targets), SPIKE_SEED, res, st)
+            for k, v in st.as_dict().items():
+                if k.startswith("ms_"):
+                    stage_ms[k] = stage_ms.get(k, 0.0) + v
+        ms = ctx.timer_stop()
+    stats = st.as_dict()
+    entries = sum(r.ref_cnt + r.mut_cnt + sum(r.err_cnt) for r in res if r.status == sp.T_HIT)
+    ms_step = ms / steps
+    out = {
+        "metric": "sam_reads_spiked_per_s", "value": n_reads * steps / (ms / 1e3), "unit": "reads/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C5 deep panel: %d of 5,000 1 kb intervals at 2000x (150 bp pairs, fragments N(200,20)), a target on every 50th base, AF 0.5-5 %%"
+                               % n_intervals + (" = one GPU's share of the 8-GPU split" if n_intervals == 625 else ""),
+                   "reads": n_reads, "sam_bytes": n, "targets": len(targets), "targets_hit": stats["n_hits"], "max_depth": stats["maxDepth"],
+                   "pileup_entries_tallied": int(entries), "spike_seed": SPIKE_SEED, "l2": "input (%.2f GB) larger than L2, no flush" % (n / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": "whole pass", "achieved": (n + out_bytes) / (ms_step / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": (n + out_bytes) / (ms_step / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "bound by the serial RNG chain over the pileups of the targets (one warp, entries staged in shared memory), not by HBM"},
+        "stages_ms_per_step": {k: v / steps for k, v in stage_ms.items()},
+        "rng_chain": {"ms_per_step": stage_ms.get("ms_chain", 0.0) / steps, "chunks": stats["chain_mode"], "draws": stats["rng_draws"],
+                      "ns_per_pileup_entry": stage_ms.get("ms_chain", 0.0) / steps * 1e6 / max(1, entries)},
+        "clocks": clk.summary(),
+    }
+    S.close()
+    ctx.host_free(hp)
+    ctx.dev_free(d_in)
+    ctx.dev_free(d_out)
+    ctx.close()
+    return out

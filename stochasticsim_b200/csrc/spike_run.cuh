@@ -810,7 +810,8 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         if (!A.R || from < k_base || serial_span(from) > M_abs) { if ((rc2 = make_stream(from, serial_span(from)))) return rc2; }
         if ((rc2 = reset_state())) return rc2;
         SSB_LAUNCH(ctx, serial_chunk_kernel, 1, 32, 0, s, d_serial, n_walk, from, is_last ? ~0ull : CHUNK_WALK_ONLY);
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, 1, 32, 0, s, A, d_serial, 1, d_draws, d_flags);
+        SSB_CUDA(ctx, cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CK_SMEM));
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel<true>, 1, 32, CK_SMEM, s, A, d_serial, 1, d_draws, d_flags);
         if ((rc2 = publish())) return rc2;
         return (hsc->flags & CHAIN_OVERRUN) ? RC_OVERRUN : SSB_OK;
     };
@@ -1055,7 +1056,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 if ((rc = publish())) return rc;                                                  // did the exact walker stay inside every window?
                 if (!hsc->flags) {
                     if ((rc = send_offset(hsc->k_end))) return rc;                                // the exit offset leaves as soon as the maps are composed
-                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel, grid_for((size_t)P * 32, 128), 128, 0, s, A, d_chunks, P, d_draws, d_flags);
+                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, chain_kernel<false>, grid_for((size_t)P * 32, 128), 128, 0, s, A, d_chunks, P, d_draws, d_flags);
                     if ((rc = publish())) return rc;                                              // sync 5
                 }
                 if (dbg_t) fprintf(stderr, "[chain %d] flags after phases 1-3: %u, odd patches %u\n", pl.index, (unsigned)hsc->flags, (unsigned)hsc->n_odd);

@@ -416,3 +416,16 @@ def test_window_miss_is_walked_again(name, chunk, group, sigma, tmp_path, ctx, m
     assert hdr + out == want[2]
     if sigma <= 0.5:
         assert st.n_window_retries > 0 or st.chain_mode == 1, "expected misses with windows this narrow"
+
+
+def test_deep_pileup_2000x(tmp_path, ctx):
+    """BASELINE C5's depth: ~2000 entries per pileup, a target every 20 bases, low VAF, overlapping pairs -- the one-warp chain with the
+    pileup staged in shared memory against the reference (whose mate search is quadratic in the depth: a short window)."""
+    prefix = sc.generate("deep_lowvaf", str(tmp_path), contigs="chr1:900", coverage=2000, read_len=150, frag_mean=200, frag_sd=20, spikes=30, af="0.005:0.05")
+    want = sc.run_cli(sc.CHECKER, prefix, str(tmp_path / "ora"), cmdname="stochasticSpike")
+    got = sc.run_cli(sc.PRODUCT, prefix, str(tmp_path / "gpu"))
+    assert want[0] == 0 and got[0] == 0, got[4]
+    assert b"maxDepth = 2" in want[1] or b"maxDepth = 1" in want[1]
+    assert got[2] == want[2], "SAM differs: " + first_diff(want[2], got[2])
+    assert got[1] == want[1]
+    assert vcf_cmp(want[3], got[3]), "truth.vcf differs: " + first_diff(want[3], got[3])
