@@ -231,6 +231,7 @@ int main(int argc, char **argv)
     size_t n_in; int mapped;
     uint8_t *in = slurp(argv[1], &n_in, &mapped);
     if (!in) { fprintf(stderr, "Couldn't open bam...\n"); return 1; }                         /* :962-965 */
+    int bgzf_input = 0;
     if (bam_is_bgzf(in, n_in)) {
         /* BGZF: inflate the blocks in parallel; a BAM inside is printed as SAM text (htslib's sam_open auto-detects the same way) */
         size_t n_raw = 0, n_txt = 0;
@@ -244,14 +245,7 @@ int main(int argc, char **argv)
             if (!txt) { fprintf(stderr, "Couldn't read header...\n"); return 1; }
             in = txt; n_in = n_txt;
         } else { in = raw; n_in = n_raw; }                                                            /* bgzip-compressed SAM text */
-        if (strcmp(argv[1], "-") != 0) {                                                              /* :1035-1039: the index must exist */
-            char ip[4200]; int have = 0;
-            snprintf(ip, sizeof ip, "%s.bai", argv[1]); if (access(ip, R_OK) == 0) have = 1;
-            snprintf(ip, sizeof ip, "%s.csi", argv[1]); if (access(ip, R_OK) == 0) have = 1;
-            size_t al = strlen(argv[1]);
-            if (al > 4 && !strcmp(argv[1] + al - 4, ".bam")) { snprintf(ip, sizeof ip, "%.*s.bai", (int)(al - 4), argv[1]); if (access(ip, R_OK) == 0) have = 1; }
-            if (!have) { fprintf(stderr, "\nCan't load index for %s..\n\n", argv[1]); exit(EXIT_FAILURE); }
-        }
+        bgzf_input = 1;
     }
     /* header = leading lines that start with '@' (sam_hdr_read, :971) */
     size_t hdr_end = 0;
@@ -299,6 +293,14 @@ int main(int argc, char **argv)
     fprintf(vcf, "##%sVersion=%s\n##%sCommand=%s %s %s %s %s\n", cmd, VERSION, cmd, argv[1], argv[2], argv[3], argv[4], argv[5]);
     fprintf(vcf, "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n", sample ? sample : "SAMPLE");
 
+    if (bgzf_input && strcmp(argv[1], "-") != 0) {                                            /* :1035-1039: the index must exist (checked where the reference checks: after both headers) */
+        char ip[4200]; int have = 0;
+        snprintf(ip, sizeof ip, "%s.bai", argv[1]); if (access(ip, R_OK) == 0) have = 1;
+        snprintf(ip, sizeof ip, "%s.csi", argv[1]); if (access(ip, R_OK) == 0) have = 1;
+        size_t al = strlen(argv[1]);
+        if (al > 4 && !strcmp(argv[1] + al - 4, ".bam")) { snprintf(ip, sizeof ip, "%.*s.bai", (int)(al - 4), argv[1]); if (access(ip, R_OK) == 0) have = 1; }
+        if (!have) { fflush(vcf); fflush(out); fprintf(stderr, "\nCan't load index for %s..\n\n", argv[1]); exit(EXIT_FAILURE); }
+    }
     fasta_t fa;
     if (load_fasta(argv[2], &fa) < 0) { fprintf(stderr, "Could not load faidx: %s\n", argv[2]); return 1; }   /* :1042-1046 */
     FILE *cfg = fopen(argv[3], "r");
