@@ -4,7 +4,7 @@
 //
 // Shape: persistent blocks (exactly the resident ones) pull 32 KiB tiles of the body in order (atomic ticket).  A block
 //   1. asks the tile it is likely to draw next into L2 and stages its own tile (+ an overhang for the line that runs past
-//      the end) in shared memory with asynchronous 16-byte copies;
+//      the end) in shared memory with ONE bulk asynchronous copy (cp.async.bulk = TMA, completion on an mbarrier; SASS: UBLKCP);
 //   2. finds newlines byte-parallel: SWAR zero-byte test per 32-bit word, 16-bit mask per 16-byte
 //      chunk, block-wide exclusive scan of the per-thread popcounts -> ordered line starts;
 //   3. publishes its line count at once; warp 0 then finds the end of the tile's last line and learns the global index of
@@ -781,6 +781,64 @@ __device__ __forceinline__ uint32_t long_fields(const uint8_t *L, uint32_t seq_o
     return bad;
 }
 
+// Decoupled look-back (one warp): lines in all tiles before `tile`.  Every tile publishes its own line count at once (ST_AGG) and its
+// inclusive prefix when it knows it (ST_INC).  The frontier of known inclusive prefixes moves one window per L2 round trip, so the
+// window is wide: the warp inspects 256 predecessors per hop, all loads of a hop in flight.  Publishes this tile's inclusive prefix.
+__device__ __forceinline__ unsigned long long tile_lookback(unsigned long long *__restrict__ tile_state, size_t tile, uint32_t n_here, int lane)
+{
+    unsigned long long excl = 0;
+    volatile unsigned long long *ts = tile_state;
+    if (tile != 0) {
+        long long j = (long long)tile - 1;
+        for (;;) {
+            const long long hi = j - 8 * lane;                     // this lane looks at tiles hi, hi-1, .. hi-7
+            unsigned long long v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = 2ull << 62; if (hi - k >= 0) v[k] = ts[hi - k]; }     // before tile 0: inclusive prefix 0
+            unsigned long long sum = 0; bool has_inc = false;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (has_inc) continue;
+                while ((v[k] & ST_MASK) == 0) v[k] = ts[hi - k];                      // not published yet
+                sum += v[k] & ~ST_MASK;
+                has_inc = (v[k] & ST_MASK) == ST_INC;
+            }
+            const unsigned inc = __ballot_sync(0xffffffffu, has_inc);
+            const int first = inc ? __ffs(inc) - 1 : 31;           // nearest lane that met an inclusive prefix
+            unsigned long long c = lane <= first ? sum : 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            excl += c;
+            if (inc) break;
+            j -= 256;
+        }
+        if (lane == 0) atomicExch(&tile_state[tile], ST_INC | (excl + n_here));
+    }
+    return excl;
+}
+
+// ---- bulk asynchronous copy (TMA, 1-D) of a tile into shared memory, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_tile(void *dst_smem, const void *src_global, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                       // earlier generic-proxy accesses to the buffer are ordered before the copy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 __global__ void __launch_bounds__(THREADS)
 parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamRec *__restrict__ recs, size_t rec_cap,
              unsigned long long *__restrict__ tile_state, unsigned int *__restrict__ ticket,
@@ -799,11 +857,13 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
     __shared__ unsigned long long s_last_end;
     __shared__ int4 s_wkey[THREADS / 32];
     __shared__ unsigned int s_nexc;
+    __shared__ __align__(8) unsigned long long s_mbar;          // completion of the tile's bulk copy
 
     const size_t n_tiles = (n + TILE - 1) / TILE;
     const int tid_ = threadIdx.x, lane = tid_ & 31, wid = tid_ >> 5;
     int tid_cache = -1;
-    if (tid_ == 0) s_nexc = 0;
+    uint32_t mbar_phase = 0;
+    if (tid_ == 0) { s_nexc = 0; mbar_init(&s_mbar, 1); }
 
     for (;;) {
         __syncthreads();
@@ -822,14 +882,11 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 if (a < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(body + a));
             }
         }
-        // 1. stage: asynchronous 16-byte copies, all in flight at once (no registers in between)
+        // 1. stage: ONE bulk asynchronous copy (TMA) of the tile and its overhang, issued by one thread; everybody waits on the mbarrier
         if (T0 + TILE + OVERHANG <= n && ((uintptr_t)body & 15u) == 0) {
-            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(text);
-#pragma unroll 6
-            for (uint32_t o = (uint32_t)tid_ * 16; o < (uint32_t)(TILE + OVERHANG); o += THREADS * 16)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + o), "l"(body + T0 + o) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (tid_ == 0) bulk_load_tile(text, body + T0, (uint32_t)(TILE + OVERHANG), &s_mbar);
+            mbar_wait(&s_mbar, mbar_phase);
+            mbar_phase ^= 1u;
         } else {
             for (size_t o = (size_t)tid_ * 16; T0 + o < stage_end; o += THREADS * 16) {
                 if (T0 + o + 16 <= n && ((uintptr_t)body & 15u) == 0) *reinterpret_cast<uint4 *>(text + o) = *reinterpret_cast<const uint4 *>(body + T0 + o);
@@ -889,37 +946,9 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         if (tid_ == 0) atomicExch(&tile_state[tile], (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)n_here);
         if (n_here > MAX_LINES) {                                      // > 2048 lines in 32 KiB cannot be SAM
             if (tid_ == 0 && atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = T0;
-            // 3b. decoupled look-back for the global index of this tile's first line.  The frontier of known inclusive
-            //     prefixes moves one window per L2 round trip, so the window is wide: warp 0 inspects 256 predecessors per hop.
+            // 3b. the global index of this tile's first line (warp 0)
             if (wid == 0) {
-                unsigned long long excl = 0;
-                volatile unsigned long long *ts = tile_state;
-                if (tile != 0) {
-                    long long j = (long long)tile - 1;
-                    for (;;) {
-                        const long long hi = j - 8 * lane;                     // this lane looks at tiles hi, hi-1, .. hi-7
-                        unsigned long long v[8];
-    #pragma unroll
-                        for (int k = 0; k < 8; k++) { v[k] = 2ull << 62; if (hi - k >= 0) v[k] = ts[hi - k]; }     // before tile 0: inclusive prefix 0
-                        unsigned long long sum = 0; bool has_inc = false;
-    #pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            if (has_inc) continue;
-                            while ((v[k] & ST_MASK) == 0) v[k] = ts[hi - k];                      // not published yet
-                            sum += v[k] & ~ST_MASK;
-                            has_inc = (v[k] & ST_MASK) == ST_INC;
-                        }
-                        const unsigned inc = __ballot_sync(0xffffffffu, has_inc);
-                        const int first = inc ? __ffs(inc) - 1 : 31;           // nearest lane that met an inclusive prefix
-                        unsigned long long c = lane <= first ? sum : 0ull;
-    #pragma unroll
-                        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                        excl += c;
-                        if (inc) break;
-                        j -= 256;
-                    }
-                    if (lane == 0) atomicExch(&tile_state[tile], ST_INC | (excl + n_here));
-                }
+                const unsigned long long excl = tile_lookback(tile_state, tile, n_here, lane);
                 if (lane == 0) { s_base = excl; if (tile == n_tiles - 1) *n_lines_out = excl + n_here; }
             }
             __syncthreads();
@@ -950,37 +979,9 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (lane == 0) s_last_end = e > n ? n : e;
         }
         __syncthreads();
-        // 3b. decoupled look-back for the global index of this tile's first line.  The frontier of known inclusive
-        //     prefixes moves one window per L2 round trip, so the window is wide: warp 0 inspects 256 predecessors per hop.
+        // 3b. the global index of this tile's first line (warp 0, while the other warps parse)
         if (wid == 0) {
-            unsigned long long excl = 0;
-            volatile unsigned long long *ts = tile_state;
-            if (tile != 0) {
-                long long j = (long long)tile - 1;
-                for (;;) {
-                    const long long hi = j - 8 * lane;                     // this lane looks at tiles hi, hi-1, .. hi-7
-                    unsigned long long v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) { v[k] = 2ull << 62; if (hi - k >= 0) v[k] = ts[hi - k]; }     // before tile 0: inclusive prefix 0
-                    unsigned long long sum = 0; bool has_inc = false;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        if (has_inc) continue;
-                        while ((v[k] & ST_MASK) == 0) v[k] = ts[hi - k];                      // not published yet
-                        sum += v[k] & ~ST_MASK;
-                        has_inc = (v[k] & ST_MASK) == ST_INC;
-                    }
-                    const unsigned inc = __ballot_sync(0xffffffffu, has_inc);
-                    const int first = inc ? __ffs(inc) - 1 : 31;           // nearest lane that met an inclusive prefix
-                    unsigned long long c = lane <= first ? sum : 0ull;
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                    excl += c;
-                    if (inc) break;
-                    j -= 256;
-                }
-                if (lane == 0) atomicExch(&tile_state[tile], ST_INC | (excl + n_here));
-            }
+            const unsigned long long excl = tile_lookback(tile_state, tile, n_here, lane);
             if (lane == 0) { s_base = excl; if (tile == n_tiles - 1) *n_lines_out = excl + n_here; }
         }
         // 4a. heads.  The threads of warps 1..3 take one line each; the lanes of a warp stay together (parse_head_conv).  A line that

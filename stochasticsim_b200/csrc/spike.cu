@@ -136,43 +136,62 @@ __device__ bool same_qname(const uint8_t *sam, const SamRec &a, const SamRec &b)
     return true;
 }
 
-__global__ void mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
-                             const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ k_end,
-                             const uint32_t *__restrict__ k_hash32, size_t K, uint32_t *__restrict__ nxt, uint32_t *__restrict__ prv,
-                             uint8_t *__restrict__ cplx)
+constexpr int MATES_TPB = 256, MATES_TILE = 1280;          // reads per block; hashes and start keys staged per block (their own reads + 1024 ahead)
+
+__global__ void __launch_bounds__(MATES_TPB)
+mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
+             const unsigned long long *__restrict__ k_start, const unsigned long long *__restrict__ k_end,
+             const uint32_t *__restrict__ k_hash32, size_t K, uint32_t *__restrict__ nxt, uint32_t *__restrict__ prv,
+             uint8_t *__restrict__ cplx)
 {
-    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // The reads that start inside a read's span follow it directly (start order): at 100x a hundred or so.  The block stages the
+    // 32-bit hash folds and the start keys of its own reads and of the 1024 behind them in shared memory; only a read whose span
+    // reaches beyond that (very deep input) goes back to global memory for the rest.
+    __shared__ uint32_t s_hash[MATES_TILE];
+    __shared__ unsigned long long s_start[MATES_TILE];
+    const size_t b0 = (size_t)blockIdx.x * MATES_TPB;
+    for (int i = threadIdx.x; i < MATES_TILE; i += MATES_TPB) {
+        const size_t g = b0 + i;
+        s_hash[i] = g < K ? k_hash32[g] : 0u;
+        s_start[i] = g < K ? k_start[g] : ~0ull;
+    }
+    __syncthreads();
+    const size_t o = b0 + threadIdx.x;
     if (o >= K) return;
     const unsigned long long lim = k_end[o];       // same tid, pos < end  <=>  start key < end key
-    const uint32_t h = k_hash32[o];                // candidates by a 32-bit fold of the QNAME hash; same_qname() decides
+    const uint32_t h = s_hash[threadIdx.x];        // candidates by a 32-bit fold of the QNAME hash; same_qname() decides
     uint32_t first = NO_MATE; bool more = false;
-    // reads that start inside this read's span: [o + 1, hi).  The bound is found once (galloping, then bisection), so the
-    // scan itself only touches the hashes.
-    size_t hi;
-    {
-        size_t step = 64, lo = o + 1;
-        hi = lo;
-        while (hi < K && k_start[hi] < lim) { lo = hi + 1; hi += step; step <<= 1; }
-        if (hi > K) hi = K;
-        while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (k_start[mid] < lim) lo = mid + 1; else hi = mid; }
-    }
-    for (size_t b0 = o + 1; b0 < hi; b0 += 4) {
-      // four candidates per step: the loads do not depend on each other
-      uint32_t hb[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) hb[u] = (b0 + u < hi) ? k_hash32[b0 + u] : ~h;
-      if (hb[0] != h && hb[1] != h && hb[2] != h && hb[3] != h) continue;
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const size_t b = b0 + u;
-        if (hb[u] != h || b >= hi) continue;
-        if (!same_qname(sam, recs[k_rec[o]], recs[k_rec[b]])) continue;
+    auto candidate = [&](size_t b) {
+        if (!same_qname(sam, recs[k_rec[o]], recs[k_rec[b]])) return;
         if (first == NO_MATE) { first = (uint32_t)b; prv[b] = (uint32_t)o; }    // injective: see DESIGN.md (mate links)
         else {
             // three or more same-name reads overlap: every member takes the exact brute-force path
             more = true; cplx[o] = 1; cplx[first] = 1; cplx[b] = 1;
         }
-      }
+    };
+    // inside the tile: [threadIdx.x + 1, t_hi)
+    int lo = threadIdx.x + 1, hi = MATES_TILE;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_start[mid] < lim) lo = mid + 1; else hi = mid; }
+    const int t_hi = lo;
+    for (int t = threadIdx.x + 1; t < t_hi; t++) if (s_hash[t] == h) candidate(b0 + t);
+    if (t_hi == MATES_TILE && b0 + MATES_TILE < K) {
+        // the span reaches beyond the staged reads: the rest from global memory (galloping bound, then four hashes per step)
+        size_t g_hi;
+        {
+            size_t step = 64, l = b0 + MATES_TILE;
+            g_hi = l;
+            while (g_hi < K && k_start[g_hi] < lim) { l = g_hi + 1; g_hi += step; step <<= 1; }
+            if (g_hi > K) g_hi = K;
+            while (l < g_hi) { const size_t mid = (l + g_hi) >> 1; if (k_start[mid] < lim) l = mid + 1; else g_hi = mid; }
+        }
+        for (size_t c0 = b0 + MATES_TILE; c0 < g_hi; c0 += 4) {
+            uint32_t hb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) hb[u] = (c0 + u < g_hi) ? k_hash32[c0 + u] : ~h;
+            if (hb[0] != h && hb[1] != h && hb[2] != h && hb[3] != h) continue;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (hb[u] == h && c0 + u < g_hi) candidate(c0 + u);
+        }
     }
     nxt[o] = first | (more ? MATE_MORE : 0u);
 }

@@ -588,7 +588,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         SPK_CHECK_ARENA(ar);
         SSB_CUDA(ctx, cudaMemsetAsync(prv, 0xff, K * sizeof(uint32_t), s));
         SSB_CUDA(ctx, cudaMemsetAsync(cplx, 0, K, s));
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, mates_kernel, grid_for(K, 128), 128, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash32, K, nxt, prv, cplx);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, mates_kernel, grid_for(K, MATES_TPB), MATES_TPB, 0, s, d_sam, recs, k_rec, k_start, k_end, k_hash32, K, nxt, prv, cplx);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, clipend_kernel, grid_for(K, 256), 256, 0, s, k_end, K, rg, ce);
         if ((rc = scan_max_excl(ar, ctx, ce, pm, K, 0ull))) return rc;
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, newcov_kernel, grid_for(K, 256), 256, 0, s, k_start, ce, pm, K, rg, rflag, newcov);
