@@ -5,7 +5,7 @@
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v $(EXTRA_NVFLAGS)
 LIBDIR    := stochasticsim_b200/lib
 CSRC      := stochasticsim_b200/csrc
 HOST      := stochasticsim_b200/host

@@ -5,8 +5,9 @@
 // Shape: persistent blocks (exactly the resident ones) pull 32 KiB tiles of the body in order (atomic ticket).  A block
 //   1. asks the tile it is likely to draw next into L2 and stages its own tile (+ an overhang for the line that runs past
 //      the end) in shared memory with ONE bulk asynchronous copy (cp.async.bulk = TMA, completion on an mbarrier; SASS: UBLKCP);
-//   2. finds newlines byte-parallel: SWAR zero-byte test per 32-bit word, 16-bit mask per 16-byte
-//      chunk, block-wide exclusive scan of the per-thread popcounts -> ordered line starts;
+//   2. finds newlines byte-parallel: SWAR zero-byte test per 32-bit word; the few chunks that hold one note its position, warp ballots
+//      count them per (iteration, warp) cell and a 64-cell scan orders the line starts (tiles that do not look like SAM -- two newlines
+//      within 16 bytes -- and the ragged last tiles take the general path: 16-bit mask per chunk, block-wide scan of popcounts);
 //   3. publishes its line count at once; warp 0 then finds the end of the tile's last line and learns the global index of
 //      the first one from a decoupled look-back over per-tile line counts (single pass, no separate counting kernel)
 //      WHILE
@@ -27,6 +28,7 @@ constexpr int THREADS   = 128;
 constexpr int MAX_LINES = 2048;                 // a valid SAM line has >= 22 bytes -> <= 1490 per tile
 constexpr int CHUNKS    = TILE / 16;            // 16-byte chunks per tile
 constexpr int CPT       = CHUNKS / THREADS;     // chunks per thread (a multiple of 8)
+static_assert(CPT * (THREADS / 32) == 64, "the one-pass newline search scans 64 (iteration, warp) cells, two per lane");
 constexpr int REFW      = 4096;                 // reference window staged per tile for the base-vs-reference comparison
 constexpr int EXC_BUF   = 1024;                 // exceptional bases of one tile, kept in shared memory until the tile is done
 // shared memory of a block: the staged text, then two regions that change hands inside a tile:
@@ -50,6 +52,7 @@ struct ContigNames {          // device: concatenated names + offsets, for RNAME
     // (it is one of the halo lines in front of this shard's own) and is not kept; n_keep counts the kept lines.
     unsigned long long keep_lo; unsigned long long *n_keep;
     unsigned long long *n_float;      // lines flagged REC_AUX_F
+    unsigned long long *max_end;      // largest end coordinate of a kept line (the output-order sort packs its keys with it)
 };
 
 // applies the shard's lower bound to a parsed record
@@ -839,7 +842,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
     } while (!ok);
 }
 
-__global__ void __launch_bounds__(THREADS)
+#ifndef SSB_PARSE_MINBLOCKS
+#define SSB_PARSE_MINBLOCKS 5      // 5 blocks of 128 threads per SM: 96 registers (a few spills in per-tile code) against 112 and 4 blocks
+#endif
+__global__ void __launch_bounds__(THREADS, SSB_PARSE_MINBLOCKS)
 parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamRec *__restrict__ recs, size_t rec_cap,
              unsigned long long *__restrict__ tile_state, unsigned int *__restrict__ ticket,
              unsigned long long *__restrict__ n_lines_out, SpikeErr *__restrict__ err)
@@ -857,11 +863,13 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
     __shared__ unsigned long long s_last_end;
     __shared__ int4 s_wkey[THREADS / 32];
     __shared__ unsigned int s_nexc;
+    __shared__ unsigned int s_cell[CPT * (THREADS / 32)];            // line starts per (iteration, warp) of the one-pass newline search
     __shared__ __align__(8) unsigned long long s_mbar;          // completion of the tile's bulk copy
 
     const size_t n_tiles = (n + TILE - 1) / TILE;
     const int tid_ = threadIdx.x, lane = tid_ & 31, wid = tid_ >> 5;
     int tid_cache = -1;
+    int end_max = 0;                                                   // largest end of a kept line this thread has seen
     uint32_t mbar_phase = 0;
     if (tid_ == 0) { s_nexc = 0; mbar_init(&s_mbar, 1); }
 
@@ -895,73 +903,136 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
         }
         if (tid_ == 0) s_first = (T0 == 0) ? 1u : (body[T0 - 1] == '\n');
         __syncthreads();
-        // 2. newline masks per 16-byte chunk (chunk c covers tile bytes [16c, 16c+16))
-        const size_t tile_bytes = (T0 + TILE <= n) ? TILE : n - T0;
-        for (int c = tid_; c < CHUNKS; c += THREADS) {
-            uint32_t m = 0;
-            if ((size_t)c * 16 < tile_bytes) {
-                m = nl_mask16(*reinterpret_cast<const uint4 *>(text + c * 16));
-                size_t rem = tile_bytes - (size_t)c * 16;
-                if (rem < 16) m &= (1u << rem) - 1u;
-            }
-            masks[c] = (uint16_t)m;
-        }
-        __syncthreads();
-        // a line starts after every newline except one sitting on the last byte of the tile (or of the body)
-        // thread t owns chunks [CPT t, CPT t + CPT)
-        uint32_t mym[CPT]; uint32_t cnt = 0;
-        {
+        // 2'. the usual tile (full, SAM-like: never two newlines within 16 bytes, a thread meets at most NL_KEEP of them): one pass.  Chunk
+        //     c = 128 it + tid; a chunk with a newline is rare (one in ~20), so only the zero-byte test runs for every chunk and the position
+        //     is worked out where one was found.  Line starts are ordered by chunk: the warp ballots count them per (iteration, warp) cell,
+        //     and a scan over the 64 cells gives every cell its first slot.  Anything else falls through to the general steps 2-3 below.
+        uint32_t n_here = 0, first = s_first;
+        bool lines_done = false;
+        if (T0 + TILE + OVERHANG <= n) {
+            // pass 1, branch free: which of this thread's chunks hold a newline (bit it of `anym`), and its rank among the lanes of the warp
+            // that found one in the same iteration (5 bits each, six to a word)
+            uint32_t anym = 0, rk[3] = {0u, 0u, 0u};
 #pragma unroll
-            for (int q = 0; q < CPT / 8; q++) {
-                const uint4 mm = *reinterpret_cast<const uint4 *>(masks + CPT * tid_ + 8 * q);
-                const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+            for (int it = 0; it < CPT; it++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(text + (it * THREADS + tid_) * 16);
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                uint32_t z = 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++) { mym[8 * q + 2 * k] = w4[k] & 0xFFFFu; mym[8 * q + 2 * k + 1] = w4[k] >> 16; }
-            }
-            if (tid_ == THREADS - 1) mym[CPT - 1] &= 0x7FFFu;        // newline on the last byte of a full tile: next tile's line
-            // drop a newline that is the very last byte of the body: nothing starts after it
-            if (n - T0 <= (size_t)TILE) {
-#pragma unroll
-                for (int k = 0; k < CPT; k++) {
-                    const size_t cb = T0 + (size_t)(CPT * tid_ + k) * 16;
-                    if (n > cb && n - cb <= 16) mym[k] &= ~(1u << (n - cb - 1));
+                for (int j = 0; j < 4; j++) {
+                    uint32_t zj = ~((((w4[j] ^ 0x0A0A0A0Au) & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w4[j]) & 0x80808080u;      // 0x80 per '\n'
+                    if (it == CPT - 1 && j == 3 && tid_ == THREADS - 1) zj &= 0x00ffffffu;     // newline on the last byte of the tile: the next tile's line
+                    z |= zj;
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < CPT; k++) cnt += __popc(mym[k]);
-        }
-        // block exclusive scan of cnt
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        if (lane == 31) s_warp_tot[wid] = incl;
-        __syncthreads();
-        uint32_t warp_base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < THREADS / 32; w++) { uint32_t t = s_warp_tot[w]; if (w < wid) warp_base += t; total += t; }
-        const uint32_t first = s_first;
-        uint32_t my_base = first + warp_base + incl - cnt;
-        const uint32_t n_here = first + total;
-        // 3a. this tile's line count is published at once; the look-back itself (3b) runs on warp 0 while the other warps parse
-        if (tid_ == 0) atomicExch(&tile_state[tile], (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)n_here);
-        if (n_here > MAX_LINES) {                                      // > 2048 lines in 32 KiB cannot be SAM
-            if (tid_ == 0 && atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = T0;
-            // 3b. the global index of this tile's first line (warp 0)
-            if (wid == 0) {
-                const unsigned long long excl = tile_lookback(tile_state, tile, n_here, lane);
-                if (lane == 0) { s_base = excl; if (tile == n_tiles - 1) *n_lines_out = excl + n_here; }
+                const bool any = z != 0u;
+                const unsigned bal = __ballot_sync(0xffffffffu, any);
+                anym |= (any ? 1u : 0u) << it;
+                rk[it / 6] |= (uint32_t)__popc(bal & ((1u << lane) - 1u)) << (5 * (it % 6));
+                if (lane == 0) s_cell[it * (THREADS / 32) + wid] = (uint32_t)__popc(bal);
             }
             __syncthreads();
-            continue;
-        }
-        if (tid_ == 0 && first) starts[0] = 0;
-        if (cnt) {
+            // every warp scans the 64 cells for itself (two per lane)
+            const uint32_t c0 = s_cell[2 * lane], c1 = s_cell[2 * lane + 1];
+            uint32_t incl = c0 + c1;
 #pragma unroll
-            for (int k = 0; k < CPT; k++) {
-                uint32_t m = mym[k];
-                while (m) {
-                    int b = __ffs(m) - 1; m &= m - 1;
-                    starts[my_base++] = (uint16_t)((CPT * tid_ + k) * 16 + b + 1);
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t ex0 = incl - c0 - c1;                        // first slot of cell 2 lane; cell 2 lane + 1 starts c0 later
+            bool odd = first + total > (uint32_t)MAX_LINES;             // (block uniform)
+            // pass 2, only where a newline was seen (about one chunk in twenty): its position; two in one chunk make the tile odd
+            const unsigned act = __ballot_sync(0xffffffffu, anym != 0u && !odd);
+            for (unsigned left = act; left;) {                          // (the shuffles need every lane: warp uniform loop over the lanes' turns)
+                const bool mine = anym != 0u && !odd;
+                const int it = mine ? __ffs(anym) - 1 : 0;
+                const uint32_t cell = (uint32_t)it * (THREADS / 32) + wid;
+                const uint32_t pa = __shfl_sync(0xffffffffu, ex0, cell >> 1), pb = __shfl_sync(0xffffffffu, c0, cell >> 1);
+                if (mine) {
+                    anym &= anym - 1u;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(text + (it * THREADS + tid_) * 16);
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) m |= (((~((((w4[j] ^ 0x0A0A0A0Au) & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w4[j]) & 0x80808080u) * 0x00204081u) >> 28) << (4 * j);
+                    if (it == CPT - 1 && tid_ == THREADS - 1) m &= 0x7fffu;
+                    if (m & (m - 1u)) odd = true;
+                    else starts[first + pa + ((cell & 1u) ? pb : 0u) + (((it < 6 ? rk[0] : it < 12 ? rk[1] : rk[2]) >> (5 * (it < 6 ? it : it < 12 ? it - 6 : it - 12))) & 31u)] = (uint16_t)((it * THREADS + tid_) * 16 + __ffs(m));
+                }
+                left = __ballot_sync(0xffffffffu, anym != 0u && !odd);
+            }
+            if (!__syncthreads_or(odd)) {
+                n_here = first + total;
+                if (tid_ == 0) { atomicExch(&tile_state[tile], (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)n_here); if (first) starts[0] = 0; }
+                lines_done = true;
+            }
+        }
+        if (!lines_done) {
+            // 2. newline masks per 16-byte chunk (chunk c covers tile bytes [16c, 16c+16))
+            const size_t tile_bytes = (T0 + TILE <= n) ? TILE : n - T0;
+            for (int c = tid_; c < CHUNKS; c += THREADS) {
+                uint32_t m = 0;
+                if ((size_t)c * 16 < tile_bytes) {
+                    m = nl_mask16(*reinterpret_cast<const uint4 *>(text + c * 16));
+                    size_t rem = tile_bytes - (size_t)c * 16;
+                    if (rem < 16) m &= (1u << rem) - 1u;
+                }
+                masks[c] = (uint16_t)m;
+            }
+            __syncthreads();
+            // a line starts after every newline except one sitting on the last byte of the tile (or of the body)
+            // thread t owns chunks [CPT t, CPT t + CPT)
+            uint32_t mym[CPT]; uint32_t cnt = 0;
+            {
+#pragma unroll
+                for (int q = 0; q < CPT / 8; q++) {
+                    const uint4 mm = *reinterpret_cast<const uint4 *>(masks + CPT * tid_ + 8 * q);
+                    const uint32_t w4[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { mym[8 * q + 2 * k] = w4[k] & 0xFFFFu; mym[8 * q + 2 * k + 1] = w4[k] >> 16; }
+                }
+                if (tid_ == THREADS - 1) mym[CPT - 1] &= 0x7FFFu;        // newline on the last byte of a full tile: next tile's line
+                // drop a newline that is the very last byte of the body: nothing starts after it
+                if (n - T0 <= (size_t)TILE) {
+#pragma unroll
+                    for (int k = 0; k < CPT; k++) {
+                        const size_t cb = T0 + (size_t)(CPT * tid_ + k) * 16;
+                        if (n > cb && n - cb <= 16) mym[k] &= ~(1u << (n - cb - 1));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < CPT; k++) cnt += __popc(mym[k]);
+            }
+            // block exclusive scan of cnt
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            if (lane == 31) s_warp_tot[wid] = incl;
+            __syncthreads();
+            uint32_t warp_base = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < THREADS / 32; w++) { uint32_t t = s_warp_tot[w]; if (w < wid) warp_base += t; total += t; }
+            uint32_t my_base = first + warp_base + incl - cnt;
+            n_here = first + total;
+            // 3a. this tile's line count is published at once; the look-back itself (3b) runs on warp 0 while the other warps parse
+            if (tid_ == 0) atomicExch(&tile_state[tile], (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)n_here);
+            if (n_here > MAX_LINES) {                                      // > 2048 lines in 32 KiB cannot be SAM
+                if (tid_ == 0 && atomicCAS(&err->code, 0, SSB_E_FORMAT) == 0) err->where = T0;
+                // 3b. the global index of this tile's first line (warp 0)
+                if (wid == 0) {
+                    const unsigned long long excl = tile_lookback(tile_state, tile, n_here, lane);
+                    if (lane == 0) { s_base = excl; if (tile == n_tiles - 1) *n_lines_out = excl + n_here; }
+                }
+                __syncthreads();
+                continue;
+            }
+            if (tid_ == 0 && first) starts[0] = 0;
+            if (cnt) {
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    uint32_t m = mym[k];
+                    while (m) {
+                        int b = __ffs(m) - 1; m &= m - 1;
+                        starts[my_base++] = (uint16_t)((CPT * tid_ + k) * 16 + b + 1);
+                    }
                 }
             }
         }
@@ -1024,7 +1095,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             else rc2 = parse_line(cur, s, e, names, tid_cache, r2);
             if (rc2) { if (atomicCAS(&err->code, 0, rc2) == 0) err->where = s; memset(&r2, 0, sizeof r2); r2.line_off = s; r2.tid = -1; }
             shard_keep(r2, names);
-            if (r2.bits & REC_KEEP) atomicAdd(names.n_keep, 1ull);
+            if (r2.bits & REC_KEEP) { atomicAdd(names.n_keep, 1ull); if (r2.end > end_max) end_max = r2.end; }
             if (r2.bits & REC_AUX_F) atomicAdd(names.n_float, 1ull);
             const unsigned long long g2 = gbase + i;
             if (g2 < rec_cap) recs[g2] = r2;
@@ -1074,6 +1145,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             }
             if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = ls; memset(&r, 0, sizeof r); r.line_off = ls; r.tid = -1; }
             shard_keep(r, names);
+            if ((r.bits & REC_KEEP) && r.end > end_max) end_max = r.end;
             if (gi < rec_cap) recs[gi] = r;
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = ls;
         }
@@ -1098,6 +1170,10 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
                 if (lane == 0) s_nexc = 0;
             }
         }
+    }
+    {   // one atomic per warp and kernel
+        const int em = __reduce_max_sync(0xffffffffu, end_max);
+        if (lane == 0 && em > 0) atomicMax(names.max_end, (unsigned long long)em);
     }
 }
 

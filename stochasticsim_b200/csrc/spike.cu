@@ -72,12 +72,15 @@ __global__ void flags_kernel(const SamRec *__restrict__ recs, size_t n, uint32_t
     pkey[i] = (bits & REC_PUSHED) ? (((unsigned long long)(uint32_t)(recs[i].tid + 1) << 32) | (uint32_t)recs[i].pos) : 0ull;
 }
 
+// per output line: where it comes from (one 16-byte load in the emit kernel instead of a chain of dependent loads)
+struct __align__(16) EmitDesc { unsigned long long src_off; uint32_t len; uint32_t add_nl; };
+
 struct MaxOp { template <typename T> __device__ __forceinline__ T operator()(const T &a, const T &b) const { return a > b ? a : b; } };
 
 __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ kord,
                                const unsigned long long *__restrict__ pkey, const unsigned long long *__restrict__ pmax,
                                uint32_t *__restrict__ k_rec, unsigned long long *__restrict__ k_start, unsigned long long *__restrict__ k_end,
-                               uint32_t *__restrict__ k_len, unsigned long long *__restrict__ k_off, unsigned long long *__restrict__ k_hash, uint32_t *__restrict__ k_hash32, uint8_t *__restrict__ k_bits,
+                               EmitDesc *__restrict__ k_desc, unsigned long long *__restrict__ k_hash, uint32_t *__restrict__ k_hash32, uint8_t *__restrict__ k_bits,
                                unsigned long long *__restrict__ fold, unsigned int *__restrict__ maxspan, DevErr *err,
                                Range rg, unsigned long long halo_bytes)
 {
@@ -99,8 +102,7 @@ __global__ void compact_kernel(const SamRec *__restrict__ recs, size_t n, const 
             const unsigned long long ks = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.pos, ke = ((unsigned long long)(uint32_t)r.tid << 32) | (uint32_t)r.end;
             k_start[o] = ks;
             k_end[o] = ke;
-            k_len[o] = r.line_len + ((r.bits & REC_NO_NL) ? 1u : 0u);
-            k_off[o] = r.line_off;
+            { EmitDesc d; d.src_off = r.line_off; d.len = r.line_len; d.add_nl = (r.bits & REC_NO_NL) ? 1u : 0u; k_desc[o] = d; }   // a body without a final newline gets one
             k_hash[o] = r.qhash; k_hash32[o] = (uint32_t)r.qhash ^ (uint32_t)(r.qhash >> 32); k_bits[o] = r.bits;
             span = clip_e(ke, rg) - clip_s(ks, rg);            // the part of the read inside the shard's range
         }
@@ -136,7 +138,8 @@ __device__ bool same_qname(const uint8_t *sam, const SamRec &a, const SamRec &b)
     return true;
 }
 
-constexpr int MATES_TPB = 256, MATES_TILE = 1280;          // reads per block; hashes and start keys staged per block (their own reads + 1024 ahead)
+constexpr int MATES_TPB = 512, MATES_TILE = 1024, MATES_SLOTS = 4096;     // reads per block; its own reads + 512 ahead are staged and hashed per block
+constexpr uint32_t MATES_NIL = 0xffffffffu;
 
 __global__ void __launch_bounds__(MATES_TPB)
 mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, const uint32_t *__restrict__ k_rec,
@@ -145,15 +148,22 @@ mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, c
              uint8_t *__restrict__ cplx)
 {
     // The reads that start inside a read's span follow it directly (start order): at 100x a hundred or so.  The block stages the
-    // 32-bit hash folds and the start keys of its own reads and of the 1024 behind them in shared memory; only a read whose span
-    // reaches beyond that (very deep input) goes back to global memory for the rest.
+    // 32-bit hash folds and the start keys of its own reads and of the 512 behind them, and chains them into a small hash table
+    // (push-front with an atomic exchange): a read then meets only the few entries of its own bucket instead of every read under its
+    // span.  Only a read whose span reaches beyond the staged reads (very deep input) goes back to global memory for the rest.
     __shared__ uint32_t s_hash[MATES_TILE];
     __shared__ unsigned long long s_start[MATES_TILE];
+    __shared__ uint32_t s_head[MATES_SLOTS];
+    __shared__ uint16_t s_next[MATES_TILE];
     const size_t b0 = (size_t)blockIdx.x * MATES_TPB;
+    for (int i = threadIdx.x; i < MATES_SLOTS; i += MATES_TPB) s_head[i] = MATES_NIL;
+    __syncthreads();
     for (int i = threadIdx.x; i < MATES_TILE; i += MATES_TPB) {
         const size_t g = b0 + i;
-        s_hash[i] = g < K ? k_hash32[g] : 0u;
+        const uint32_t hh = g < K ? k_hash32[g] : 0u;
+        s_hash[i] = hh;
         s_start[i] = g < K ? k_start[g] : ~0ull;
+        if (g < K) s_next[i] = (uint16_t)atomicExch(&s_head[(hh * 0x9E3779B1u) >> 20], (uint32_t)i);       // NIL -> 0xffff
     }
     __syncthreads();
     const size_t o = b0 + threadIdx.x;
@@ -161,20 +171,18 @@ mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, c
     const unsigned long long lim = k_end[o];       // same tid, pos < end  <=>  start key < end key
     const uint32_t h = s_hash[threadIdx.x];        // candidates by a 32-bit fold of the QNAME hash; same_qname() decides
     uint32_t first = NO_MATE; bool more = false;
-    auto candidate = [&](size_t b) {
+    auto candidate = [&](size_t b) {               // (the bucket is met in no particular order: `first` is the lowest so far)
         if (!same_qname(sam, recs[k_rec[o]], recs[k_rec[b]])) return;
-        if (first == NO_MATE) { first = (uint32_t)b; prv[b] = (uint32_t)o; }    // injective: see DESIGN.md (mate links)
+        if (first == NO_MATE) first = (uint32_t)b;
         else {
             // three or more same-name reads overlap: every member takes the exact brute-force path
             more = true; cplx[o] = 1; cplx[first] = 1; cplx[b] = 1;
+            if ((uint32_t)b < first) first = (uint32_t)b;
         }
     };
-    // inside the tile: [threadIdx.x + 1, t_hi)
-    int lo = threadIdx.x + 1, hi = MATES_TILE;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_start[mid] < lim) lo = mid + 1; else hi = mid; }
-    const int t_hi = lo;
-    for (int t = threadIdx.x + 1; t < t_hi; t++) if (s_hash[t] == h) candidate(b0 + t);
-    if (t_hi == MATES_TILE && b0 + MATES_TILE < K) {
+    for (uint32_t t = s_head[(h * 0x9E3779B1u) >> 20]; t < (uint32_t)MATES_TILE; t = s_next[t])
+        if (t > threadIdx.x && s_hash[t] == h && s_start[t] < lim) candidate(b0 + t);
+    if (s_start[MATES_TILE - 1] < lim && b0 + MATES_TILE < K) {
         // the span reaches beyond the staged reads: the rest from global memory (galloping bound, then four hashes per step)
         size_t g_hi;
         {
@@ -193,6 +201,7 @@ mates_kernel(const uint8_t *__restrict__ sam, const SamRec *__restrict__ recs, c
             for (int u = 0; u < 4; u++) if (hb[u] == h && c0 + u < g_hi) candidate(c0 + u);
         }
     }
+    if (first != NO_MATE) prv[first] = (uint32_t)o;                         // injective: see DESIGN.md (mate links)
     nxt[o] = first | (more ? MATE_MORE : 0u);
 }
 
@@ -278,21 +287,16 @@ __global__ void cls_kernel(const CovRun *__restrict__ runs, size_t R, int64_t n_
 // ------------------------------------------------------------------------------------------
 __global__ void iota_kernel(uint32_t *p, size_t n) { size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = (uint32_t)i; }
 
-// per output line: where it comes from (one 16-byte load in the emit kernel instead of a chain of dependent loads)
-struct __align__(16) EmitDesc { unsigned long long src_off; uint32_t len; uint32_t add_nl; };
-
-__global__ void outlen_kernel(const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ s_end, const uint32_t *__restrict__ k_len, const unsigned long long *__restrict__ k_off,
-                              const uint8_t *__restrict__ k_bits, size_t K, Range rg, unsigned long long *__restrict__ len, EmitDesc *__restrict__ desc,
-                              unsigned long long *__restrict__ n_owned)
+__global__ void outlen_kernel(const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ s_end, const EmitDesc *__restrict__ k_desc,
+                              size_t K, Range rg, unsigned long long *__restrict__ len, EmitDesc *__restrict__ desc, unsigned long long *__restrict__ n_owned)
 {
     size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool mine = false;
     if (o < K) {
-        const uint32_t ord = perm[o];
         mine = owns_last(s_end[o], rg);                 // a read whose last base lies beyond the range is written by the next shard
-        const uint32_t kl = k_len[ord]; const uint32_t nonl = (k_bits[ord] & REC_NO_NL) ? 1u : 0u;       // kl counts the newline the line will get
-        EmitDesc d; d.src_off = k_off[ord]; d.len = mine ? kl - nonl : 0u; d.add_nl = mine ? nonl : 0u;
-        len[o] = mine ? kl : 0u;
+        EmitDesc d = k_desc[perm[o]];                   // (one 16-byte gather; the order is nearly the start order)
+        if (!mine) { d.len = 0u; d.add_nl = 0u; }
+        len[o] = (unsigned long long)d.len + d.add_nl;
         desc[o] = d;
     }
     const unsigned m = __ballot_sync(0xffffffffu, mine);

@@ -368,13 +368,41 @@ constexpr int P1_EW_CAP  = 1024;               // staged draw words (32768 draws
 constexpr int P1_CW_CAP  = P1_SEG / 32 + 2;
 constexpr size_t P1_SMEM = (size_t)(P1_EW_CAP + P1_CW_CAP) * sizeof(uint4);
 
-// One step = one window of 32 draws from kr against 32 loci from gr, both shifted into place: the lock step runs to the
-// first draw that does not end its locus (z: that position, one-hot); that locus then takes the next draw of the window
-// that does (y, one-hot).  No branch and no inner loop: a lone walker is one dependency chain, so the step is kept short;
-// a locus that finds no such draw in the window simply stays the current locus of the next step.
+// One step = one window of 32 draws from kr against 32 loci from gr, both shifted into place.  A stage of the step runs the lock step to
+// the first draw that does not end its locus (z, one-hot); that locus then takes the next draw of the window that does (y, one-hot).
+// Every draw that ends nothing delays the loci by one place against the draws (`skew`), so the next stage compares the same window with
+// the locus planes shifted once more: P1_STAGES stages share one set of loads (~19 loci per step instead of ~4; the kernel is bound by
+// integer issue: C2, one B200: 1 stage 19.8 ms, 3: 13.9, 4: 13.0, 5: 12.4, 6: 12.2).  No branch and no inner loop: a lone walker is one dependency chain.  `done`: the draws consumed so far (ones below
+// the cursor), `nonend`: those of them that ended no locus.  A locus that finds no ending draw in the window (y = 0) takes the rest of
+// the window and stays the current locus of the next step; later stages then see a full `done` and change nothing.
+constexpr int P1_STAGES = 6;
+template <int P1_STAGES_T>
 __device__ __forceinline__ int walk_seg(const SegPlanes &P, uint32_t &gr, const uint32_t gto, uint32_t &kr)
 {
-    while (gr < gto) {
+    while (gr + 32u <= gto) {                                             // a full window of loci ahead
+        const uint32_t a = kr & 31u, b = gr & 31u, we = kr >> 5, wc = gr >> 5;
+        if (we + 2u > P.we_n) return (P.kb + kr + 96ull > P.M) ? CHAIN_OVERRUN : CHAIN_COMPLEX;
+        const uint4 ea = P.e[we], eb = P.e[we + 1], ca = P.c[wc], cb = P.c[wc + 1];
+        const uint32_t e0 = __funnelshift_r(ea.x, eb.x, a), e1 = __funnelshift_r(ea.y, eb.y, a), ej = __funnelshift_r(ea.z, eb.z, a);
+        const uint32_t c0 = __funnelshift_r(ca.x, cb.x, b), c1 = __funnelshift_r(ca.y, cb.y, b), cx = __funnelshift_r(ca.z, cb.z, b);
+        uint32_t done = 0u, nonend = 0u, skew = 0u;
+#pragma unroll
+        for (int s = 0; s < P1_STAGES_T; s++) {
+            const uint32_t s0 = c0 << skew, s1 = c1 << skew, sx = cx << skew;      // locus gr + i - skew stands at draw kr + i
+            const uint32_t term = (((e0 ^ s0) | (e1 ^ s1) | sx) & ~ej) | done;     // bit i: draw kr+i ends its locus (or is behind the cursor)
+            const uint32_t z = ~term & (term + 1u);                                // first draw that does not (0: none, the window is used up)
+            const uint32_t m0 = (s0 & z) ? 0xffffffffu : 0u, m1 = (s1 & z) ? 0xffffffffu : 0u, mx = (sx & z) ? 0xffffffffu : 0u;
+            const uint32_t ends = ((e0 ^ m0) | (e1 ^ m1) | mx) & ~ej;              // draws of the window that would end that locus
+            const uint32_t above = ends & ~(z | (z - 1u));                         // ... after the failed one
+            const uint32_t y = above & (0u - above);                               // the first of them (0: none in this window)
+            nonend |= y - z;                                                       // draws [z, y) ended nothing (y = 0: from z to the top)
+            done = y | (y - 1u);                                                   // cursor behind y (y = 0: behind the window)
+            if (s + 1 < P1_STAGES_T) skew = (uint32_t)__popc(nonend);
+        }
+        const uint32_t d = (uint32_t)__popc(done);
+        kr += d; gr += d - (uint32_t)__popc(nonend);
+    }
+    while (gr < gto) {                                                    // the last loci of the stretch: one stage, pairs past the end masked
         const uint32_t a = kr & 31u, b = gr & 31u, we = kr >> 5, wc = gr >> 5;
         if (we + 2u > P.we_n) return (P.kb + kr + 96ull > P.M) ? CHAIN_OVERRUN : CHAIN_COMPLEX;
         const uint4 ea = P.e[we], eb = P.e[we + 1], ca = P.c[wc], cb = P.c[wc + 1];
@@ -396,6 +424,7 @@ __device__ __forceinline__ int walk_seg(const SegPlanes &P, uint32_t &gr, const 
 }
 
 // walk [g, g_to) including the targets inside, counting draws only
+template <int ST>
 __device__ int dry_walk(const ChainArgs &A, const SegPlanes &P, int64_t g, const int64_t g_to, size_t h, unsigned long long &k)
 {
     if (k < P.kb) return CHAIN_COMPLEX;
@@ -403,13 +432,13 @@ __device__ int dry_walk(const ChainArgs &A, const SegPlanes &P, int64_t g, const
     int rc = 0;
     while (h < A.H && A.hits[h].locus_index < g_to) {
         const int64_t gt = A.hits[h].locus_index;
-        if ((rc = walk_seg(P, gr, (uint32_t)(gt - P.gb), kr))) return rc;
+        if ((rc = walk_seg<ST>(P, gr, (uint32_t)(gt - P.gb), kr))) return rc;
         k = P.kb + kr;
         if ((rc = dry_apply(A, h, gt, k))) return rc;
         if (k - P.kb >= ((unsigned long long)P.we_n << 5)) return (k + 96ull > P.M) ? CHAIN_OVERRUN : CHAIN_COMPLEX;
         kr = (uint32_t)(k - P.kb); gr = (uint32_t)(gt + 1 - P.gb); h++;
     }
-    if ((rc = walk_seg(P, gr, (uint32_t)(g_to - P.gb), kr))) return rc;
+    if ((rc = walk_seg<ST>(P, gr, (uint32_t)(g_to - P.gb), kr))) return rc;
     k = P.kb + kr;
     return 0;
 }
@@ -423,6 +452,7 @@ struct BoundaryList { unsigned long long off; uint32_t cnt; uint32_t pad; };
 __device__ __forceinline__ uint32_t isqrt_up(uint32_t x) { uint32_t r = (uint32_t)sqrtf((float)x) + 1u; return r; }
 
 // One block per slice.  kbuf/lobuf: two ping-pong halves of `stride` slots each.
+template <int ST>
 __global__ void __launch_bounds__(P1_THREADS)
 phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, const SliceDesc *__restrict__ slices,
               unsigned long long *__restrict__ kbuf, uint32_t *__restrict__ lobuf, unsigned long long stride,
@@ -488,7 +518,7 @@ phase1_kernel(ChainArgs A, int64_t L, const GroupDesc *__restrict__ groups, cons
         unsigned long long tmin = ~0ull, tmax = 0ull;
         for (uint32_t i = tid; i < alive; i += P1_THREADS) {
             unsigned long long k = kb[cur][i];
-            bad |= dry_walk(A, SP, g, gc, h0, k);
+            bad |= dry_walk<ST>(A, SP, g, gc, h0, k);
             kb[cur][i] = k;
             if (k < tmin) tmin = k;
             if (k > tmax) tmax = k;

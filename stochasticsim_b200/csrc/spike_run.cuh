@@ -35,6 +35,7 @@ struct RunScalars {                 // written by kernels of the main stream, mi
     unsigned long long odd_bloom, draws, pool_used, k_out, k_end;
     unsigned long long n_se, first_strad, halo_lines, miss[2];
     long long carry_t, carry_h;
+    unsigned long long max_end;
 };
 struct RunScalarsA {                // written by kernels of the second stream
     unsigned long long total_out, n_owned;
@@ -80,9 +81,21 @@ __global__ void copy_bytes_kernel(const uint8_t *__restrict__ src, uint8_t *__re
         for (size_t i = done + tid; i < n; i += nt) dst[i] = src[i];
     }
 }
-__global__ void out_total_kernel(const unsigned long long *__restrict__ out_off, const unsigned long long *__restrict__ olen, size_t K, unsigned long long *__restrict__ total)
+__global__ void out_total_kernel(unsigned long long *__restrict__ out_off, const unsigned long long *__restrict__ olen, size_t K, unsigned long long *__restrict__ total)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *total = out_off[K - 1] + olen[K - 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { const unsigned long long t = out_off[K - 1] + olen[K - 1]; *total = t; out_off[K] = t; }
+}
+// Output order = end order: (tid, end) keys packed into 32 bits when the contigs and the largest end of a kept read allow it
+// (one contig of 59 Mb: 26 bits = four radix passes over 4-byte keys instead of five over 8-byte keys)
+__global__ void pack_end_kernel(const unsigned long long *__restrict__ k_end, size_t K, int pos_bits, uint32_t *__restrict__ key32, uint32_t *__restrict__ iota)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < K) { const unsigned long long e = k_end[o]; key32[o] = ((uint32_t)(e >> 32) << pos_bits) | (uint32_t)e; iota[o] = (uint32_t)o; }
+}
+__global__ void unpack_end_kernel(const uint32_t *__restrict__ key32, size_t K, int pos_bits, unsigned long long *__restrict__ s_end)
+{
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < K) { const uint32_t u = key32[o]; s_end[o] = ((unsigned long long)(pos_bits >= 32 ? 0u : u >> pos_bits) << 32) | (pos_bits >= 32 ? u : (u & ((1u << pos_bits) - 1u))); }
 }
 __global__ void first_strad_kernel(const unsigned long long *__restrict__ k_end, const uint32_t *__restrict__ k_rec, const SamRec *__restrict__ recs, size_t K, Range rg,
                                    unsigned long long *__restrict__ first_strad)
@@ -202,6 +215,7 @@ struct ShardPlan {
 struct ssb_spike {
     ssb_ctx *ctx;
     int n_contigs;
+    int p1_resident;                          // blocks of phase1_kernel the device holds at once
     char *d_names; uint32_t *d_name_off;
     uint8_t **d_seq_ptrs; int64_t *d_lens;
     std::vector<uint8_t *> d_seqs;
@@ -282,6 +296,7 @@ extern "C" int ssb_spike_create(ssb_ctx *ctx, const ssb_contig *contigs, int n_c
         } else sp->d_seqs.push_back(d);
         ptrs.push_back(d); lens.push_back(d ? contigs[i].len : 0);
     }
+    { int occ = 1; SPK_CREATE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, phase1_kernel<P1_STAGES>, P1_THREADS, P1_SMEM)); sp->p1_resident = occ * ctx->sm_count; }
     SPK_CREATE(cudaMalloc(&sp->d_names, names.size() + 1));
     SPK_CREATE(cudaMalloc(&sp->d_name_off, off.size() * sizeof(uint32_t)));
     SPK_CREATE(cudaMalloc(&sp->d_seq_ptrs, (ptrs.size() + 1) * sizeof(uint8_t *)));
@@ -482,7 +497,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             SSB_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
             if (attempt) { SSB_CUDA(ctx, cudaMemsetAsync(dsc, 0, sizeof(RunScalars), s)); SSB_CUDA(ctx, cudaMemsetAsync(&dsc->first_strad, 0xff, sizeof(unsigned long long), s)); }
             samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_lens,
-                                        no_list ? NULL : exc_list, &dsc->exc_count, exc_cap, rg.lo, &dsc->n_keep, &dsc->n_float};
+                                        no_list ? NULL : exc_list, &dsc->exc_count, exc_cap, rg.lo, &dsc->n_keep, &dsc->n_float, &dsc->max_end};
             int occ = 1;
             SSB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, samparse::parse_kernel, samparse::THREADS, samparse::SMEM_BYTES));
             if (occ < 1) occ = 1;
@@ -505,22 +520,21 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
 
     // ---------------------------------------------------------------- keep / sortedness / compaction
     uint32_t *keep = NULL, *kord = NULL;
-    uint32_t *k_rec = NULL, *k_len = NULL, *nxt = NULL, *prv = NULL; uint8_t *cplx = NULL, *k_bits = NULL;
-    unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL, *k_off = NULL; uint32_t *k_hash32 = NULL;
+    uint32_t *k_rec = NULL, *nxt = NULL, *prv = NULL; EmitDesc *k_desc = NULL; uint8_t *cplx = NULL, *k_bits = NULL;
+    unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL; uint32_t *k_hash32 = NULL;
     unsigned long long *d_halo_lines = &dsc->halo_lines;
     if (N) {
         keep = ar.get<uint32_t>(N); kord = ar.get<uint32_t>(N);
         unsigned long long *pkey = ar.get<unsigned long long>(N), *pmax = ar.get<unsigned long long>(N);
-        k_rec = ar.get<uint32_t>(K); k_len = ar.get<uint32_t>(K); nxt = ar.get<uint32_t>(K);
+        k_rec = ar.get<uint32_t>(K); k_desc = ar.get<EmitDesc>(K); nxt = ar.get<uint32_t>(K);
         k_start = ar.get<unsigned long long>(K); k_end = ar.get<unsigned long long>(K); k_hash = ar.get<unsigned long long>(K); k_hash32 = ar.get<uint32_t>(K); k_bits = ar.get<uint8_t>(K);
-        k_off = ar.get<unsigned long long>(K);
         SPK_CHECK_ARENA(ar);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, flags_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, pkey);
         int rc;
         if ((rc = scan_sum(ar, ctx, keep, kord, N))) return rc;
         if ((rc = scan_max_excl(ar, ctx, pkey, pmax, N, 0ull))) return rc;
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, compact_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, kord, pkey, pmax, k_rec, k_start, k_end, k_len,
-                     k_off, k_hash, k_hash32, k_bits, &dsc->fold, &dsc->maxspan, d_err, rg, (unsigned long long)pl.halo_bytes);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, compact_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, kord, pkey, pmax, k_rec, k_start, k_end, k_desc,
+                     k_hash, k_hash32, k_bits, &dsc->fold, &dsc->maxspan, d_err, rg, (unsigned long long)pl.halo_bytes);
         if (pl.halo_bytes) SSB_LAUNCH(ctx, halo_lines_kernel, 1, 32, 0, s, recs, N, (unsigned long long)pl.halo_bytes, d_halo_lines);
         if (K && (pl.count > 1 || seq)) SSB_LAUNCH(ctx, first_strad_kernel, grid_for(K, 256), 256, 0, s, k_end, k_rec, recs, K, rg, &dsc->first_strad);
     }
@@ -534,18 +548,28 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     if (K) {
         int rc;
         uint32_t *iota = arA.get<uint32_t>(K); perm = arA.get<uint32_t>(K); s_end = arA.get<unsigned long long>(K);
-        unsigned long long *olen = arA.get<unsigned long long>(K); out_off = arA.get<unsigned long long>(K); ord_off = arA.get<unsigned long long>(K);
+        unsigned long long *olen = arA.get<unsigned long long>(K); out_off = arA.get<unsigned long long>(K + 1); ord_off = arA.get<unsigned long long>(K);
         EmitDesc *edesc = arA.get<EmitDesc>(K);
         SPK_CHECK_ARENA(arA);
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, iota_kernel, grid_for(K, 256), 256, 0, sA, iota, K);
-        int tid_bits = 1; while ((1 << tid_bits) < sp->n_contigs + 1 && tid_bits < 31) tid_bits++;
+        int tid_bits = 0; while ((1ll << tid_bits) < (long long)sp->n_contigs && tid_bits < 31) tid_bits++;
+        int pos_bits = 1; while (pos_bits < 32 && (1ull << pos_bits) <= hsc->max_end) pos_bits++;
         size_t bytes = 0;
-        cub::DeviceRadixSort::SortPairs(NULL, bytes, k_end, s_end, iota, perm, K, 0, 32 + tid_bits, sA);
-        void *tmp = arA.get<uint8_t>(bytes); SPK_CHECK_ARENA(arA);
-        SSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, bytes, k_end, s_end, iota, perm, K, 0, 32 + tid_bits, sA));   // stable: ties keep input order
+        if (pos_bits + tid_bits <= 32 && !getenv("SSB_SORT64")) {
+            uint32_t *key32 = arA.get<uint32_t>(K), *skey32 = arA.get<uint32_t>(K);
+            cub::DeviceRadixSort::SortPairs(NULL, bytes, key32, skey32, iota, perm, K, 0, pos_bits + tid_bits, sA);
+            void *tmp = arA.get<uint8_t>(bytes); SPK_CHECK_ARENA(arA);
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, pack_end_kernel, grid_for(K, 256), 256, 0, sA, k_end, K, pos_bits, key32, iota);
+            SSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, bytes, key32, skey32, iota, perm, K, 0, pos_bits + tid_bits, sA));   // stable: ties keep input order
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, unpack_end_kernel, grid_for(K, 256), 256, 0, sA, skey32, K, pos_bits, s_end);
+        } else {
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, iota_kernel, grid_for(K, 256), 256, 0, sA, iota, K);
+            cub::DeviceRadixSort::SortPairs(NULL, bytes, k_end, s_end, iota, perm, K, 0, 32 + tid_bits + 1, sA);
+            void *tmp = arA.get<uint8_t>(bytes); SPK_CHECK_ARENA(arA);
+            SSB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, bytes, k_end, s_end, iota, perm, K, 0, 32 + tid_bits + 1, sA));   // stable: ties keep input order
+        }
         ctx->launches += 8;
         SSB_CUDA(ctx, cudaEventRecord(sp->ev_sort, sA));
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, outlen_kernel, grid_for(K, 256), 256, 0, sA, perm, s_end, k_len, k_off, k_bits, K, rg, olen, edesc, &dscA->n_owned);
+        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, outlen_kernel, grid_for(K, 256), 256, 0, sA, perm, s_end, k_desc, K, rg, olen, edesc, &dscA->n_owned);
         if ((rc = scan_sum(arA, ctx, olen, out_off, K))) return rc;
         SSB_LAUNCH(ctx, out_total_kernel, 1, 32, 0, sA, out_off, olen, K, &dscA->total_out);
         SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, ordoff_kernel, grid_for(K, 256), 256, 0, sA, perm, out_off, K, ord_off);
@@ -745,7 +769,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
 
     // chain state (allocated only when there is something to walk)
     PlpEntry *ent = NULL; uint8_t *hflag = NULL;
-    int P = 1; int64_t Lc = n_walk; int Rg = 1, G = 1; uint32_t wt = 16384;
+    int P = 1; int64_t Lc = n_walk; int Rg = 1, Rg0 = 1, G = 1; bool Rg_fixed = false, wt_fixed = false; uint32_t wt = 16384;
     const double *h_mean = NULL, *h_var = NULL;
     unsigned int *d_flags = &dsc->flags, *n_patches = &dsc->n_patches;
     unsigned long long *d_draws = &dsc->draws, *d_pool_used = &dsc->pool_used;
@@ -907,8 +931,9 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         A.contig_seq = (const uint8_t *const *)sp->d_seq_ptrs; A.err = d_err;
         // groups of Rg consecutive chunks share one start-offset window; the window is cut into slices of ~wt offsets
         Rg = (int)(114688 / Lc); if (Rg < 1) Rg = 1;                        // phase 1 works on groups of ~112 k loci (see spike_chain.cuh)
-        if (const char *e = getenv("SSB_CHAIN_GROUP")) { if (atoi(e) >= 1) Rg = atoi(e); }
-        if (const char *e = getenv("SSB_CHAIN_SLICE")) { if (atoi(e) >= 1) wt = (uint32_t)atoi(e); }
+        Rg0 = Rg;
+        if (const char *e = getenv("SSB_CHAIN_GROUP")) { if (atoi(e) >= 1) { Rg = atoi(e); Rg_fixed = true; } }
+        if (const char *e = getenv("SSB_CHAIN_SLICE")) { if (atoi(e) >= 1) { wt = (uint32_t)atoi(e); wt_fixed = true; } }
         G = (P + Rg - 1) / Rg;
         d_gk = ar.get<unsigned long long>((size_t)G); SPK_CHECK_ARENA(ar);
     }
@@ -939,6 +964,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         std::vector<GroupDesc> h_groups; std::vector<SliceDesc> h_slices;
         unsigned long long woff = 0; double cm_end = 0, cv_end = 0;
         auto make_geometry = [&](double centre, double var0, bool exact_entry) {
+            G = (P + Rg - 1) / Rg;
             h_groups.assign((size_t)G, GroupDesc()); h_slices.clear(); woff = 0;
             double cm = centre, cv = var0;
             for (int q = 0; q < G; q++) {
@@ -957,6 +983,27 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 for (int f = gd.f0; f < gd.f0 + gd.nf; f++) { cm += h_mean[f]; cv += h_var[f]; }
             }
             cm_end = cm; cv_end = cv;
+        };
+        // Every slice is one block, and a block lives as long as its group is long: more slices than the device holds at once means a second
+        // round of blocks behind the first (a shard far down the stream has windows several times as wide as the first one's).  Longer groups
+        // need fewer slices and less work, at the price of a longer lone-walker tail: the shortest group length whose slices are all resident.
+        auto choose_geometry = [&](double centre, double var0, bool exact_entry) {
+            static const int num[] = {2, 3, 4, 6, 8, 12, 16, 24, 32};       // group length in halves of the base length
+            if (!wt_fixed) wt = 16384;
+            for (size_t i = 0; i < sizeof num / sizeof num[0]; i++) {
+                if (!Rg_fixed) { Rg = Rg0 * num[i] / 2; if (Rg < 1) Rg = 1; }
+                make_geometry(centre, var0, exact_entry);
+                if (Rg_fixed || h_slices.size() <= (size_t)sp->p1_resident || Rg >= P) break;
+            }
+            // ... and the narrowest slices that still fit: the same work in more blocks keeps more warps in flight in the long tail of a group
+            // (C2, one B200: 16384 offsets per slice 12.2 ms, 12288 11.7, 10240 10.9)
+            if (!wt_fixed && h_slices.size() <= (size_t)sp->p1_resident) {
+                for (uint32_t w = wt - 1024; w >= 4096; w -= 1024) {
+                    const uint32_t keep = wt;
+                    wt = w; make_geometry(centre, var0, exact_entry);
+                    if (h_slices.size() > (size_t)sp->p1_resident) { wt = keep; make_geometry(centre, var0, exact_entry); break; }
+                }
+            }
         };
 
         int n_retries = 0;
@@ -980,7 +1027,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 break;
             }
             const bool exact_entry = k_in_known;
-            make_geometry(exact_entry ? (double)k_in : c_in, exact_entry ? 0.0 : v_in, exact_entry);
+            choose_geometry(exact_entry ? (double)k_in : c_in, exact_entry ? 0.0 : v_in, exact_entry);
             const size_t n_slices = h_slices.size();
             const unsigned long long pool_cap = woff + (1ull << 20);
             // the stream must cover the top of the last window (and everything a lone walker can reach)
@@ -1011,7 +1058,9 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             SSB_CUDA(ctx, cudaMemsetAsync(d_pool_used, 0, 8, s));
             SSB_CUDA(ctx, cudaMemsetAsync(d_lists, 0, (n_slices + SPARE) * (size_t)Rg * sizeof(BoundaryList), s));
             SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[14], s));
-            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, (int)n_slices, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
+            auto p1k = phase1_kernel<P1_STAGES>;                 // SSB_P1_STAGES: conflicts resolved per walker step (measurement switch)
+            if (const char *e = getenv("SSB_P1_STAGES")) { const int v = atoi(e); p1k = v == 1 ? phase1_kernel<1> : v == 2 ? phase1_kernel<2> : v == 3 ? phase1_kernel<3> : v == 4 ? phase1_kernel<4> : v == 5 ? phase1_kernel<5> : phase1_kernel<6>; }
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, p1k, (int)n_slices, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
                          d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, d_dbg, 0);
             SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[15], s));
             if (d_dbg) {
@@ -1075,7 +1124,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                     SSB_LAUNCH(ctx, copy_words_kernel, 1, 32, 0, s, (const uint32_t *)gd_, (uint32_t *)(d_groups + q), (unsigned int)(sizeof gd / 4));
                     SSB_LAUNCH(ctx, copy_words_kernel, 1, 32, 0, s, (const uint32_t *)sd_, (uint32_t *)(d_slices + n_slices + retry), (unsigned int)(sizeof sd / 4));
                     if ((rc = reset_state())) return rc;
-                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, phase1_kernel, 1, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
+                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, p1k, 1, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
                                  d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, (unsigned long long *)NULL, (int)(n_slices + retry));
                     stats->n_runs += 0;
                     n_retries++;
