@@ -100,50 +100,51 @@ def header_for(name, contig_len):
     return ("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n@PG\tID:gen_synth\tPN:gen_synth\n" % (name, contig_len)).encode()
 
 
-# ---- where to cut ONE input of N contigs into N coordinate shards so that every GPU finishes at the same time.  A shard's cost is its
-# reads (everything but the chain) plus phase 1 of the RNG chain, whose windows widen with the square root of the loci in front of the
-# shard (the rand() offset there is only known to +-4 sigma while the shards work side by side).  Constants: measured on C2 (one contig):
-# 36 ms for everything but phase 1, phase 1 = 6.2 ms + 8.1 ms * (x1^1.5 - x0^1.5) for the contig range [x0, x1).
-COST_BASE, COST_P1_FIXED, COST_P1_GROW = 36.0, 6.2, 8.1
+# ---- where to cut ONE input of N contigs into N coordinate shards so that every GPU finishes at the same time.  Timeline of a shard
+# of length l (in contigs) over the contig range [x0, x1): everything up to the pileup entries (PRE * l), then the output branch (OUT * l:
+# emit + tallies, which needs nothing from the other shards), then -- not before EVERY shard has reached the exchange of expected draw
+# counts, time A = PRE * the longest shard -- phase 1 of the RNG chain, whose windows widen with the square root of the loci in front of
+# the shard (P1_LIN * l + P1_GROW * (x1^1.5 - x0^1.5): the rand() offset there is only known to +-4 sigma while the shards work side by
+# side), then the composition, phase 3 and the patches (POST * l).  Constants: ms per C2 contig, measured on B200.
+PRE, OUT, P1_LIN, P1_GROW, POST = 22.8, 9.0, 8.2, 4.5, 3.3
 
 
-def shard_cost(x0, x1):
-    return COST_BASE * (x1 - x0) + COST_P1_FIXED + COST_P1_GROW * (x1 ** 1.5 - x0 ** 1.5)
+def shard_finish(x0, x1, a_all):
+    ln = x1 - x0
+    return max((PRE + OUT) * ln, a_all) + P1_LIN * ln + P1_GROW * (x1 ** 1.5 - x0 ** 1.5) + POST * ln
 
 
 def balanced_cuts(n_shards, n_contigs, balance=True):
     """Cut positions x_0 = 0 < x_1 < ... < x_N = n_contigs in contig units."""
     if not balance or n_shards == 1:
         return [n_contigs * g / n_shards for g in range(n_shards + 1)]
-    lo_t, hi_t = 0.0, shard_cost(0.0, float(n_contigs))
-    for _ in range(60):                          # bisection on the common cost per shard
-        t = (lo_t + hi_t) / 2
-        x = 0.0
+
+    def cuts_for(t, a_all):
+        x, cuts = 0.0, [0.0]
         for _g in range(n_shards):
             a, b = x, float(n_contigs) + 1.0
-            for _ in range(60):
+            for _ in range(60):                      # the longest shard from x that is done by t
                 m = (a + b) / 2
-                if shard_cost(x, m) < t:
+                if shard_finish(x, m, a_all) <= t:
                     a = m
                 else:
                     b = m
             x = a
-        if x < n_contigs:
-            lo_t = t
-        else:
-            hi_t = t
-    cuts, x = [0.0], 0.0
-    for _g in range(n_shards - 1):
-        a, b = x, float(n_contigs)
-        for _ in range(60):
-            m = (a + b) / 2
-            if shard_cost(x, m) < hi_t:
-                a = m
+            cuts.append(x)
+        return cuts
+
+    a_all, cuts = 0.0, None
+    for _ in range(12):                              # fixed point on the time of the exchange
+        lo_t, hi_t = 0.0, 1e5
+        for _ in range(60):                          # bisection on the common finishing time
+            t = (lo_t + hi_t) / 2
+            if cuts_for(t, a_all)[-1] >= n_contigs:
+                hi_t = t
             else:
-                b = m
-        x = a
-        cuts.append(x)
-    cuts.append(float(n_contigs))
+                lo_t = t
+        cuts = cuts_for(hi_t, a_all)
+        a_all = PRE * max(cuts[i + 1] - cuts[i] for i in range(n_shards))
+    cuts[-1] = float(n_contigs)
     return cuts
 
 
@@ -174,8 +175,11 @@ def run(args, D):
     n_spikes = 10_000
     N = D.world
     names = ["chr19"] if N == 1 else ["chr19.%d" % g for g in range(N)]
-    # ONE input: N contigs of the same generator seed, cut into N coordinate ranges of equal expected cost (SSB_BENCH_BALANCE=0: one contig each).
-    balance = os.environ.get("SSB_BENCH_BALANCE", "0") != "0"      # default: one contig per shard -- phase 1 cannot start before the slowest rank has parsed (the window centres need every earlier shard's expected draws), so equal reads per rank win
+    # ONE input: N contigs of the same generator seed, cut into N coordinate ranges of equal expected finishing time (SSB_BENCH_BALANCE=0: one contig each).
+    # default: one contig per shard.  Cuts for equal finishing time (SSB_BENCH_BALANCE=1: later shards simulate wider windows, so they get fewer reads) were
+    # measured at N=4: 57.4 ms against 57.0 -- the shards meet at three exchanges before phase 1 (loci per shard, the target reduction, the expected
+    # draws), so a shard with fewer reads only waits longer there
+    balance = os.environ.get("SSB_BENCH_BALANCE", "0") != "0"
     cuts = balanced_cuts(N, N, balance)
     HALO = 1024                                               # bases: 150 bp reads with a few indels span < 200
     def to_pos(x):                                            # contig units -> (contig, position)
@@ -325,7 +329,7 @@ def run(args, D):
                                 "ONE coordinate-sorted SAM over %d chr19-sized contigs (C2 per contig: 150bp paired reads at %gx, 10k SBS spike loci each; one seed, one "
                                 ".spike table, one rand() stream), cut by coordinate range, shard g on GPU g" % (N, coverage))
                                + ("" if args.scale == 1.0 else f" (depth scaled x{args.scale})"),
-                   "cuts_in_contigs": [round(c, 4) for c in cuts], "cut_rule": ("equal expected cost per shard (reads + phase 1 of the RNG chain, whose windows widen with the loci in front of the shard)" if balance and N > 1 else "one contig per shard"),
+                   "cuts_in_contigs": [round(c, 4) for c in cuts], "cut_rule": ("equal expected finishing time per shard (a shard further down the stream simulates wider windows of rand() offsets in phase 1, so it gets fewer reads)" if balance and N > 1 else "one contig per shard"),
                    "reads_on_rank0": n_reads, "sam_bytes_on_rank0": n, "covered_loci_on_rank0": stats["numberOfLociCovered"], "spike_seed": SPIKE_SEED,
                    "targets": len(targets), "targets_hit_on_rank0": stats["n_hits"], "l2": "input (%.2f GB) larger than L2, no flush" % (n / 1e9),
                    "collective": "none" if N == 1 else

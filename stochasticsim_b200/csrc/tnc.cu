@@ -28,6 +28,7 @@
 // kernel jump over N blocks count 16-byte chunks (256 per 4 KiB segment).
 #include "common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -46,9 +47,9 @@ struct TncDevState {                          // mirrors ssb_tnc_carry
 };
 static_assert(sizeof(TncDevState) == sizeof(ssb_tnc_carry), "state layout");
 
-__host__ __device__ inline bool is_base(uint8_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+__host__ __device__ inline bool is_base(uint8_t c) { const uint32_t d = (uint32_t)c - 0x41u; return d < 20u && ((0x80045u >> d) & 1u); }   // A C G T = 0x41 + {0, 2, 6, 19}
 // reference index order A<C<G<T (tncCountsProfile.c:14-77)
-__host__ __device__ inline int ref_code(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
+__host__ __device__ inline int ref_code(uint8_t c) { const uint32_t s = ((uint32_t)c >> 1) & 3u; return (int)(s ^ (s >> 1)); }            // (c one of A C G T) bits 2..1: A 0, C 1, T 2, G 3
 
 // ---- scan kernel ------------------------------------------------------------------------------
 // Every thread takes 16 bytes per iteration.  Fast path (all bytes of the chunk and of its 2-byte halo are one of
@@ -131,14 +132,17 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
     const size_t warp_first = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) - lane) * TNC_SUB;
     for (size_t cbase = warp_first; cbase < n_chunks; cbase += stride) {
       unsigned long long nl64 = 0;                                                     // bit 16*sub + i: byte i of sub-chunk `sub` is '\n'
+      // a warp step whose 128 chunks are all whole and have their halo inside the piece runs without the edge tests (INTERIOR)
+      auto warp_step = [&](auto interior_tag) {
+      constexpr bool INTERIOR = decltype(interior_tag)::value;
 #pragma unroll 1
       for (int sub = 0; sub < TNC_SUB; sub++) {
         const size_t chunk = cbase + (size_t)sub * 32 + lane;
-        uint32_t nlmask = 0;
+        uint32_t nlmask = 0; bool nobase = false;
         const size_t p0 = chunk * TNC_BPT;
-        if (chunk < n_chunks) {
+        if (INTERIOR || chunk < n_chunks) {
             uint32_t w[4];
-            if (p0 + TNC_BPT <= n) {
+            if (INTERIOR || p0 + TNC_BPT <= n) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(b + p0);
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
             } else {
@@ -146,11 +150,11 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
                 for (int j = 0; j < 4; j++) w[j] = ld_word(b, n, p0 + 4 * j);
             }
             uint32_t hw;                                                               // the 4 bytes before the chunk
-            if (p0) hw = *reinterpret_cast<const uint32_t *>(b + p0 - 4);
+            if (INTERIOR || p0) hw = *reinterpret_cast<const uint32_t *>(b + p0 - 4);
             else hw = (uint32_t)st.prev[0] << 8 | (uint32_t)st.prev[1] << 16 | (uint32_t)st.prev[2] << 24;
             const uint32_t s0 = symbols(w[0]), s1 = symbols(w[1]), s2 = symbols(w[2]), s3 = symbols(w[3]), sh = symbols(hw);
             const uint32_t bad = not_acgtnl(w[0], s0) | not_acgtnl(w[1], s1) | not_acgtnl(w[2], s2) | not_acgtnl(w[3], s3) | (not_acgtnl(hw, sh) & 0xFFFF0000u);
-            if (bad == 0u && p0 + TNC_BPT <= n) {
+            if (bad == 0u && (INTERIOR || p0 + TNC_BPT <= n)) {
                 // ---- fast path ----
                 atomicAdd(&hist4[pack4(__funnelshift_r(sh, s0, 16))], 1u);       // windows ending at 0, 1
                 atomicAdd(&hist4[pack4(s0)], 1u);                                // windows ending at 2, 3
@@ -166,11 +170,7 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
                              (((((f2 >> 2) * 0x00204081u) >> 21) & 0xFu) << 8) | (((((f3 >> 2) * 0x00204081u) >> 21) & 0xFu) << 12);
                 }
             } else {
-                // ---- generic path: every position on its own ----
-                uint8_t c[19];
-                c[0] = (uint8_t)(hw >> 8); c[1] = (uint8_t)(hw >> 16); c[2] = (uint8_t)(hw >> 24);
-#pragma unroll
-                for (int j = 0; j < 4; j++) { c[3 + 4 * j] = (uint8_t)w[j]; c[4 + 4 * j] = (uint8_t)(w[j] >> 8); c[5 + 4 * j] = (uint8_t)(w[j] >> 16); c[6 + 4 * j] = (uint8_t)(w[j] >> 24); }
+                // ---- generic path: exact flags per byte, windows from SWAR codes ----
                 // upper-case base flags (bit 7 per byte) and newline flags of the four words, exactly
                 uint32_t bf[4], nf[4], anyb = 0, anyn = 0;
 #pragma unroll
@@ -183,9 +183,9 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
                 if (anyn) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) nlmask |= ((((nf[j] >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * j);
-                    if (p0 + TNC_BPT > n) nlmask &= (1u << (n - p0)) - 1u;
+                    if (!INTERIOR && p0 + TNC_BPT > n) nlmask &= (1u << (n - p0)) - 1u;
                 }
-                if (!anyb) atomicAdd(&seg_nobase[p0 >> TNC_SEG_SHIFT], 1u);
+                if (!anyb) nobase = true;
                 else {
                     // base flags of positions -2 .. 15 as a bit mask (bit i+2 <-> position i); a window ends where three in a row are set
                     const uint32_t hz = zero_bytes_mask(not_acgtnl(hw, symbols(hw))) & (hw << 1);
@@ -193,21 +193,35 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
 #pragma unroll
                     for (int j = 0; j < 4; j++) bm |= ((((bf[j] >> 7) * 0x00204081u) >> 21) & 0xFu) << (2 + 4 * j);
                     uint32_t win = bm & (bm >> 1) & (bm >> 2);                                        // bit i: window ending at position i
-                    if (p0 + TNC_BPT > n) win &= (1u << (n - p0)) - 1u;
-                    while (win) {
-                        const int i = __ffs(win) - 1; win &= win - 1;
-                        atomicAdd(&hist3[16 * ref_code(c[i + 1]) + 4 * ref_code(c[i + 2]) + ref_code(c[i + 3])], 1u);
+                    if (!INTERIOR && p0 + TNC_BPT > n) win &= (1u << (n - p0)) - 1u;
+                    if (win) {
+                        // reference codes (A 0, C 1, G 2, T 3) of every byte, then per byte the index 16 r[i-2] + 4 r[i-1] + r[i] of the window that ends there
+                        auto codes = [](uint32_t x) { const uint32_t sy = (x >> 1) & 0x03030303u; return sy ^ ((sy >> 1) & 0x01010101u); };
+                        auto index = [](uint32_t prev, uint32_t cur) { return cur + 4u * __funnelshift_r(prev, cur, 24) + 16u * __funnelshift_r(prev, cur, 16); };
+                        const uint32_t rh = codes(hw), r0 = codes(w[0]), r1 = codes(w[1]), r2 = codes(w[2]), r3 = codes(w[3]);
+                        const uint32_t xw[4] = {index(rh, r0), index(r0, r1), index(r1, r2), index(r2, r3)};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            uint32_t wj = (win >> (4 * j)) & 0xFu;
+                            while (wj) { const int k = __ffs(wj) - 1; wj &= wj - 1; atomicAdd(&hist3[(xw[j] >> (8 * k)) & 63u], 1u); }
+                        }
                     }
                 }
             }
-            if (chunk == 0) {
+            if (!INTERIOR && chunk == 0) {
                 // newlines that close the halo of the piece (positions -2 and -1) are handled right here
                 if (st.prev[1] == '\n') handle_newline(b, (long)n, st, -2, hist3, exc_count, exc, exc_cap);
                 if (st.prev[2] == '\n') handle_newline(b, (long)n, st, -1, hist3, exc_count, exc, exc_cap);
             }
         }
+        {   // chunks without an upper-case base, counted per 4 KiB segment: the 32 chunks of a warp step lie in one segment -> one atomic
+            const unsigned nb = __ballot_sync(0xffffffffu, nobase);
+            if (nb && lane == 0) atomicAdd(&seg_nobase[((cbase + (size_t)sub * 32) * TNC_BPT) >> TNC_SEG_SHIFT], (uint32_t)__popc(nb));
+        }
         nl64 |= (unsigned long long)nlmask << (16 * sub);
       }
+      };
+      if (cbase > 0 && (cbase + (size_t)TNC_SUB * 32) * TNC_BPT <= n) warp_step(std::true_type{}); else warp_step(std::false_type{});
         // ---- queue the newline positions of this warp iteration, drain 32 at a time ----
         const unsigned has_nl = __ballot_sync(0xffffffffu, nl64 != 0ull);
         if (has_nl) {
