@@ -299,8 +299,8 @@ __global__ void outlen_kernel(const uint32_t *__restrict__ perm, const unsigned 
         len[o] = (unsigned long long)d.len + d.add_nl;
         desc[o] = d;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, mine);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_owned, (unsigned long long)__popc(m));
+    const int cnt = __syncthreads_count(mine);          // one atomic per block: a million per-warp atomics on one address cost more than the gather
+    if (threadIdx.x == 0 && cnt) atomicAdd(n_owned, (unsigned long long)cnt);
 }
 
 __global__ void ordoff_kernel(const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ out_off, size_t K, unsigned long long *__restrict__ ord_off)
