@@ -987,21 +987,23 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         // Every slice is one block, and a block lives as long as its group is long: more slices than the device holds at once means a second
         // round of blocks behind the first (a shard far down the stream has windows several times as wide as the first one's).  Longer groups
         // need fewer slices and less work, at the price of a longer lone-walker tail: the shortest group length whose slices are all resident.
+        size_t resident = (size_t)sp->p1_resident;
+        if (const char *e = getenv("SSB_P1_RESIDENT")) { if (atoi(e) >= 1) resident = (size_t)atoi(e); }          // (tests: a device that holds only a few blocks)
         auto choose_geometry = [&](double centre, double var0, bool exact_entry) {
             static const int num[] = {2, 3, 4, 6, 8, 12, 16, 24, 32};       // group length in halves of the base length
             if (!wt_fixed) wt = 16384;
             for (size_t i = 0; i < sizeof num / sizeof num[0]; i++) {
                 if (!Rg_fixed) { Rg = Rg0 * num[i] / 2; if (Rg < 1) Rg = 1; }
                 make_geometry(centre, var0, exact_entry);
-                if (Rg_fixed || h_slices.size() <= (size_t)sp->p1_resident || Rg >= P) break;
+                if (Rg_fixed || h_slices.size() <= resident || Rg >= P) break;
             }
             // ... and the narrowest slices that still fit: the same work in more blocks keeps more warps in flight in the long tail of a group
             // (C2, one B200: 16384 offsets per slice 12.2 ms, 12288 11.7, 10240 10.9)
-            if (!wt_fixed && h_slices.size() <= (size_t)sp->p1_resident) {
+            if (!wt_fixed && h_slices.size() <= resident) {
                 for (uint32_t w = wt - 1024; w >= 4096; w -= 1024) {
                     const uint32_t keep = wt;
                     wt = w; make_geometry(centre, var0, exact_entry);
-                    if (h_slices.size() > (size_t)sp->p1_resident) { wt = keep; make_geometry(centre, var0, exact_entry); break; }
+                    if (h_slices.size() > resident) { wt = keep; make_geometry(centre, var0, exact_entry); break; }
                 }
             }
         };

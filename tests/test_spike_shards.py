@@ -167,6 +167,23 @@ def test_shards_with_window_maps(name, count, chunk, group, slice_, tmp_path, ct
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,count,chunk,resident", [("plain", 3, 96, 2), ("mask_n_ref", 4, 128, 3), ("deep_lowvaf", 2, 64, 1)])
+def test_shards_with_geometry_fitted_to_a_small_device(name, count, chunk, resident, tmp_path, ctx, monkeypatch):
+    """A shard behind the first has windows several times as wide as the first one's; when their slices would not all be resident it takes
+    longer groups.  A "device" of one to three blocks makes the small inputs take that path in every shard."""
+    prefix = sc.generate(name, str(tmp_path))
+    hdr, body, names, seqs, targets = _load(prefix)
+    with sp.Spike(ctx, names, seqs) as s:
+        out1, res1, st1 = s.run_host(body, targets, 434)
+    monkeypatch.setenv("SSB_CHAIN_CHUNK", str(chunk))
+    monkeypatch.setenv("SSB_P1_RESIDENT", str(resident))
+    out, res, sts, se, n = sp.run_sharded([ctx], names, seqs, body, targets, 434, count, 600)
+    assert out == out1
+    assert [_res_key(r) for r in res] == [_res_key(r) for r in res1]
+    assert any(s_.chain_mode > 1 for s_ in sts[1:]), "expected a shard behind the first to use the window maps"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,shards", [("plain", 2), ("overlap_heavy", 4), ("two_contigs_window", 4), ("mask_n_ref", 3)])
 def test_cli_shards_match_reference_binary(name, shards, tmp_path, ctx):
     """The drop-in main with SSB_SHARDS=N (N logical shards on the devices at hand) against the reference binary: same SAM, same
