@@ -53,7 +53,17 @@ struct ContigNames {          // device: concatenated names + offsets, for RNAME
     unsigned long long keep_lo; unsigned long long *n_keep;
     unsigned long long *n_float;      // lines flagged REC_AUX_F
     unsigned long long *max_end;      // largest end coordinate of a kept line (the output-order sort packs its keys with it)
+    // per line, next to the record: kept? and the sortedness key of a pushed read ((tid + 1) << 32 | pos, 0 otherwise) -- what the
+    // compaction scans need, so that nobody has to read the 64-byte records again just for two fields
+    uint32_t *keep_flag; unsigned long long *pkey;
 };
+
+__device__ __forceinline__ void line_keys(const ContigNames &names, unsigned long long g, const SamRec &r)
+{
+    names.keep_flag[g] = (r.bits & REC_KEEP) ? 1u : 0u;
+    // bam_plp_push compares (tid, pos) of every pushed read with the running maximum
+    names.pkey[g] = (r.bits & REC_PUSHED) ? (((unsigned long long)(uint32_t)(r.tid + 1) << 32) | (uint32_t)r.pos) : 0ull;
+}
 
 // applies the shard's lower bound to a parsed record
 __device__ __forceinline__ void shard_keep(SamRec &r, const ContigNames &names)
@@ -1099,7 +1109,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (r2.bits & REC_KEEP) { atomicAdd(names.n_keep, 1ull); if (r2.end > end_max) end_max = r2.end; }
             if (r2.bits & REC_AUX_F) atomicAdd(names.n_float, 1ull);
             const unsigned long long g2 = gbase + i;
-            if (g2 < rec_cap) recs[g2] = r2;
+            if (g2 < rec_cap) { recs[g2] = r2; line_keys(names, g2, r2); }
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = s;
         }
         bool in_win = false; int32_t w_lo = 0; int wtid = -1;
@@ -1147,7 +1157,7 @@ parse_kernel(const uint8_t *__restrict__ body, size_t n, ContigNames names, SamR
             if (rc) { if (atomicCAS(&err->code, 0, rc) == 0) err->where = ls; memset(&r, 0, sizeof r); r.line_off = ls; r.tid = -1; }
             shard_keep(r, names);
             if ((r.bits & REC_KEEP) && r.end > end_max) end_max = r.end;
-            if (gi < rec_cap) recs[gi] = r;
+            if (gi < rec_cap) { recs[gi] = r; line_keys(names, gi, r); }
             else if (atomicCAS(&err->code, 0, SSB_E_NOMEM) == 0) err->where = ls;
         }
         {   // kept lines of this tile: one atomic per warp

@@ -60,18 +60,8 @@ __device__ __forceinline__ void owned_span(const Range &r, int tid, int64_t &x_l
 }
 
 // ------------------------------------------------------------------------------------------
-// keep flags / sortedness keys
+// compaction of the kept lines (keep flags and sortedness keys come from the tokeniser, sam_parse.cuh:line_keys)
 // ------------------------------------------------------------------------------------------
-__global__ void flags_kernel(const SamRec *__restrict__ recs, size_t n, uint32_t *__restrict__ keep, unsigned long long *__restrict__ pkey)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t bits = recs[i].bits;
-    keep[i] = (bits & REC_KEEP) ? 1u : 0u;
-    // bam_plp_push compares (tid, pos) of every pushed read with the running maximum
-    pkey[i] = (bits & REC_PUSHED) ? (((unsigned long long)(uint32_t)(recs[i].tid + 1) << 32) | (uint32_t)recs[i].pos) : 0ull;
-}
-
 // per output line: where it comes from (one 16-byte load in the emit kernel instead of a chain of dependent loads)
 struct __align__(16) EmitDesc { unsigned long long src_off; uint32_t len; uint32_t add_nl; };
 

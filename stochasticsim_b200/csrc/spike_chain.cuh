@@ -14,12 +14,14 @@
 //                 which draws end their locus; the run of trailing ones advances both cursors, a zero starts
 //                 the "repeat draw" loop of that locus.  ~4 loci per iteration.
 //   phase 1       the walk is a monotone map k_in -> k_out per stretch of loci, and walkers that meet stay
-//                 together.  Chunks are taken in groups; for a group EVERY start offset of a +-5 sigma window
+//                 together.  Chunks are taken in groups; for a group EVERY start offset of a +-4 sigma window
 //                 around the expected offset (mean 4/3 draw per GCAT locus, variance 4/9) is simulated, and
 //                 duplicates are dropped at geometrically spaced checkpoints: W walkers shrink like W/sqrt(loci),
 //                 so a group of length L costs ~2 W sqrt(L) walker-loci instead of W L -- the longer the group the
-//                 less work per locus.  The window is cut into slices (one block each) to keep the GPU full, and
-//                 the survivors at every chunk end inside the group are recorded.  Targets are dry-run per walker.
+//                 less work per locus.  The window is cut into slices (one block each; the host sizes groups and
+//                 slices so that all blocks are resident at once), and the survivors at every chunk end inside the
+//                 group are recorded.  A walker step resolves up to six "draw ends nothing" conflicts per set of
+//                 loads (walk_seg).  Targets are dry-run per walker.
 //   phase 2       one warp composes the group maps in order (a table lookup per group); then every chunk looks up
 //                 its exact start offset in its group's recorded survivors.
 //   phase 3       one warp per chunk repeats the walk from its exact offset and applies the targets for real

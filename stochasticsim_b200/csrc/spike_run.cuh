@@ -480,7 +480,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
 
     // ---------------------------------------------------------------- parse
     size_t N = 0, K = 0;
-    SamRec *recs = NULL;
+    SamRec *recs = NULL; uint32_t *keep = NULL; unsigned long long *pkey = NULL;      // per line: the record, kept?, sortedness key (written by the tokeniser)
     unsigned long long *exc_list = NULL, exc_cap = 0, n_list = 0;
     const bool no_list = getenv("SSB_NO_EXC_LIST") != NULL;
     if (n) {
@@ -492,12 +492,12 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         exc_list = ar.get<unsigned long long>(exc_cap); SPK_CHECK_ARENA(ar);
         SSB_CUDA(ctx, cudaFuncSetAttribute(samparse::parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, samparse::SMEM_BYTES));
         for (int attempt = 0; attempt < 2; attempt++) {
-            recs = ar.get<SamRec>(rec_cap); SPK_CHECK_ARENA(ar);
+            recs = ar.get<SamRec>(rec_cap); keep = ar.get<uint32_t>(rec_cap); pkey = ar.get<unsigned long long>(rec_cap); SPK_CHECK_ARENA(ar);
             SSB_CUDA(ctx, cudaMemsetAsync(tile_state, 0, n_tiles * sizeof(unsigned long long), s));
             SSB_CUDA(ctx, cudaMemsetAsync(ticket, 0, sizeof(unsigned int), s));
             if (attempt) { SSB_CUDA(ctx, cudaMemsetAsync(dsc, 0, sizeof(RunScalars), s)); SSB_CUDA(ctx, cudaMemsetAsync(&dsc->first_strad, 0xff, sizeof(unsigned long long), s)); }
             samparse::ContigNames names{sp->d_names, sp->d_name_off, sp->n_contigs, (const uint8_t *const *)sp->d_seq_ptrs, sp->d_lens,
-                                        no_list ? NULL : exc_list, &dsc->exc_count, exc_cap, rg.lo, &dsc->n_keep, &dsc->n_float, &dsc->max_end};
+                                        no_list ? NULL : exc_list, &dsc->exc_count, exc_cap, rg.lo, &dsc->n_keep, &dsc->n_float, &dsc->max_end, keep, pkey};
             int occ = 1;
             SSB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, samparse::parse_kernel, samparse::THREADS, samparse::SMEM_BYTES));
             if (occ < 1) occ = 1;
@@ -519,17 +519,16 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
     dbg_mark("parsed");
 
     // ---------------------------------------------------------------- keep / sortedness / compaction
-    uint32_t *keep = NULL, *kord = NULL;
+    uint32_t *kord = NULL;
     uint32_t *k_rec = NULL, *nxt = NULL, *prv = NULL; EmitDesc *k_desc = NULL; uint8_t *cplx = NULL, *k_bits = NULL;
     unsigned long long *k_start = NULL, *k_end = NULL, *k_hash = NULL; uint32_t *k_hash32 = NULL;
     unsigned long long *d_halo_lines = &dsc->halo_lines;
     if (N) {
-        keep = ar.get<uint32_t>(N); kord = ar.get<uint32_t>(N);
-        unsigned long long *pkey = ar.get<unsigned long long>(N), *pmax = ar.get<unsigned long long>(N);
+        kord = ar.get<uint32_t>(N);
+        unsigned long long *pmax = ar.get<unsigned long long>(N);
         k_rec = ar.get<uint32_t>(K); k_desc = ar.get<EmitDesc>(K); nxt = ar.get<uint32_t>(K);
         k_start = ar.get<unsigned long long>(K); k_end = ar.get<unsigned long long>(K); k_hash = ar.get<unsigned long long>(K); k_hash32 = ar.get<uint32_t>(K); k_bits = ar.get<uint8_t>(K);
         SPK_CHECK_ARENA(ar);
-        SSB_LAUNCH_P(ctx, SSB_K_SPIKE_OTHER, flags_kernel, grid_for(N, 256), 256, 0, s, recs, N, keep, pkey);
         int rc;
         if ((rc = scan_sum(ar, ctx, keep, kord, N))) return rc;
         if ((rc = scan_max_excl(ar, ctx, pkey, pmax, N, 0ull))) return rc;
