@@ -625,11 +625,12 @@ __device__ __forceinline__ uint32_t udec_conv(const uint8_t *L, uint32_t &p, uin
         const uint32_t c = L[p];
         if (c == '\t') break;
         const uint32_t d = c - '0';
-        bad |= (uint32_t)(d > 9u) | (uint32_t)(v > 214748364u) | (uint32_t)(v == 214748364u && d > 7u);
+        bad |= (uint32_t)(d > 9u);
         v = v * 10u + d;
         p++;
     }
-    bad |= (uint32_t)(p >= len) | (uint32_t)(p == p0) | (uint32_t)(p - p0 > 10u) | (uint32_t)(v > maxv);
+    // up to nine digits cannot overflow; a longer field (a position beyond 999,999,999) is left to the careful parser, which checks the range digit by digit
+    bad |= (uint32_t)(p >= len) | (uint32_t)(p == p0) | (uint32_t)(p - p0 > 9u) | (uint32_t)(v > maxv);
     bad |= (uint32_t)(p - p0 > 1u && L[p0] == '0');
     out = v;
     return bad;
@@ -674,7 +675,7 @@ __device__ __forceinline__ uint32_t parse_head_conv(const Cursor &cur, const uin
         const uint32_t c = L[p];
         if (c == '\t') break;
         const uint32_t d = c - '0';
-        if (d <= 9u) { if (!nd) first = c; num = num * 10u + d; nd++; bad |= (uint32_t)(nd > 9u) | (uint32_t)(num > 0x0fffffffu); }
+        if (d <= 9u) { if (!nd) first = c; num = num * 10u + d; nd++; bad |= (uint32_t)(nd > 8u); }           // (eight digits < 2^28; longer: the careful parser decides)
         else {
             bad |= (uint32_t)(!nd) | (uint32_t)(nd > 1u && first == '0');
             const bool m = c == 'M' || c == '=' || c == 'X', dn = c == 'D' || c == 'N', is = c == 'I' || c == 'S', hp = c == 'H' || c == 'P';
