@@ -1099,7 +1099,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             }
             // ---- compose from the exact offset, chunk boundaries, phase 3.  A walker that leaves its group's window is walked through
             //      that group again on its own (one block, exact entry), and the composition is repeated.
-            bool ok = false, restart = false;
+            bool restart = false;
             for (int retry = 0; retry <= SPARE; retry++) {
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, G, d_groups, d_lists, Rg, pool_k, pool_lo, d_kin, d_gk, &dsc->k_end, d_flags, dsc->miss);
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, boundary_kernel, (P + 127) / 128, 128, 0, s, P, Rg, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_chunks, d_flags);
@@ -1127,15 +1127,12 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                     if ((rc = reset_state())) return rc;
                     SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, p1k, 1, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
                                  d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, (unsigned long long *)NULL, (int)(n_slices + retry));
-                    stats->n_runs += 0;
                     n_retries++;
                     continue;
                 }
-                ok = true;
                 break;
             }
             if (restart) { stream_extra = stream_extra ? stream_extra * 2 : (unsigned long long)(M_abs - k_base); continue; }
-            (void)ok;
             if (hsc->flags & CHAIN_OVERRUN) { stream_extra = stream_extra ? stream_extra * 2 : (unsigned long long)(M_abs - k_base); continue; }
             if (hsc->flags || hsc->n_odd) { parallel = false; continue; }                          // too complex / odd patches (or misses without end): the plain serial chain decides
             k_out_final = is_last ? hsc->draws : hsc->k_end;
@@ -1672,9 +1669,10 @@ extern "C" int ssb_spike_seq_errors(ssb_spike *sp, ssb_seq_error *dst, size_t ca
 }
 
 // test hook (host only): the optional-field check of the tokeniser on one TAG:TYPE:VALUE text
+namespace { struct HostBytes { const char *p; __host__ __device__ uint8_t operator()(size_t i) const { return (uint8_t)p[i]; } }; }
 extern "C" int ssb_test_aux_ok(const char *field, size_t n)
 {
-    auto at = [=](size_t i) -> uint8_t { return (uint8_t)field[i]; };
+    const HostBytes at{field};
     const int rc = samparse::aux_ok_t(at, (size_t)0, n);
     return rc == samparse::AUX_FLOAT ? samparse::aux_float_ok_t(at, (size_t)0, n) : rc;
 }
