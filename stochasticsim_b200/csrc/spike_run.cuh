@@ -985,7 +985,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
         };
         // Every slice is one block, and a block lives as long as its group is long: more slices than the device holds at once means a second
         // round of blocks behind the first (a shard far down the stream has windows several times as wide as the first one's).  Longer groups
-        // need fewer slices and less work, at the price of a longer lone-walker tail: the shortest group length whose slices are all resident.
+        // need fewer slices and less work, at the price of a longer lone-walker tail: the shortest group length whose slices (at their widest) fill at most 85 % of the device.
         size_t resident = (size_t)sp->p1_resident;
         if (const char *e = getenv("SSB_P1_RESIDENT")) { if (atoi(e) >= 1) resident = (size_t)atoi(e); }          // (tests: a device that holds only a few blocks)
         auto choose_geometry = [&](double centre, double var0, bool exact_entry) {
@@ -994,7 +994,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             for (size_t i = 0; i < sizeof num / sizeof num[0]; i++) {
                 if (!Rg_fixed) { Rg = Rg0 * num[i] / 2; if (Rg < 1) Rg = 1; }
                 make_geometry(centre, var0, exact_entry);
-                if (Rg_fixed || h_slices.size() <= resident || Rg >= P) break;
+                if (Rg_fixed || h_slices.size() * 20 <= resident * 17 || Rg >= P) break;     // 85 %: room to narrow the slices below (tools/sweep_late_shard.sh)
             }
             // ... and the narrowest slices that still fit: the same work in more blocks keeps more warps in flight in the long tail of a group
             // (C2, one B200: 16384 offsets per slice 12.2 ms, 12288 11.7, 10240 10.9)
@@ -1028,7 +1028,9 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 break;
             }
             const bool exact_entry = k_in_known;
-            choose_geometry(exact_entry ? (double)k_in : c_in, exact_entry ? 0.0 : v_in, exact_entry);
+            double v_extra = 0.0;                               // SSB_CHAIN_EXTRA_VAR: widen the windows as if that many draws' variance lay in front (measurement: a late shard's phase 1 on one GPU)
+            if (const char *e = getenv("SSB_CHAIN_EXTRA_VAR")) { const double v = atof(e); if (v > 0) v_extra = v; }
+            choose_geometry(exact_entry ? (double)k_in : c_in, (exact_entry ? 0.0 : v_in) + v_extra, exact_entry);
             const size_t n_slices = h_slices.size();
             const unsigned long long pool_cap = woff + (1ull << 20);
             // the stream must cover the top of the last window (and everything a lone walker can reach)
