@@ -109,7 +109,7 @@ __device__ __forceinline__ void handle_newline(const uint8_t *__restrict__ b, lo
 }
 
 __global__ void __launch_bounds__(TNC_BLOCK)
-tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__restrict__ st_in,
+tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__restrict__ st_in, const uint8_t *__restrict__ prev3,
                 unsigned long long *__restrict__ counts, uint32_t *__restrict__ exc_count,
                 uint32_t *__restrict__ exc, uint32_t exc_cap, uint32_t *__restrict__ seg_nobase)
 {
@@ -120,7 +120,11 @@ tnc_scan_kernel(const uint8_t *__restrict__ b, size_t n, const TncDevState *__re
     for (int i = threadIdx.x; i < TNC_BINS; i += TNC_BLOCK) hist4[i] = 0;
     if (threadIdx.x < 64) hist3[threadIdx.x] = 0;
     __syncthreads();
-    TncDevState st = *st_in;
+    // The scan needs only the three bytes in front of the piece from the state; for a piece behind another one in the same buffer they are
+    // read from there (prev3), so that it need not wait for the previous piece's fix-up kernel, which is what writes the state.
+    TncDevState st;
+    if (prev3) { st.started = 1; st.prev[0] = prev3[0]; st.prev[1] = prev3[1]; st.prev[2] = prev3[2]; st.carry = 0; st.frag_nonempty = 0; st.frag_first = 0; st.frag_has_base = 0; }
+    else st = *st_in;
     if (!st.started) { st.prev[0] = st.prev[1] = st.prev[2] = '\n'; }                 // start of file behaves like "\n\n\n"
     uint32_t qn = 0;                                                                   // entries in this warp's newline queue (warp uniform)
     uint32_t *q = nlq[wid];
@@ -456,12 +460,13 @@ struct TncScratch {
     uint32_t            exc_cap;
     uint32_t           *seg;         // per 4 KiB segment: number of 16-byte chunks without an upper-case base
     size_t              seg_words;
+    uint32_t           *exc_count2, *exc2, *seg2;   // second set (device-resident runs: piece i+1 is scanned while piece i is fixed up); NULL otherwise
     uint8_t            *tail;        // first byte after the scratch arrays (256-byte aligned)
 };
 
 size_t tnc_exc_cap(size_t piece_bytes) { return piece_bytes / 16 + (1u << 16); }
 
-int tnc_scratch(ssb_ctx *ctx, size_t piece_bytes, size_t extra_bytes, TncScratch *s)
+int tnc_scratch(ssb_ctx *ctx, size_t piece_bytes, size_t extra_bytes, TncScratch *s, bool two_sets = false)
 {
     size_t cap = tnc_exc_cap(piece_bytes);
     size_t seg_words = (piece_bytes >> TNC_SEG_SHIFT) + 2;
@@ -470,6 +475,10 @@ int tnc_scratch(ssb_ctx *ctx, size_t piece_bytes, size_t extra_bytes, TncScratch
     const size_t seg_off = head;
     head += seg_words * sizeof(uint32_t);
     head = (head + 255) & ~(size_t)255;
+    const size_t exc2_off = head;
+    if (two_sets) { head += cap * sizeof(uint32_t); head = (head + 255) & ~(size_t)255; }
+    const size_t seg2_off = head;
+    if (two_sets) { head += seg_words * sizeof(uint32_t); head = (head + 255) & ~(size_t)255; }
     int r = ssb_scratch_reserve(ctx, head + extra_bytes);
     if (r) return r;
     uint8_t *base = (uint8_t *)ctx->scratch;
@@ -482,6 +491,9 @@ int tnc_scratch(ssb_ctx *ctx, size_t piece_bytes, size_t extra_bytes, TncScratch
     s->exc_cap = (uint32_t)cap;
     s->seg = (uint32_t *)(base + seg_off);
     s->seg_words = seg_words;
+    s->exc_count2 = two_sets ? (uint32_t *)(base + 136) : NULL;      // (inside the range tnc_begin clears)
+    s->exc2 = two_sets ? (uint32_t *)(base + exc2_off) : NULL;
+    s->seg2 = two_sets ? (uint32_t *)(base + seg2_off) : NULL;
     s->tail = base + head;
     return SSB_OK;
 }
@@ -503,7 +515,7 @@ int tnc_piece(ssb_ctx *ctx, cudaStream_t stream, const uint8_t *d, size_t n, con
     int max_grid = ctx->sm_count * 8;            // persistent: every block folds its 1296-bin histogram once
     if (grid > max_grid) grid = max_grid;
     if (grid < 1) grid = 1;
-    SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, s.acc, s.exc_count, s.exc, s.exc_cap, s.seg);
+    SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, stream, d, n, st_in, (const uint8_t *)NULL, s.acc, s.exc_count, s.exc, s.exc_cap, s.seg);
     int fgrid = ctx->sm_count * 4;
     SSB_LAUNCH_P(ctx, SSB_K_TNC_FIXUP, tnc_fixup_kernel, fgrid, 128, 0, stream, d, n, st_in, st_out, s.acc, s.exc_count, s.ovf, s.exc, s.exc_cap, s.seg);
     return SSB_OK;
@@ -517,18 +529,41 @@ int tnc_begin(ssb_ctx *ctx, cudaStream_t stream, const TncScratch &s, const ssb_
     return SSB_OK;
 }
 
-// Device-resident buffer of any size, cut into pieces of at most `piece` bytes.
+// Device-resident buffer of any size, cut into pieces of at most `piece` bytes.  The scan of piece i+1 does not depend on the fix-up of piece i
+// (see tnc_scan_kernel: prev3), so the scans run back to back on the compute stream and the fix-ups, which carry the state from piece to piece,
+// follow on the second stream; two sets of exception lists alternate.
 int tnc_run_device(ssb_ctx *ctx, const uint8_t *d, size_t n, size_t piece, const TncScratch &s, int *cur_io)
 {
     int cur = *cur_io;
     size_t off = 0;
+    cudaStream_t sS = ctx->stream, sF = s.exc2 ? ctx->copy_stream : ctx->stream;
+    int i = 0;
     do {
-        size_t len = n - off < piece ? n - off : piece;
-        int r = tnc_piece(ctx, ctx->stream, d + off, len, s, s.st[cur], s.st[cur ^ 1]);
-        if (r) return r;
+        const size_t len = n - off < piece ? n - off : piece;
+        const int k = s.exc2 ? (i & 1) : 0;
+        uint32_t *exc_count = k ? s.exc_count2 : s.exc_count, *exc = k ? s.exc2 : s.exc, *seg = k ? s.seg2 : s.seg;
+        if (s.exc2 && i >= 2) SSB_CUDA(ctx, cudaStreamWaitEvent(sS, ctx->ev[2 + k], 0));           // set k: fixed up and free again
+        SSB_CUDA(ctx, cudaMemsetAsync(exc_count, 0, sizeof(uint32_t), sS));
+        SSB_CUDA(ctx, cudaMemsetAsync(seg, 0, ((len >> TNC_SEG_SHIFT) + 2) * sizeof(uint32_t), sS));
+        const size_t n_chunks = (len + TNC_BPT - 1) / TNC_BPT;
+        int grid = (int)((n_chunks + (size_t)TNC_BLOCK * TNC_SUB - 1) / ((size_t)TNC_BLOCK * TNC_SUB));
+        const int max_grid = ctx->sm_count * 8;            // persistent: every block folds its 1296-bin histogram once
+        if (grid > max_grid) grid = max_grid;
+        if (grid < 1) grid = 1;
+        const uint8_t *prev3 = (s.exc2 && off >= 3) ? d + off - 3 : NULL;
+        if (s.exc2 && !prev3 && i > 0) SSB_CUDA(ctx, cudaStreamWaitEvent(sS, ctx->ev[2 + ((i - 1) & 1)], 0));  // (cannot happen with pieces of >= 32 bytes: the state itself)
+        SSB_LAUNCH_P(ctx, SSB_K_TNC_SCAN, tnc_scan_kernel, grid, TNC_BLOCK, 0, sS, d + off, len, s.st[cur], prev3, s.acc, exc_count, exc, s.exc_cap, seg);
+        if (s.exc2) { SSB_CUDA(ctx, cudaEventRecord(ctx->ev[k], sS)); SSB_CUDA(ctx, cudaStreamWaitEvent(sF, ctx->ev[k], 0)); }
+        SSB_LAUNCH_P(ctx, SSB_K_TNC_FIXUP, tnc_fixup_kernel, ctx->sm_count * 4, 128, 0, sF, d + off, len, s.st[cur], s.st[cur ^ 1], s.acc, exc_count, s.ovf, exc, s.exc_cap, seg);
+        if (s.exc2) SSB_CUDA(ctx, cudaEventRecord(ctx->ev[2 + k], sF));
         cur ^= 1;
         off += len;
+        i++;
     } while (off < n);
+    if (s.exc2) {                                           // the compute stream goes on when the last fix-ups are done
+        SSB_CUDA(ctx, cudaStreamWaitEvent(sS, ctx->ev[2 + ((i - 1) & 1)], 0));
+        if (i >= 2) SSB_CUDA(ctx, cudaStreamWaitEvent(sS, ctx->ev[2 + (i & 1)], 0));
+    }
     *cur_io = cur;
     return SSB_OK;
 }
@@ -544,9 +579,10 @@ extern "C" int ssb_tnc_count_device(ssb_ctx *ctx, const uint8_t *d_fasta, size_t
     if (((uintptr_t)d_fasta & 15) != 0) return SSB_E_ARG;          // 16-byte vector loads
     SSB_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t piece = n < TNC_MAX_PIECE ? n : TNC_MAX_PIECE;
+    if (const char *e = getenv("SSB_TNC_PIECE")) { const size_t v = strtoull(e, NULL, 10) & ~(size_t)15; if (v >= 32 && v < piece) piece = v; }     // (tests: many pieces on a small input)
     for (int attempt = 0; attempt < 2; attempt++) {
         TncScratch s;
-        int r = tnc_scratch(ctx, piece, 0, &s);
+        int r = tnc_scratch(ctx, piece, 0, &s, n > piece);       // several pieces: two sets, the scans run ahead of the fix-ups
         if (r) return r;
         // attempt 1 (after an overflow): pieces so small that the list holds their worst case
         size_t use = attempt == 0 ? piece : TNC_SAFE_PIECE;

@@ -83,6 +83,24 @@ def test_fuzz_cut_anywhere(ctx):
         assert np.array_equal(total, want), (data, cuts)
 
 
+def test_device_pieces_scan_ahead_of_fixup(ctx, monkeypatch):
+    """A device-resident FASTA larger than one piece: the scans of the pieces run back to back (each takes the three bytes in front of it
+    from the buffer), the fix-up kernels follow on a second stream and carry the state from piece to piece, two exception lists alternate.
+    Pieces from 32 bytes to 100 kB on inputs with headers, N blocks, lower-case runs and short lines."""
+    rng = random.Random(29)
+    data = fc.genome_like(rng, 400_000, width=60, n_block=(50_000, 71_003), lower_runs=20, contigs=3)
+    want = ob.tnc_counts(data)
+    for piece in (4096, 65_536, 100_000):
+        monkeypatch.setenv("SSB_TNC_PIECE", str(piece))
+        got, carry = gpu_counts_device(ctx, data, want_carry=True)
+        assert np.array_equal(got, want), piece
+        assert carry.as_tuple() == ssb.tnc.carry_after(data).as_tuple(), piece
+    for i in range(60):
+        data = fc.random_fasta(rng, max_lines=60)
+        monkeypatch.setenv("SSB_TNC_PIECE", str(rng.choice([32, 48, 64, 256])))
+        assert np.array_equal(gpu_counts_device(ctx, data), ob.tnc_counts(data)), data
+
+
 def test_host_chunking(ctx, monkeypatch):
     rng = random.Random(23)
     data = fc.genome_like(rng, 400_000, width=60, n_block=(50_000, 71_003), lower_runs=20, contigs=3)
