@@ -446,7 +446,7 @@ __device__ int dry_walk(const ChainArgs &A, const SegPlanes &P, int64_t g, const
 }
 
 // group q = chunks [f0, f0 + nf): one start-offset window [klo, klo + W), cut into S slices of w offsets (blocks b0 ..)
-struct GroupDesc { unsigned long long klo; uint32_t W, w, S, b0; int32_t f0, nf; };
+struct GroupDesc { unsigned long long klo; uint32_t W, w, S, b0; int32_t f0, nf; unsigned long long toff; };   // toff: walker slot of window index 0 (= where the group's entry -> exit table begins)
 struct SliceDesc { int32_t q; uint32_t i0, n; unsigned long long off; };        // window indices [i0, i0 + n); walker slots at off
 // survivors of one slice at the end of one chunk: (lowest window index of the class, draw offset) pairs in `pool`
 struct BoundaryList { unsigned long long off; uint32_t cnt; uint32_t pad; };
@@ -581,34 +581,42 @@ __device__ __forceinline__ bool boundary_lookup(const GroupDesc &gd, int r, unsi
     return true;
 }
 
-// phase 2a: one warp walks the group maps in order from the exact entry offset k_in.  gk[q] = exact draw offset at the start of group q.
+// phase 2a, preparation: the map of a group as a flat table, exit offset per window index (the survivors of a slice at the group's last chunk end
+// are classes of consecutive window indices).  It is written over the walker slots of phase 1, which are free by now: one block per slice.
+__global__ void __launch_bounds__(128)
+map_fill_kernel(const GroupDesc *__restrict__ groups, const SliceDesc *__restrict__ slices, const BoundaryList *__restrict__ lists, int max_nf,
+                const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo, unsigned long long *__restrict__ table, int block0)
+{
+    const unsigned int bx = blockIdx.x + (unsigned int)block0;
+    const SliceDesc sd = slices[bx];
+    const GroupDesc gd = groups[sd.q];
+    const BoundaryList bl = lists[(size_t)bx * max_nf + (gd.nf - 1)];
+    unsigned long long *t = table + sd.off;                        // window index sd.i0 + j <-> t[j]
+    for (uint32_t i = threadIdx.x; i < bl.cnt; i += blockDim.x) {
+        const uint32_t a = pool_lo[bl.off + i] - sd.i0, b = (i + 1 < bl.cnt) ? pool_lo[bl.off + i + 1] - sd.i0 : sd.n;
+        const unsigned long long k = pool_k[bl.off + i];
+        for (uint32_t j = a; j < b; j++) t[j] = k;
+    }
+}
+
+// phase 2a: the exact walker goes through the groups in order from the exact entry offset k_in -- one dependent load per group (the next group's
+// descriptor is fetched while the table answers).  gk[q] = exact draw offset at the start of group q.
 __global__ void __launch_bounds__(32)
-compose_kernel(int G, const GroupDesc *__restrict__ groups, const BoundaryList *__restrict__ lists, int max_nf,
-               const unsigned long long *__restrict__ pool_k, const uint32_t *__restrict__ pool_lo,
+compose_kernel(int G, const GroupDesc *__restrict__ groups, const unsigned long long *__restrict__ table,
                const unsigned long long *__restrict__ k_in, unsigned long long *__restrict__ gk, unsigned long long *__restrict__ k_end, unsigned int *__restrict__ flags,
                unsigned long long *__restrict__ miss /* [0] group whose window the walker missed, [1] its exact entry offset */)
 {
-    const int lane = threadIdx.x;
+    if (threadIdx.x) return;
     unsigned long long k = *k_in;
+    GroupDesc gd = groups[0];
     for (int q = 0; q < G; q++) {
-        const GroupDesc gd = groups[q];
-        if (lane == 0) gk[q] = k;
-        if (k < gd.klo || k - gd.klo >= gd.W) { if (lane == 0) { miss[0] = (unsigned long long)q; miss[1] = k; atomicOr(flags, (unsigned int)CHAIN_MISS); } return; }
-        const uint32_t idx = (uint32_t)(k - gd.klo);
-        uint32_t sl = idx / gd.w; if (sl >= gd.S) sl = gd.S - 1;
-        const BoundaryList bl = lists[(size_t)(gd.b0 + sl) * max_nf + (gd.nf - 1)];
-        const uint32_t *lo = pool_lo + bl.off;
-        uint32_t best = 0;                               // last survivor with lo <= idx
-        for (uint32_t base = 0; base < bl.cnt; base += 32) {
-            const uint32_t i = base + lane;
-            const bool le = i < bl.cnt && lo[i] <= idx;
-            const unsigned m = __ballot_sync(0xffffffffu, le);
-            if (m) best = base + 31 - __clz(m);
-            if (m != 0xffffffffu) break;
-        }
-        k = pool_k[bl.off + best];
+        const GroupDesc nx = groups[q + 1 < G ? q + 1 : q];
+        gk[q] = k;
+        if (k < gd.klo || k - gd.klo >= gd.W) { miss[0] = (unsigned long long)q; miss[1] = k; atomicOr(flags, (unsigned int)CHAIN_MISS); return; }
+        k = table[gd.toff + (k - gd.klo)];
+        gd = nx;
     }
-    if (lane == 0) *k_end = k;
+    *k_end = k;
 }
 
 // A shard that is entered with an offset it does not know yet (its predecessors are still working) prepares the answer:

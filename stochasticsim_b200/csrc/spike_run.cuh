@@ -974,7 +974,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                 double lo = cm - half; if (lo < 0) lo = 0;
                 gd.klo = (unsigned long long)lo; gd.W = one ? 1u : (uint32_t)(cm + half - (double)gd.klo) + 2u;
                 uint32_t S = (gd.W + wt - 1) / wt; gd.w = (gd.W + S - 1) / S; S = (gd.W + gd.w - 1) / gd.w;
-                gd.S = S; gd.b0 = (uint32_t)h_slices.size();
+                gd.S = S; gd.b0 = (uint32_t)h_slices.size(); gd.toff = woff;
                 for (uint32_t sl = 0; sl < S; sl++) {
                     SliceDesc sd; sd.q = q; sd.i0 = sl * gd.w; sd.n = (sd.i0 + gd.w <= gd.W) ? gd.w : gd.W - sd.i0; sd.off = woff; woff += sd.n;
                     h_slices.push_back(sd);
@@ -1066,6 +1066,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, p1k, (int)n_slices, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
                          d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, d_dbg, 0);
             SSB_CUDA(ctx, cudaEventRecord(sp->ev_t[15], s));
+            SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, map_fill_kernel, (int)n_slices, 128, 0, s, d_groups, d_slices, d_lists, Rg, pool_k, pool_lo, kbuf, 0);     // group maps as flat tables (over the walker slots)
             if (d_dbg) {
                 unsigned long long h_dbg[8];
                 SSB_CUDA(ctx, cudaMemcpyAsync(h_dbg, d_dbg, 64, cudaMemcpyDeviceToHost, s));
@@ -1103,7 +1104,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
             //      that group again on its own (one block, exact entry), and the composition is repeated.
             bool restart = false;
             for (int retry = 0; retry <= SPARE; retry++) {
-                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, G, d_groups, d_lists, Rg, pool_k, pool_lo, d_kin, d_gk, &dsc->k_end, d_flags, dsc->miss);
+                SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, compose_kernel, 1, 32, 0, s, G, d_groups, kbuf, d_kin, d_gk, &dsc->k_end, d_flags, dsc->miss);
                 SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, boundary_kernel, (P + 127) / 128, 128, 0, s, P, Rg, d_groups, d_lists, Rg, pool_k, pool_lo, d_gk, d_chunks, d_flags);
                 if ((rc = publish())) return rc;                                                  // did the exact walker stay inside every window?
                 if (!hsc->flags) {
@@ -1117,7 +1118,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                     if (dbg_t) fprintf(stderr, "[chain %d] window of group %d missed (offset %llu, window [%llu, +%u)): walking it alone\n", pl.index, q, km, h_groups[q].klo, h_groups[q].W);
                     if (km < k_base || km + 64 > M_abs) { restart = true; break; }                // outside the generated stream: start over with a longer one
                     GroupDesc gd = h_groups[q];
-                    gd.klo = km; gd.W = 1; gd.w = 1; gd.S = 1; gd.b0 = (uint32_t)(n_slices + retry);
+                    gd.klo = km; gd.W = 1; gd.w = 1; gd.S = 1; gd.b0 = (uint32_t)(n_slices + retry); gd.toff = woff + retry;
                     h_groups[q] = gd;
                     SliceDesc sd; sd.q = q; sd.i0 = 0; sd.n = 1; sd.off = woff + retry;
                     uint8_t *gh = NULL, *gd_ = NULL, *sh_ = NULL, *sd_ = NULL;
@@ -1129,6 +1130,7 @@ int run_shard(ssb_spike *sp, const ShardPlan &pl, const uint8_t *d_sam, size_t n
                     if ((rc = reset_state())) return rc;
                     SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, p1k, 1, P1_THREADS, P1_SMEM, s, A, Lc, d_groups, d_slices, kbuf, lobuf, wstride,
                                  d_lists, Rg, pool_k, pool_lo, d_pool_used, pool_cap, d_flags, (unsigned long long *)NULL, (int)(n_slices + retry));
+                    SSB_LAUNCH_P(ctx, SSB_K_SPIKE_CHAIN, map_fill_kernel, 1, 128, 0, s, d_groups, d_slices, d_lists, Rg, pool_k, pool_lo, kbuf, (int)(n_slices + retry));
                     n_retries++;
                     continue;
                 }
